@@ -1,0 +1,167 @@
+"""CPU: pin oracle/ (the checker) against the reference-generated goldens and the reference's
+own known-answer tests for this path."""
+import numpy as np
+import pytest
+
+from oracle import ewk_oracle as O
+from oracle import librosa_restated as L
+from easywakeword_b200 import synth
+from helpers import detect_stream_for, sha
+
+
+# ---- Appendix A anchors of the restated front-end ---------------------------------------
+def test_mel_filterbank_anchors():
+    M = L.mel_filterbank()
+    assert M.shape == (128, 257) and M.dtype == np.float32
+    assert int((M > 0).sum()) == 504
+    assert np.unravel_index(M.argmax(), M.shape) == (3, 3)
+    assert abs(float(M.max()) - 0.042366076) < 1e-9
+    assert abs(float(L.hz_to_mel(8000.0)) - 45.245640471924965) < 1e-12
+    nnz = (M > 0).sum(axis=1)
+    assert nnz.min() == 1 and nnz.max() == 12
+
+
+def test_mel_and_dct_against_torchaudio():
+    ta = pytest.importorskip("torchaudio")
+    import scipy.fft
+    fb = ta.functional.melscale_fbanks(257, 0.0, 8000.0, 128, 16000, norm="slaney", mel_scale="slaney").T.numpy()
+    assert np.abs(fb - L.mel_filterbank()).max() < 1e-6
+    d = ta.functional.create_dct(20, 128, "ortho").T.numpy()
+    D = scipy.fft.dct(np.eye(128), axis=0, type=2, norm="ortho")[:20]
+    assert np.abs(D - d).max() < 1e-5
+
+
+def test_hann_window():
+    w = L.hann_window(512)
+    assert w[0] == 0 and abs(w[256] - 1) < 1e-15 and abs(w.sum() - 256) < 1e-9 and abs((w ** 2).sum() - 192) < 1e-9
+
+
+def test_bundled_word_anchor(word):
+    assert len(word) == 15503
+    m = L.mfcc(word)
+    assert m.shape == (20, 97) and m.dtype == np.float32
+    np.testing.assert_allclose(m.mean(1)[:4], [-530.33685, 98.579170, -19.178118, 25.856405], rtol=2e-6)
+
+
+# ---- reference known-answer tests (tests/test_wakeword_simulated.py:104-205, 330-360) ----
+@pytest.mark.parametrize("sig", ["sine440", "speech_like"])
+def test_self_similarity_is_exactly_100(sig, golden_matcher):
+    a = golden_matcher[f"in_{sig}"]
+    m = O.WordMatcherOracle()
+    m.set_reference(a)
+    ok, sim = m.matches(a)
+    assert ok and sim == 100.0
+
+
+def test_reference_inequalities(golden_matcher):
+    m = O.WordMatcherOracle()
+    m.set_reference(golden_matcher["in_sine440"])
+    assert m.matches(golden_matcher["in_sine880"])[1] < 100.0
+    assert m.matches(golden_matcher["in_noise42"])[1] < 100.0
+    assert m.matches(golden_matcher["in_sine440_half"])[1] > 50.0
+    # LEARNINGS.md:92-93 doc pins ("89 %+", "77 %+")
+    assert 89.0 < m.matches(golden_matcher["in_sine880"])[1] < 90.5
+    assert 77.0 < m.matches(golden_matcher["in_noise42"])[1] < 79.0
+
+
+def test_no_reference_raises():
+    with pytest.raises(ValueError, match="No reference word set"):
+        O.WordMatcherOracle().calculate_similarity(np.zeros(16000, np.float32))
+
+
+# ---- oracle == reference (goldens written by the reference's classes) ---------------------
+def test_matcher_equals_reference_goldens(golden_matcher, word):
+    g = golden_matcher
+    tpl = {"word": word, "sine440": g["in_sine440"], "speech_like": g["in_speech_like"]}
+    ms = {}
+    for k, a in tpl.items():
+        ms[k] = O.WordMatcherOracle()
+        ms[k].set_reference(a)
+        assert np.array_equal(ms[k].reference_mfcc_mean, g[f"tpl_{k}_mean"])
+        assert np.array_equal(ms[k].reference_mfcc_std, g[f"tpl_{k}_std"])
+    for name in g["names"]:
+        a = g[f"in_{name}"]
+        mean, std = O.extract_mfcc(a)
+        assert np.array_equal(mean, g[f"mean_{name}"], equal_nan=True), name
+        assert np.array_equal(std, g[f"std_{name}"], equal_nan=True), name
+        assert np.array_equal(O.mfcc_frames(a), g[f"mfcc_{name}"]), name
+        assert g[f"mfcc_{name}"].shape == (20, 1 + len(a) // 160)
+        for k in tpl:
+            ok, sim = ms[k].matches(a)
+            assert np.array_equal(np.float64(sim), g[f"score_{k}_{name}"], equal_nan=True), (k, name)
+            assert bool(ok) == bool(g[f"match_{k}_{name}"])
+
+
+def test_detect_equals_reference_goldens(golden_detect, word):
+    g, cases = golden_detect
+    n_events = n_nomatch = 0
+    for c in cases:
+        n = c["name"]
+        s = detect_stream_for(c, word)
+        assert sha(s) == str(g[f"{n}_stream_sha"]), f"synthetic stream for {n} drifted"
+        o = O.detect_stream(s, word, block=c["block"], fast=True, **c["params"])
+        assert o["full_tick"] == int(g[f"{n}_full_tick"])
+        assert o["ticks_run"] == int(g[f"{n}_ticks_run"])
+        assert np.array_equal(o["trace_tick"], g[f"{n}_trace_tick"])
+        assert np.array_equal(o["trace_silent"], g[f"{n}_trace_silent"])
+        assert np.array_equal(o["trace_thr"], g[f"{n}_trace_thr"])
+        assert [e["tick"] for e in o["events"]] == list(g[f"{n}_ev_tick"])
+        assert [e["seg_len"] for e in o["events"]] == list(g[f"{n}_ev_len"])
+        assert np.array_equal(np.array([e["score"] for e in o["events"]]), g[f"{n}_ev_score"])
+        assert [e["matched"] for e in o["events"]] == list(g[f"{n}_ev_match"])
+        assert o["timeouts"] == list(g[f"{n}_timeouts"])
+        n_events += len(o["events"])
+        n_nomatch += sum(not e["matched"] for e in o["events"])
+    assert n_events >= 50 and n_nomatch >= 8
+
+
+def test_config1_expected_events(golden_detect):
+    """ring full at tick 101, one level-2 call at tick 156, 17 600 samples, 99.5034."""
+    g, _ = golden_detect
+    assert int(g["config1_full_tick"]) == 101
+    assert list(g["config1_ev_tick"]) == [156] and list(g["config1_ev_len"]) == [17600]
+    assert abs(float(g["config1_ev_score"][0]) - 99.5034) < 1e-3 and bool(g["config1_ev_match"][0])
+
+
+def test_slow_and_fast_threshold_paths_identical(word):
+    c = dict(seed=2004, seconds=30, noise=0.012, gain=(2.0, 5.0))
+    s = detect_stream_for(c, word)
+    a = O.detect_stream(s, word, block=512, fast=False, max_ticks=200)
+    b = O.detect_stream(s, word, block=512, fast=True, max_ticks=200)
+    assert np.array_equal(a["trace_thr"], b["trace_thr"]) and np.array_equal(a["trace_silent"], b["trace_silent"])
+
+
+def test_dense_equals_reference_goldens(golden_dense, word):
+    g = golden_dense
+    tpls = [word, g["tpl2"]]
+    for si in range(2):
+        x, _ = synth.stream(int(g[f"s{si}_seed"]), 12.0, word, gain=(1.0, 4.0), zero_gaps=int(g[f"s{si}_zero_gaps"]))
+        x = synth.from_int16(synth.to_int16(x))
+        assert sha(x) == str(g[f"s{si}_sha"])
+        hops = g[f"s{si}_hops"][::6]
+        sc = O.dense_scores(x, tpls, hops)
+        np.testing.assert_array_equal(sc.astype(np.float64), g[f"s{si}_scores"][::6])
+
+
+@pytest.mark.needs_reference
+def test_reference_unmodified_matches_oracle_live(word):
+    """Build container only: the reference's own classes (unmodified, on the shim) vs the restatement."""
+    from oracle import ref_harness as H
+    c = dict(seed=4242, seconds=25, noise=0.003, gain=(2.0, 4.0))
+    s = detect_stream_for(c, word)
+    P = dict(speech_duration_min=0.6, speech_duration_max=1.5, timeout=8)
+    r = H.run_reference_stream(s, word, block=512, **P)
+    o = O.detect_stream(s, word, block=512, fast=True, **P)
+    assert np.array_equal(r["trace_silent"], o["trace_silent"]) and np.array_equal(r["trace_thr"], o["trace_thr"])
+    assert [(e["tick"], e["seg_len"], e["score"]) for e in r["events"]] == \
+           [(e["tick"], e["seg_len"], e["score"]) for e in o["events"]]
+    assert r["timeouts"] == o["timeouts"]
+
+
+def test_level3_preprocessing_and_vad(word):
+    y = O.prepare_for_level3(word.astype(np.float64) + 0.01)
+    assert abs(np.max(np.abs(y)) - 1.0) < 1e-12 and abs(np.mean(np.clip(y, -1, 1))) < 0.05
+    assert O.analyze_reference_audio_duration(word) == pytest.approx(0.69)
+    assert O.auto_speech_durations(word) == (pytest.approx(0.69), pytest.approx(1.38))
+    assert O.auto_speech_durations(word, user_min=0.5) == (0.5, 1.0)
+    assert O.auto_speech_durations(np.zeros(100, np.float32)) [1] >= O.auto_speech_durations(np.zeros(100, np.float32))[0] > 0
