@@ -1,0 +1,52 @@
+// Context object behind the opaque ewk_ctx handle of include/ewk.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "ewk_frame.cuh"
+#include "ewk_segment.cuh"
+#include "ewk_tables.hpp"
+
+#define EWK_MAX_TEMPLATES 64
+
+namespace ewk {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void free() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace ewk
+
+struct ewk_ctx {
+    int device = 0;
+    int sm_count = 0;
+    ewk_config cfg{};
+    std::string err;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    ewk::DeviceTables* d_tables = nullptr;
+    ewk::TemplateFeat* d_tmpl = nullptr;
+    std::vector<ewk::TemplateFeat> h_tmpl;
+    ewk::DevBuf b_pcm, b_desc, b_ws, b_feat, b_scores, b_matched, b_frames, b_off;
+
+    void fail(const char* fmt, ...);
+    int init();
+    void release();
+    int init_streams() { return 0; }
+    void release_streams() {}
+    int launch_segments(const ewk::SegDesc* d_segs, int n_seg, int max_frames, long long spill_frames, int n_tmpl,
+                        int tmpl_first, float threshold, float* d_feat, float* d_frames, float* d_scores,
+                        unsigned char* d_matched);
+};
