@@ -182,3 +182,195 @@ class Context:
 
     def synchronize(self):
         self._ck(self.lib.ewk_synchronize(self.h))
+
+
+# ------------------------------------------------------------------------------------------
+# stream bank bindings
+class StreamParams(C.Structure):
+    _fields_ = [("similarity_threshold", C.c_float), ("frame_size", C.c_int32),
+                ("pre_speech_silence", C.c_double), ("speech_duration_min", C.c_double),
+                ("speech_duration_max", C.c_double), ("post_speech_silence", C.c_double),
+                ("timeout", C.c_double), ("min_threshold", C.c_double),
+                ("template_first", C.c_int32), ("template_count", C.c_int32),
+                ("live", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Event(C.Structure):
+    _fields_ = [("stream", C.c_int32), ("kind", C.c_int32), ("tick", C.c_int64), ("seg_start", C.c_int64),
+                ("seg_len", C.c_int32), ("template_slot", C.c_int32), ("score", C.c_float), ("matched", C.c_int32)]
+
+
+class StreamStatus(C.Structure):
+    _fields_ = [("written", C.c_int64), ("visible", C.c_int64), ("tick", C.c_int64),
+                ("silence_threshold", C.c_double), ("last_rms", C.c_double), ("frame_size", C.c_int32),
+                ("state", C.c_int32), ("started", C.c_int32), ("is_silent", C.c_int32),
+                ("n_timeouts", C.c_int32), ("n_events", C.c_int32)]
+
+
+EVENT_DTYPE = np.dtype([("stream", "<i4"), ("kind", "<i4"), ("tick", "<i8"), ("seg_start", "<i8"),
+                        ("seg_len", "<i4"), ("template_slot", "<i4"), ("score", "<f4"), ("matched", "<i4")])
+RESULT_DTYPE = np.dtype([("score", "<f4"), ("flags", "<u4")])
+EV_TIMEOUT, EV_SCORED = 1, 2
+
+
+def _declare_stream_protos(lib):
+    vp, i32, i64, f32p = C.c_void_p, C.c_int, C.c_int64, _p(C.c_float)
+    protos = {
+        "ewk_default_stream_params": (C.c_int, [_p(StreamParams)]),
+        "ewk_set_stream_params": (C.c_int, [vp, i32, _p(StreamParams)]),
+        "ewk_push": (C.c_int, [vp, i32, i32, vp, i64, i64, i32]),
+        "ewk_tick": (C.c_int, [vp, i32]),
+        "ewk_tick_trace": (C.c_int, [vp, i32, vp, vp, vp, vp]),
+        "ewk_poll": (C.c_int, [vp, vp, i32, _p(C.c_int)]),
+        "ewk_stream_status_get": (C.c_int, [vp, i32, _p(StreamStatus)]),
+        "ewk_read_last": (C.c_int, [vp, i32, i64, f32p]),
+        "ewk_read_segment": (C.c_int, [vp, i32, i64, i64, f32p]),
+        "ewk_stream_results": (C.c_int, [vp, vp]),
+        "ewk_results_device_ptr": (C.c_int, [vp, _p(vp)]),
+        "ewk_set_results_buffer": (C.c_int, [vp, vp]),
+        "ewk_host_alloc": (C.c_int, [_p(vp), i64]),
+        "ewk_host_free": (C.c_int, [vp]),
+        "ewk_launch_count": (C.c_int64, [vp]),
+    }
+    for name, (res, args) in protos.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib._protos.update(protos)
+
+
+_orig_load = load
+
+
+def load():  # noqa: F811  (extends the loader above with the stream-bank prototypes)
+    lib = _orig_load()
+    if "ewk_push" not in lib._protos:
+        _declare_stream_protos(lib)
+    return lib
+
+
+def default_stream_params(**over):
+    lib = load()
+    p = StreamParams()
+    lib.ewk_default_stream_params(C.byref(p))
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise TypeError(f"unknown stream parameter {k!r}")
+        setattr(p, k, v)
+    return p
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc memory (asynchronous H2D pushes)."""
+
+    def __init__(self, shape, dtype):
+        lib = load()
+        self.lib = lib
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dt.itemsize
+        ptr = C.c_void_p()
+        rc = lib.ewk_host_alloc(C.byref(ptr), max(1, nbytes))
+        if rc != EWK_OK:
+            raise MemoryError("cudaHostAlloc failed")
+        self.ptr = ptr
+        buf = (C.c_char * nbytes).from_address(ptr.value)
+        self.array = np.frombuffer(buf, dtype=dt).reshape(shape)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self.lib.ewk_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _bank_methods():
+    def set_stream_params(self, stream=-1, params=None, **over):
+        p = params if params is not None else default_stream_params(**over)
+        self._ck(self.lib.ewk_set_stream_params(self.h, stream, C.byref(p)))
+
+    def push(self, pcm, stream0=0, where=HOST):
+        """pcm: [n_streams, n] array in the ring's dtype (rows may be strided), or (ptr, n_streams, n, stride)."""
+        if isinstance(pcm, tuple):
+            ptr, ns, n, stride = pcm
+        else:
+            want = np.int16 if self.cfg.pcm_format == PCM_I16 else np.float32
+            a = pcm if pcm.ndim == 2 else pcm.reshape(1, -1)
+            if a.dtype != want:
+                raise TypeError(f"push expects {np.dtype(want)} PCM for this context, got {a.dtype}")
+            if a.strides[1] != a.itemsize:
+                a = np.ascontiguousarray(a)
+            ns, n = a.shape
+            stride = a.strides[0] // a.itemsize if ns > 1 else n
+            ptr = a.ctypes.data
+        self._ck(self.lib.ewk_push(self.h, stream0, ns, ptr, n, stride, where))
+
+    def tick(self, n_ticks=1, trace=False):
+        if not trace:
+            self._ck(self.lib.ewk_tick(self.h, n_ticks))
+            return None
+        ns = self.cfg.n_streams
+        silent = np.empty((ns, n_ticks), np.uint8)
+        state = np.empty((ns, n_ticks), np.uint8)
+        thr = np.empty((ns, n_ticks), np.float64)
+        rms = np.empty((ns, n_ticks), np.float64)
+        self._ck(self.lib.ewk_tick_trace(self.h, n_ticks, silent.ctypes.data, state.ctypes.data, thr.ctypes.data,
+                                         rms.ctypes.data))
+        return {"silent": silent.astype(bool), "state": state, "thr": thr, "rms": rms}
+
+    def poll(self):
+        cap = self.cfg.max_events
+        out = np.zeros(cap, dtype=EVENT_DTYPE)
+        dropped = C.c_int()
+        n = self.lib.ewk_poll(self.h, out.ctypes.data, cap, C.byref(dropped))
+        if n < 0:
+            self._ck(n)
+        self.dropped = dropped.value
+        return out[:n]
+
+    def status(self, stream):
+        st = StreamStatus()
+        self._ck(self.lib.ewk_stream_status_get(self.h, stream, C.byref(st)))
+        return st
+
+    def read_last(self, stream, n_samples):
+        out = np.empty(int(n_samples), np.float32)
+        if n_samples:
+            self._ck(self.lib.ewk_read_last(self.h, stream, int(n_samples), f32ptr(out)))
+        return out
+
+    def read_segment(self, stream, seg_start, seg_len):
+        out = np.empty(int(seg_len), np.float32)
+        self._ck(self.lib.ewk_read_segment(self.h, stream, int(seg_start), int(seg_len), f32ptr(out)))
+        return out
+
+    def results(self):
+        out = np.empty(self.cfg.n_streams, dtype=RESULT_DTYPE)
+        self._ck(self.lib.ewk_stream_results(self.h, out.ctypes.data))
+        return out
+
+    def results_device_ptr(self):
+        p = C.c_void_p()
+        self._ck(self.lib.ewk_results_device_ptr(self.h, C.byref(p)))
+        return p.value
+
+    def set_results_buffer(self, device_ptr):
+        self._ck(self.lib.ewk_set_results_buffer(self.h, C.c_void_p(device_ptr)))
+
+    def set_cuda_stream(self, handle):
+        self._ck(self.lib.ewk_set_cuda_stream(self.h, C.c_void_p(handle)))
+
+    def launch_count(self):
+        return int(self.lib.ewk_launch_count(self.h))
+
+    for f in (set_stream_params, push, tick, poll, status, read_last, read_segment, results, results_device_ptr,
+              set_results_buffer, set_cuda_stream, launch_count):
+        setattr(Context, f.__name__, f)
+
+
+_bank_methods()

@@ -313,3 +313,374 @@ extern "C" int ewk_similarity_batch(ewk_ctx* ctx, int slot, const void* pcm, int
     CK(cudaStreamSynchronize(ctx->stream));
     return EWK_OK;
 }
+
+// ==========================================================================================
+// stream bank
+// ==========================================================================================
+static_assert(sizeof(StreamParams) == sizeof(ewk_stream_params), "ewk_stream_params layout");
+static_assert(sizeof(EventRec) == sizeof(ewk_event), "ewk_event layout");
+static_assert(sizeof(StreamResult) == sizeof(ewk_stream_result), "ewk_stream_result layout");
+constexpr int MIN_FRAME_SIZE = 160;
+
+extern "C" int ewk_default_stream_params(ewk_stream_params* p) {
+    if (!p) return EWK_ERR_ARG;
+    std::memset(p, 0, sizeof(*p));
+    p->similarity_threshold = 75.0f;
+    p->frame_size = 0;
+    p->pre_speech_silence = 0.8;
+    p->speech_duration_min = 0.3;
+    p->speech_duration_max = 2.0;
+    p->post_speech_silence = 0.4;
+    p->timeout = 30.0;
+    p->min_threshold = 0.005;
+    p->template_first = 0;
+    p->template_count = 1;
+    p->live = 0;
+    return EWK_OK;
+}
+
+int ewk_ctx::init_streams() {
+    ewk_ctx* ctx = this;
+    const int n = cfg.n_streams;
+    if (n == 0) return EWK_OK;
+    const size_t esz = cfg.pcm_format == EWK_PCM_I16 ? 2 : 4;
+    bank.n_streams = n;
+    bank.R = cfg.ring_samples;
+    bank.P = ((cfg.ring_samples + cfg.slack_samples + 63) / 64) * 64;
+    bank.fmt = cfg.pcm_format == EWK_PCM_I16 ? 1 : 0;
+    chunk_cap = std::max(1, cfg.ring_samples / MIN_FRAME_SIZE);
+    bank.chunk_cap = chunk_cap;
+    bank.max_events = std::max(16, cfg.max_events);
+    CK(cudaMalloc(&bank.ring, esz * (size_t)n * bank.P));
+    CK(cudaMemsetAsync(bank.ring, 0, esz * (size_t)n * bank.P, stream));          // np.zeros   wakeword.py:428
+    CK(cudaMalloc(&bank.st, sizeof(StreamState) * (size_t)n));
+    CK(cudaMalloc(&bank.prm, sizeof(StreamParams) * (size_t)n));
+    CK(cudaMalloc(&bank.chunk_ms, sizeof(double) * (size_t)n * chunk_cap));
+    CK(cudaMalloc(&bank.events, sizeof(EventRec) * (size_t)bank.max_events));
+    CK(cudaMalloc(&bank.ev_count, sizeof(int) * 4));
+    CK(cudaMemsetAsync(bank.ev_count, 0, sizeof(int) * 4, stream));
+    CK(cudaMalloc(&own_results, sizeof(StreamResult) * (size_t)n));
+    bank.results = (StreamResult*)own_results;
+    std::vector<StreamState> st(n);
+    std::memset(st.data(), 0, sizeof(StreamState) * n);
+    for (auto& x : st) x.thr = 0.01;                                                // wakeword.py:431
+    CK(cudaMemcpyAsync(bank.st, st.data(), sizeof(StreamState) * n, cudaMemcpyHostToDevice, stream));
+    ewk_stream_params dp;
+    ewk_default_stream_params(&dp);
+    StreamParams sp;
+    std::memcpy(&sp, &dp, sizeof(sp));
+    h_prm.assign(n, sp);
+    CK(cudaMemcpyAsync(bank.prm, h_prm.data(), sizeof(StreamParams) * n, cudaMemcpyHostToDevice, stream));
+    std::vector<StreamResult> rs(n);
+    for (auto& r : rs) { r.score = std::nanf(""); r.flags = 0; }
+    CK(cudaMemcpyAsync(bank.results, rs.data(), sizeof(StreamResult) * n, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    h_written.assign(n, 0);
+    h_visible_lb.assign(n, 0);
+    h_tick.assign(n, 0);
+    CK(cudaFuncSetAttribute(segment_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
+    return EWK_OK;
+}
+
+void ewk_ctx::release_streams() {
+    for (void* p : {bank.ring, (void*)bank.st, (void*)bank.prm, (void*)bank.chunk_ms, (void*)bank.events,
+                    (void*)bank.ev_count, own_results})
+        if (p) cudaFree(p);
+    bank = BankView{};
+    own_results = nullptr;
+    b_stage.free(); b_trace.free(); b_read.free();
+}
+
+static int need_streams(ewk_ctx* ctx, const char* who) {
+    if (ctx->bank.n_streams == 0) { ctx->fail("%s: context was created with n_streams = 0", who); return EWK_ERR_STATE; }
+    return EWK_OK;
+}
+
+extern "C" int64_t ewk_launch_count(const ewk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ewk_set_stream_params(ewk_ctx* ctx, int stream, const ewk_stream_params* p) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_set_stream_params");
+    if (rc) return rc;
+    const int n = ctx->bank.n_streams;
+    if (!p || stream < -1 || stream >= n) { ctx->fail("ewk_set_stream_params: bad stream %d", stream); return EWK_ERR_ARG; }
+    // the reference's constructor checks (wakeword.py:752-763), same messages
+    if (!(p->pre_speech_silence > 0)) { ctx->fail("pre_speech_silence must be positive"); return EWK_ERR_ARG; }
+    if (!(p->speech_duration_min > 0)) { ctx->fail("speech_duration_min must be positive"); return EWK_ERR_ARG; }
+    if (!(p->speech_duration_max > 0)) { ctx->fail("speech_duration_max must be positive"); return EWK_ERR_ARG; }
+    if (p->speech_duration_min > p->speech_duration_max) { ctx->fail("speech_duration_min must be <= speech_duration_max"); return EWK_ERR_ARG; }
+    if (!(p->post_speech_silence > 0)) { ctx->fail("post_speech_silence must be positive"); return EWK_ERR_ARG; }
+    if (p->frame_size != 0 && (p->frame_size < MIN_FRAME_SIZE || p->frame_size > ctx->bank.R)) {
+        ctx->fail("frame_size must be 0 or in [%d, %d]", MIN_FRAME_SIZE, ctx->bank.R);
+        return EWK_ERR_ARG;
+    }
+    if (p->template_first < 0 || p->template_count < 0 || p->template_first + p->template_count > ctx->cfg.max_templates) {
+        ctx->fail("template range [%d, %d) outside [0, %d)", p->template_first, p->template_first + p->template_count, ctx->cfg.max_templates);
+        return EWK_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    StreamParams sp;
+    std::memcpy(&sp, p, sizeof(sp));
+    const int a = stream < 0 ? 0 : stream, b = stream < 0 ? n : stream + 1;
+    for (int s = a; s < b; s++) ctx->h_prm[s] = sp;
+    CK(cudaMemcpyAsync(ctx->bank.prm + a, ctx->h_prm.data() + a, sizeof(StreamParams) * (size_t)(b - a),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EWK_OK;
+}
+
+extern "C" int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pcm, int64_t n, int64_t stride, int where) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_push");
+    if (rc) return rc;
+    BankView& B = ctx->bank;
+    if (!pcm || n_streams < 1 || stream0 < 0 || stream0 + n_streams > B.n_streams || n < 1 || stride < n) {
+        ctx->fail("ewk_push: bad arguments (stream0=%d n_streams=%d n=%lld stride=%lld)", stream0, n_streams, (long long)n, (long long)stride);
+        return EWK_ERR_ARG;
+    }
+    if (n > B.P - B.R && n > B.R) { ctx->fail("ewk_push: %lld samples exceed the ring (%d)", (long long)n, B.R); return EWK_ERR_ARG; }
+    // audio-clock streams: the push may not overwrite samples a pending tick still has to see
+    for (int s = stream0; s < stream0 + n_streams; s++) {
+        if (ctx->h_prm[s].live) continue;
+        const long long ahead = ctx->h_written[s] + n - ctx->h_visible_lb[s];
+        if (ctx->h_visible_lb[s] >= B.R && ahead > (long long)(B.P - B.R)) {
+            ctx->fail("ewk_push: stream %d would hold %lld un-gated samples, more than slack_samples=%d; call ewk_tick first",
+                      s, ahead, B.P - B.R);
+            return EWK_ERR_STATE;
+        }
+    }
+    CK(cudaSetDevice(ctx->device));
+    const size_t esz = B.fmt == 1 ? 2 : 4;
+    bool uniform = true;
+    for (int s = stream0 + 1; s < stream0 + n_streams; s++) uniform &= ctx->h_written[s] == ctx->h_written[stream0];
+    const int p0 = (int)(ctx->h_written[stream0] % B.P);
+    if (where == EWK_HOST && uniform) {
+        // host PCM lands straight in the rings: one (or, at the wrap, two) pitched H2D copies, no staging pass
+        const int first = (int)std::min<int64_t>(n, B.P - p0);
+        char* dst = (char*)B.ring + ((size_t)stream0 * B.P + p0) * esz;
+        CK(cudaMemcpy2DAsync(dst, (size_t)B.P * esz, pcm, (size_t)stride * esz, (size_t)first * esz, n_streams,
+                             cudaMemcpyHostToDevice, ctx->stream));
+        if (first < n) {
+            char* dst2 = (char*)B.ring + ((size_t)stream0 * B.P) * esz;
+            CK(cudaMemcpy2DAsync(dst2, (size_t)B.P * esz, (const char*)pcm + (size_t)first * esz, (size_t)stride * esz,
+                                 (size_t)(n - first) * esz, n_streams, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    } else {
+        const void* d_src = pcm;
+        long long d_stride = stride;
+        if (where == EWK_HOST) {
+            CK(ctx->b_stage.ensure(esz * (size_t)n * n_streams));
+            CK(cudaMemcpy2DAsync(ctx->b_stage.p, (size_t)n * esz, pcm, (size_t)stride * esz, (size_t)n * esz, n_streams,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+            d_src = ctx->b_stage.p;
+            d_stride = n;
+        }
+        const int per = esz == 2 ? 8 : 4;
+        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (n / per + 255) / 256)), (unsigned)n_streams);
+        if (B.fmt == 1) ring_push_kernel<short><<<grid, 256, 0, ctx->stream>>>(B, stream0, (const short*)d_src, d_stride, (int)n);
+        else ring_push_kernel<float><<<grid, 256, 0, ctx->stream>>>(B, stream0, (const float*)d_src, d_stride, (int)n);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    ring_commit_kernel<<<(n_streams + 255) / 256, 256, 0, ctx->stream>>>(B, stream0, n_streams, (int)n);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    for (int s = stream0; s < stream0 + n_streams; s++) ctx->h_written[s] += n;
+    return EWK_OK;
+}
+
+static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state, double* thr, double* rms) {
+    int rc = need_streams(ctx, "ewk_tick");
+    if (rc) return rc;
+    if (n_ticks < 1 || n_ticks > 4096) { ctx->fail("ewk_tick: n_ticks must be in [1, 4096]"); return EWK_ERR_ARG; }
+    BankView& B = ctx->bank;
+    CK(cudaSetDevice(ctx->device));
+    TraceView tr{};
+    const bool want = silent || state || thr || rms;
+    const size_t cells = (size_t)B.n_streams * n_ticks;
+    if (want) {
+        CK(ctx->b_trace.ensure(cells * (2 + 16)));
+        char* base = (char*)ctx->b_trace.p;
+        tr.thr = (double*)base;
+        tr.rms = (double*)(base + cells * 8);
+        tr.silent = (unsigned char*)(base + cells * 16);
+        tr.state = (unsigned char*)(base + cells * 17);
+    }
+    tick_gate_kernel<<<B.n_streams, GATE_THREADS, sizeof(double) * (size_t)B.chunk_cap, ctx->stream>>>(B, n_ticks, tr);
+    CK(cudaGetLastError());
+    const int grid = std::max(1, ctx->sm_count);
+    segment_queue_kernel<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ctx->stream>>>(
+        ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    // host mirrors (audio clock): V after these ticks, given what has been pushed
+    for (int s = 0; s < B.n_streams; s++) {
+        ctx->h_tick[s] += n_ticks;
+        const StreamParams& p = ctx->h_prm[s];
+        if (p.live) { ctx->h_visible_lb[s] = ctx->h_written[s]; continue; }
+        const int fs = p.frame_size;       // unknown (first-push latch) -> keep the conservative bound
+        if (fs > 0) {
+            const long long v = std::min((ctx->h_tick[s] * TICK / fs) * fs, (ctx->h_written[s] / fs) * fs);
+            ctx->h_visible_lb[s] = std::max(ctx->h_visible_lb[s], v);
+        }
+    }
+    if (want) {
+        if (thr) CK(cudaMemcpyAsync(thr, tr.thr, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (rms) CK(cudaMemcpyAsync(rms, tr.rms, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (silent) CK(cudaMemcpyAsync(silent, tr.silent, cells, cudaMemcpyDeviceToHost, ctx->stream));
+        if (state) CK(cudaMemcpyAsync(state, tr.state, cells, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return EWK_OK;
+}
+
+extern "C" int ewk_tick(ewk_ctx* ctx, int n_ticks) {
+    if (!ctx) return EWK_ERR_ARG;
+    return tick_impl(ctx, n_ticks, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int ewk_tick_trace(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state, double* thr, double* rms) {
+    if (!ctx) return EWK_ERR_ARG;
+    return tick_impl(ctx, n_ticks, silent, state, thr, rms);
+}
+
+extern "C" int ewk_poll(ewk_ctx* ctx, ewk_event* out, int cap, int* dropped) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_poll");
+    if (rc) return rc;
+    if (cap < 0 || (cap > 0 && !out)) { ctx->fail("ewk_poll: bad output buffer"); return EWK_ERR_ARG; }
+    BankView& B = ctx->bank;
+    CK(cudaSetDevice(ctx->device));
+    int cnt[2] = {0, 0};
+    CK(cudaMemcpyAsync(cnt, B.ev_count, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int n = std::min(cnt[0], B.max_events);
+    if (dropped) *dropped = cnt[1];
+    if (n > cap) { ctx->fail("ewk_poll: %d events pending but cap is %d", n, cap); return EWK_ERR_ARG; }
+    if (n > 0) {
+        CK(cudaMemcpyAsync(out, B.events, sizeof(EventRec) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaMemsetAsync(B.ev_count, 0, sizeof(int) * 2, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::sort(out, out + n, [](const ewk_event& a, const ewk_event& b) {
+        if (a.tick != b.tick) return a.tick < b.tick;
+        if (a.stream != b.stream) return a.stream < b.stream;
+        return a.kind < b.kind;
+    });
+    return n;
+}
+
+extern "C" int ewk_stream_status_get(ewk_ctx* ctx, int stream, ewk_stream_status* out) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_stream_status_get");
+    if (rc) return rc;
+    if (!out || stream < 0 || stream >= ctx->bank.n_streams) { ctx->fail("ewk_stream_status_get: bad stream %d", stream); return EWK_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    StreamState st;
+    CK(cudaMemcpyAsync(&st, ctx->bank.st + stream, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    out->written = st.written; out->visible = st.visible; out->tick = st.tick;
+    out->silence_threshold = st.thr; out->last_rms = st.last_rms; out->frame_size = st.frame_size;
+    out->state = st.state; out->started = st.started; out->is_silent = st.last_silent;
+    out->n_timeouts = st.n_timeouts; out->n_events = st.n_events;
+    return EWK_OK;
+}
+
+// absolute samples [a0, a0+len) of one stream as float32 into `out` (host)
+static int read_abs(ewk_ctx* ctx, int stream, long long a0, long long len, float* out) {
+    BankView& B = ctx->bank;
+    const size_t esz = B.fmt == 1 ? 2 : 4;
+    std::vector<char> tmp((size_t)len * esz);
+    const char* ring = (const char*)B.ring + (size_t)stream * B.P * esz;
+    const long long p0 = ((a0 % B.P) + B.P) % B.P;
+    const long long first = std::min<long long>(len, B.P - p0);
+    CK(cudaMemcpyAsync(tmp.data(), ring + p0 * esz, (size_t)first * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    if (first < len)
+        CK(cudaMemcpyAsync(tmp.data() + first * esz, ring, (size_t)(len - first) * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (B.fmt == 1) {
+        const short* q = (const short*)tmp.data();
+        for (long long i = 0; i < len; i++) out[i] = (float)q[i] * (1.0f / 32768.0f);
+    } else std::memcpy(out, tmp.data(), (size_t)len * 4);
+    return EWK_OK;
+}
+
+extern "C" int ewk_read_last(ewk_ctx* ctx, int stream, int64_t n_samples, float* out) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_read_last");
+    if (rc) return rc;
+    BankView& B = ctx->bank;
+    if (!out || stream < 0 || stream >= B.n_streams || n_samples < 0 || n_samples > B.R) {
+        ctx->fail("ewk_read_last: bad arguments"); return EWK_ERR_ARG;
+    }
+    if (n_samples == 0) return EWK_OK;
+    CK(cudaSetDevice(ctx->device));
+    StreamState st;
+    CK(cudaMemcpyAsync(&st, B.st + stream, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const long long V = ctx->h_prm[stream].live ? st.written : st.visible;
+    // positions never written still hold the zeros of np.zeros (wakeword.py:428)
+    const long long a0 = V - n_samples;
+    long long lead = a0 < 0 ? -a0 : 0;
+    for (long long i = 0; i < lead; i++) out[i] = 0.f;
+    if (n_samples - lead > 0) return read_abs(ctx, stream, a0 + lead, n_samples - lead, out + lead);
+    return EWK_OK;
+}
+
+extern "C" int ewk_read_segment(ewk_ctx* ctx, int stream, int64_t seg_start, int64_t seg_len, float* out) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_read_segment");
+    if (rc) return rc;
+    BankView& B = ctx->bank;
+    if (!out || stream < 0 || stream >= B.n_streams || seg_len < 1 || seg_len > B.P || seg_start < 0) {
+        ctx->fail("ewk_read_segment: bad arguments"); return EWK_ERR_ARG;
+    }
+    if (seg_start + seg_len > ctx->h_written[stream]) { ctx->fail("ewk_read_segment: segment not pushed yet"); return EWK_ERR_STATE; }
+    if (ctx->h_written[stream] - seg_start > B.P) { ctx->fail("ewk_read_segment: segment already overwritten in the ring"); return EWK_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    return read_abs(ctx, stream, seg_start, seg_len, out);
+}
+
+extern "C" int ewk_stream_results(ewk_ctx* ctx, ewk_stream_result* out) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_stream_results");
+    if (rc) return rc;
+    if (!out) { ctx->fail("ewk_stream_results: null output"); return EWK_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, ctx->bank.results, sizeof(StreamResult) * (size_t)ctx->bank.n_streams, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EWK_OK;
+}
+
+extern "C" int ewk_results_device_ptr(ewk_ctx* ctx, void** out) {
+    if (!ctx || !out) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_results_device_ptr");
+    if (rc) return rc;
+    *out = ctx->bank.results;
+    return EWK_OK;
+}
+
+extern "C" int ewk_set_results_buffer(ewk_ctx* ctx, void* device_ptr) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_set_results_buffer");
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    StreamResult* dst = device_ptr ? (StreamResult*)device_ptr : (StreamResult*)ctx->own_results;
+    if (dst != ctx->bank.results) {
+        CK(cudaMemcpyAsync(dst, ctx->bank.results, sizeof(StreamResult) * (size_t)ctx->bank.n_streams, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->bank.results = dst;
+    }
+    return EWK_OK;
+}
+
+extern "C" int ewk_host_alloc(void** out, int64_t bytes) {
+    if (!out || bytes < 1) return EWK_ERR_ARG;
+    return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? EWK_OK : EWK_ERR_NOMEM;
+}
+
+extern "C" int ewk_host_free(void* p) {
+    if (!p) return EWK_ERR_ARG;
+    return cudaFreeHost(p) == cudaSuccess ? EWK_OK : EWK_ERR_CUDA;
+}

@@ -7,6 +7,7 @@
 
 #include "ewk_frame.cuh"
 #include "ewk_segment.cuh"
+#include "ewk_streams.cuh"
 #include "ewk_tables.hpp"
 
 #define EWK_MAX_TEMPLATES 64
@@ -44,8 +45,18 @@ struct ewk_ctx {
     void fail(const char* fmt, ...);
     int init();
     void release();
-    int init_streams() { return 0; }
-    void release_streams() {}
+    // stream bank
+    ewk::BankView bank{};
+    void* own_results = nullptr;
+    ewk::DevBuf b_stage, b_trace, b_read;
+    int chunk_cap = 0;
+    long long launches = 0;
+    std::vector<ewk::StreamParams> h_prm;
+    std::vector<long long> h_written;      // host mirror of StreamState.written
+    std::vector<long long> h_visible_lb;   // lower bound of StreamState.visible (audio-clock overrun check)
+    std::vector<long long> h_tick;
+    int init_streams();
+    void release_streams();
     int launch_segments(const ewk::SegDesc* d_segs, int n_seg, int max_frames, long long spill_frames, int n_tmpl,
                         int tmpl_first, float threshold, float* d_feat, float* d_frames, float* d_scores,
                         unsigned char* d_matched);

@@ -87,53 +87,55 @@ __host__ __device__ inline size_t seg_smem_bytes(int cap_frames) {
                             (size_t)cap_frames * (LM_STRIDE + N_MFCC));
 }
 
-__global__ void __launch_bounds__(SEG_THREADS, 1)
-segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __restrict__ segs,
-                          int cap_frames, float* __restrict__ ws,           // global spill [frames][129+20]
-                          const TemplateFeat* __restrict__ tmpl, int n_tmpl, int tmpl_first,
-                          float threshold,
-                          float* __restrict__ feat_out,                      // [n_seg][40] or null
-                          float* __restrict__ frames_out,                    // [frames][20] or null
-                          float* __restrict__ scores,                        // [n_seg][n_tmpl] or null
-                          unsigned char* __restrict__ matched)               // [n_seg][n_tmpl] or null
-{
-    extern __shared__ float smem[];
-    float* melw = smem;
-    float* dct = melw + MEL_NNZ_CAP;
-    float* scratch = dct + N_MELS * N_MFCC;
-    float* red = scratch + SEG_WARPS * SCR_WARP;
-    float* lm_s = red + 64;
-    float* mf_s = lm_s + (size_t)cap_frames * LM_STRIDE;
+struct SegSmem {
+    float *melw, *dct, *scratch, *red, *lm, *mf;
+};
 
+__device__ __forceinline__ SegSmem seg_carve(float* smem, int cap_frames) {
+    SegSmem m;
+    m.melw = smem;
+    m.dct = m.melw + MEL_NNZ_CAP;
+    m.scratch = m.dct + N_MELS * N_MFCC;
+    m.red = m.scratch + SEG_WARPS * SCR_WARP;
+    m.lm = m.red + 64;
+    m.mf = m.lm + (size_t)cap_frames * LM_STRIDE;
+    return m;
+}
+
+// once per CTA: tables into shared memory, per-lane constants into registers
+__device__ __forceinline__ void seg_prologue(const DeviceTables* __restrict__ T, const SegSmem& m, LaneConsts& lc) {
+    for (int i = threadIdx.x; i < MEL_NNZ_CAP; i += SEG_THREADS) m.melw[i] = T->mel_w[i];
+    for (int i = threadIdx.x; i < N_MELS * N_MFCC; i += SEG_THREADS) m.dct[i] = T->dct_t[i];
+    init_lane_consts(lc, T, threadIdx.x & 31);
+    __syncthreads();
+}
+
+// Phases A-D for one segment by the whole CTA.  Returns a shared-memory pointer to mean[20] ++ std[20]
+// (valid until the next call).  All threads must call it.
+__device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegSmem& m, const LaneConsts& lc,
+                                                   int cap_frames, float* __restrict__ ws,
+                                                   float* __restrict__ frames_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const SegDesc sd = segs[blockIdx.x];
     const int F = 1 + sd.len / HOP;
-    float* lm = lm_s;
-    float* mf = mf_s;
+    float* lm = m.lm;
+    float* mf = m.mf;
     if (F > cap_frames) {
         lm = ws + (size_t)sd.ws_frame_off * (LM_STRIDE + N_MFCC);
         mf = lm + (size_t)F * LM_STRIDE;
     }
-
-    for (int i = tid; i < MEL_NNZ_CAP; i += SEG_THREADS) melw[i] = T->mel_w[i];
-    for (int i = tid; i < N_MELS * N_MFCC; i += SEG_THREADS) dct[i] = T->dct_t[i];
-    LaneConsts lc;
-    init_lane_consts(lc, T, lane);
-    __syncthreads();
-
     PcmReader rd;
     rd.f = sd.fmt == 0 ? (const float*)sd.base : nullptr;
     rd.q = sd.fmt == 1 ? (const short*)sd.base : nullptr;
     rd.ring = sd.ring; rd.len = sd.len; rd.start = sd.start;
 
     // ---- phase A
-    float* scr = scratch + warp * SCR_WARP;
+    float* scr = m.scratch + warp * SCR_WARP;
     float vmax = -INFINITY;
     for (int t = warp; t < F; t += SEG_WARPS) {
         const int f0 = t * HOP - N_FFT / 2;
         warp_power_spectrum([&](int i) { return make_float2(rd.at(f0 + i), rd.at(f0 + i + 1)); }, lc, scr, lane);
         float v[4];
-        warp_log_mel(scr + 2 * SCR_PLANE, melw, lc, v);
+        warp_log_mel(scr + 2 * SCR_PLANE, m.melw, lc, v);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             lm[(size_t)t * LM_STRIDE + lane + 32 * j] = v[j];
@@ -143,11 +145,11 @@ segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __r
     // ---- phase B
 #pragma unroll
     for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
-    if (lane == 0) red[warp] = vmax;
+    if (lane == 0) m.red[warp] = vmax;
     __syncthreads();
-    float gmax = red[0];
+    float gmax = m.red[0];
 #pragma unroll
-    for (int w = 1; w < SEG_WARPS; w++) gmax = fmaxf(gmax, red[w]);
+    for (int w = 1; w < SEG_WARPS; w++) gmax = fmaxf(gmax, m.red[w]);
     const float floor_db = gmax - 80.0f;       // librosa.power_to_db(top_db=80)
     __syncthreads();
 
@@ -160,7 +162,7 @@ segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __r
         for (int k = 0; k < 10; k++) acc[k] = 0.f;
         for (int b = 0; b < N_MELS; b++) {
             const float x = fmaxf(row[b], floor_db);
-            const float2* d = reinterpret_cast<const float2*>(dct + b * N_MFCC + 10 * g);
+            const float2* d = reinterpret_cast<const float2*>(m.dct + b * N_MFCC + 10 * g);
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 const float2 w = d[k];
@@ -179,8 +181,8 @@ segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __r
 
     // ---- phase D: mean / std over frames; thread = (slice of frames, coefficient)
     constexpr int SL = 12;                       // 12 * 20 = 240 active threads
-    float* part = scratch;                       // [SL][20], scratch is free now
-    float* feat = scratch + SL * N_MFCC;         // mean[20] ++ std[20]
+    float* part = m.scratch;                     // [SL][20], the FFT scratch is free now
+    float* feat = m.scratch + SL * N_MFCC;       // mean[20] ++ std[20]
     const int k = tid % N_MFCC, sl = tid / N_MFCC;
     if (sl < SL) {
         float s = 0.f;
@@ -196,9 +198,9 @@ segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __r
     }
     __syncthreads();
     if (sl < SL) {
-        const float m = feat[k];
+        const float mu = feat[k];
         float s = 0.f;
-        for (int t = sl; t < F; t += SL) { const float d = mf[(size_t)t * N_MFCC + k] - m; s = fmaf(d, d, s); }
+        for (int t = sl; t < F; t += SL) { const float d = mf[(size_t)t * N_MFCC + k] - mu; s = fmaf(d, d, s); }
         part[sl * N_MFCC + k] = s;
     }
     __syncthreads();
@@ -209,6 +211,27 @@ segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __r
         feat[N_MFCC + tid] = sqrtf(s / (float)F);
     }
     __syncthreads();
+    return feat;
+}
+
+// K3, batch form: one CTA per caller-described segment (extract_mfcc / calculate_similarity / matches).
+__global__ void __launch_bounds__(SEG_THREADS, 1)
+segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __restrict__ segs,
+                          int cap_frames, float* __restrict__ ws,           // global spill [frames][129+20]
+                          const TemplateFeat* __restrict__ tmpl, int n_tmpl, int tmpl_first,
+                          float threshold,
+                          float* __restrict__ feat_out,                      // [n_seg][40] or null
+                          float* __restrict__ frames_out,                    // [frames][20] or null
+                          float* __restrict__ scores,                        // [n_seg][n_tmpl] or null
+                          unsigned char* __restrict__ matched)               // [n_seg][n_tmpl] or null
+{
+    extern __shared__ float smem[];
+    const SegSmem m = seg_carve(smem, cap_frames);
+    LaneConsts lc;
+    seg_prologue(T, m, lc);
+    const int tid = threadIdx.x;
+    const SegDesc sd = segs[blockIdx.x];
+    const float* feat = segment_features(sd, m, lc, cap_frames, ws, frames_out);
     if (feat_out && tid < FEAT) feat_out[(size_t)blockIdx.x * FEAT + tid] = feat[tid];
     if (scores && tid < n_tmpl) {
         const TemplateFeat& tf = tmpl[tmpl_first + tid];

@@ -1,0 +1,460 @@
+// K1 ring_push and K2 tick_gate: the level-1 data plane of the reference, batched over streams.
+//
+//   K1  SoundBuffer._add_sound_to_buffer   (/root/reference/easywakeword/wakeword.py:454-465)
+//   K2  SoundBuffer._adjust_silence_threshold + is_silent (wakeword.py:472-496) and the 4-state
+//       timing machine + segment cut of WakeWord._detect_word (wakeword.py:1036-1118, 1155-1157)
+//
+// Device layout (all SoA over streams): a PHYSICAL ring of P = ring + slack samples per stream
+// (int16 or f32) holding absolute sample a at a % P.  The reference's logical ring of R samples is
+// the most recent R samples visible at a tick; keeping `slack` older samples lets one push run
+// ahead of the ticks that consume it while every intermediate tick still sees exactly the ring
+// content the reference would have had (chunk RMS values are recomputed from samples, never
+// updated incrementally, so there is no drift).
+//
+// Time is the audio clock: tick k has time k*0.1 (float64, computed with the same IEEE operations
+// as the oracle, no FMA contraction) and sees V_k = floor(1600 k / frame_size) * frame_size samples.
+#pragma once
+#include "ewk_frame.cuh"
+#include "ewk_segment.cuh"
+
+#ifndef EWK_MAX_TEMPLATES
+#define EWK_MAX_TEMPLATES 64
+#endif
+
+namespace ewk {
+
+constexpr int GATE_THREADS = 128;
+constexpr int TICK = 1600;              // int(0.1 * 16000)            wakeword.py:492, 500
+constexpr int MAX_SEG = 48000;          // 3.0 s cap                   wakeword.py:1114-1118
+
+enum : int { ST_WAITING = 0, ST_IN_SILENCE = 1, ST_IN_SOUND = 2, ST_AFTER_SOUND = 3 };
+enum : int { EV_PENDING = 0, EV_TIMEOUT = 1, EV_SCORED = 2 };
+
+struct StreamParams {               // mirrors ewk_stream_params (include/ewk.h)
+    float similarity_threshold;
+    int frame_size;
+    double pre_speech_silence, speech_duration_min, speech_duration_max, post_speech_silence;
+    double timeout;
+    double min_threshold;
+    int template_first, template_count;
+    int live;
+    int reserved;
+};
+
+struct StreamState {
+    long long written;      // samples pushed so far (absolute index of the next sample)
+    long long visible;      // V of the last processed tick
+    long long tick;         // k of the last processed tick
+    double thr;             // SoundBuffer.silence_threshold (init 0.01, wakeword.py:431)
+    double silence_start, sound_start, sound_end, start_time;
+    double last_rms;
+    int frame_size;         // 0 until the first push (wakeword.py:457-458)
+    int state;
+    int started;            // _detect_word entered (buffer was full at some tick)
+    int last_silent;
+    int chunks_valid;       // chunk mean-squares reflect the ring at `visible`
+    int n_timeouts;
+    int n_events;
+    int pad;
+};
+
+struct EventRec {           // mirrors ewk_event
+    int stream;
+    int kind;
+    long long tick;
+    long long seg_start;    // absolute sample index of the segment's first sample
+    int seg_len;
+    int tmpl;
+    float score;
+    int matched;
+};
+
+struct StreamResult {       // dense per-stream record (what multi-GPU runs gather)
+    float score;            // score of the stream's latest level-2 evaluation (NaN before the first)
+    unsigned flags;         // bit0 matched(latest) | bit1 silent | bits2-3 state | bit4 event this call | bits 8.. event count
+};
+
+struct BankView {
+    void* ring;             // [n_streams][P]
+    StreamState* st;
+    StreamParams* prm;
+    double* chunk_ms;       // [n_streams][chunk_cap] mean square per storage-order chunk
+    EventRec* events;
+    int* ev_count;          // [0] count, [1] dropped
+    StreamResult* results;
+    int n_streams, R, P, fmt, chunk_cap, max_events;
+};
+
+struct TraceView {          // optional per-tick trace for parity tests: [n_streams][n_ticks]
+    unsigned char* silent;
+    unsigned char* state;
+    double* thr;
+    double* rms;
+};
+
+// ------------------------------------------------------------------------------------ K1
+// src[s * stride + i] (i < n) -> ring of stream stream0 + s at absolute index written + i.
+// 16-byte vector path when source and destination runs are 16-byte aligned, scalar otherwise.
+template <typename T>
+__global__ void ring_push_kernel(BankView B, int stream0, const T* __restrict__ src, long long stride, int n) {
+    const int s = blockIdx.y;
+    constexpr int V = 16 / sizeof(T);
+    T* ring = (T*)B.ring + (size_t)(stream0 + s) * B.P;
+    const T* in = src + (size_t)s * stride;
+    const long long w = B.st[stream0 + s].written;
+    const int p0 = (int)(w % B.P);
+    const bool vec = (p0 % V == 0) && (n % V == 0) && (B.P % V == 0) && ((((size_t)in) & 15) == 0);
+    if (vec) {
+        const int nv = n / V;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
+            int p = p0 + i * V;
+            if (p >= B.P) p -= B.P;
+            *reinterpret_cast<int4*>(ring + p) = __ldg(reinterpret_cast<const int4*>(in) + i);
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            int p = p0 + i;
+            if (p >= B.P) p -= B.P;
+            ring[p] = in[i];
+        }
+    }
+}
+
+// bookkeeping after the payload of a push landed (kernel or 2-D copy): written += n, frame_size latch
+__global__ void ring_commit_kernel(BankView B, int stream0, int n_streams, int n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    StreamState& st = B.st[stream0 + s];
+    if (st.frame_size == 0) {
+        const int fs = B.prm[stream0 + s].frame_size;
+        st.frame_size = fs > 0 ? fs : n;                               // wakeword.py:457-458
+    }
+    st.written += n;
+}
+
+// ------------------------------------------------------------------------------------ K2 helpers
+// Sum of squares of absolute samples [a0, a0+len) of one stream, in double.  int16 sums are in
+// integer units (exact); the caller scales by 2^-30.  Whole warp cooperates; result in every lane.
+__device__ __forceinline__ double warp_sumsq(const BankView& B, int s, long long a0, int len, int lane) {
+    double acc = 0.0;
+    if (len <= 0) return 0.0;
+    int p0 = (int)(a0 % B.P);
+    if (B.fmt == 1) {
+        const short* ring = (const short*)B.ring + (size_t)s * B.P;
+        // 16-byte body when aligned and not wrapping; scalar head/tail otherwise
+        int i = 0;
+        if ((p0 & 7) == 0 && p0 + len <= B.P) {
+            const int nv = len >> 3;
+            const int4* v = reinterpret_cast<const int4*>(ring + p0);
+            long long iacc = 0;
+            for (int k = lane; k < nv; k += 32) {
+                const int4 q = __ldg(v + k);
+                const int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int lo = (short)(w[u] & 0xffff), hi = w[u] >> 16;
+                    iacc += (long long)(lo * lo) + (long long)(hi * hi);
+                }
+            }
+            acc = (double)iacc;
+            i = nv << 3;
+        }
+        long long iacc = 0;
+        for (int k = i + lane; k < len; k += 32) {
+            int p = p0 + k;
+            if (p >= B.P) p -= B.P;
+            const int q = ring[p];
+            iacc += (long long)(q * q);
+        }
+        acc += (double)iacc;
+    } else {
+        const float* ring = (const float*)B.ring + (size_t)s * B.P;
+        for (int k = lane; k < len; k += 32) {
+            int p = p0 + k;
+            if (p >= B.P) p -= B.P;
+            const double x = (double)ring[p];
+            acc = fma(x, x, acc);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    return acc;
+}
+
+// mean square of storage-order chunk c as the reference's ring holds it when V samples are visible:
+// logical position p < V % R was written in the current lap, p >= V % R in the previous one.
+__device__ __forceinline__ double warp_chunk_ms(const BankView& B, int s, long long V, int fs, int c, int lane) {
+    const long long lap = V / B.R;
+    const int q = (int)(V % B.R);
+    const int lo = c * fs, hi = lo + fs;
+    const int split = min(max(q, lo), hi);            // [lo, split) current lap, [split, hi) previous lap
+    double ss = 0.0;
+    if (split > lo) ss += warp_sumsq(B, s, lap * B.R + lo, split - lo, lane);
+    if (hi > split) ss += warp_sumsq(B, s, (lap - 1) * B.R + split, hi - split, lane);
+    if (B.fmt == 1) ss *= (1.0 / 1073741824.0);       // (q/32768)^2, exact power of two
+    return ss / (double)fs;                           // np.mean(frame**2)            wakeword.py:481
+}
+
+// np.percentile(rms, 25) with numpy's default 'linear' method and its _lerp, on sqrt(ms[0..n)).
+// Block-wide rank counting; result valid in thread 0.  sel[2] is shared scratch.
+__device__ __forceinline__ double block_percentile25_rms(const double* ms, int n, double* sel, int tid) {
+    const double vi = (double)n * 0.25 - 0.25;        // n*q + (alpha + q*(1-alpha-beta)) - 1, alpha=beta=1
+    const int k_lo = (int)floor(vi);
+    const int k_hi = min(k_lo + 1, n - 1);
+    for (int i = tid; i < n; i += GATE_THREADS) {
+        const long long vi_bits = __double_as_longlong(ms[i]);
+        int r = 0;
+        for (int j = 0; j < n; j++) {
+            const long long vj = __double_as_longlong(ms[j]);
+            r += (vj < vi_bits) || (vj == vi_bits && j < i);
+        }
+        if (r == k_lo) sel[0] = ms[i];
+        if (r == k_hi) sel[1] = ms[i];
+    }
+    __syncthreads();
+    const double a = sqrt(sel[0]), b = sqrt(sel[1]);
+    const double t = vi - (double)k_lo;
+    const double diff = __dsub_rn(b, a);
+    double r = __dadd_rn(a, __dmul_rn(diff, t));
+    if (t >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, t)));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------ K2
+// One CTA per stream, n_ticks sequential ticks.
+__global__ void __launch_bounds__(GATE_THREADS)
+tick_gate_kernel(BankView B, int n_ticks, TraceView tr) {
+    extern __shared__ double sm_d[];
+    double* ms = sm_d;                               // [chunk_cap]
+    __shared__ double piece[GATE_THREADS / 32];
+    __shared__ double sel[2];
+    __shared__ double recent_ss;
+
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    StreamState st = B.st[s];
+    const StreamParams prm = B.prm[s];
+    const int fs = st.frame_size;
+    const int n_chunks = fs > 0 ? B.R / fs : 0;
+    double* g_ms = B.chunk_ms + (size_t)s * B.chunk_cap;
+    const bool use_chunks = n_chunks > 0 && n_chunks <= B.chunk_cap;
+    if (use_chunks && st.chunks_valid)
+        for (int i = tid; i < n_chunks; i += GATE_THREADS) ms[i] = g_ms[i];
+    __syncthreads();
+    unsigned evflag = 0;
+
+    for (int j = 0; j < n_ticks; j++) {
+        const long long k = st.tick + 1;
+        long long V = st.visible;
+        if (fs > 0) {
+            const long long avail = (st.written / fs) * fs;
+            V = prm.live ? st.written : min((k * TICK / fs) * fs, avail);
+            if (V < st.visible) V = st.visible;
+        }
+        const bool full = fs > 0 && V >= B.R;                          // is_buffer_full   wakeword.py:515-517
+
+        // ---- adaptive threshold (wakeword.py:467-486): only once the ring has been filled
+        if (full && use_chunks && V > st.visible) {
+            const long long dv = V - st.visible;
+            // storage-order chunks touched by the new samples: logical positions [q0, q0+dv) mod R
+            int c1 = 0, n1 = n_chunks, n2 = 0;
+            if (st.chunks_valid && dv < B.R) {
+                const int q0 = (int)(st.visible % B.R);
+                const long long e = q0 + dv;                            // exclusive end, unwrapped
+                const int e1 = (int)min(e, (long long)B.R);
+                c1 = q0 / fs;
+                n1 = (e1 - 1) / fs - c1 + 1;
+                if (e > B.R) n2 = (int)((e - B.R - 1) / fs) + 1;        // wrapped part starts at chunk 0
+            }
+            for (int i = warp; i < n1 + n2; i += GATE_THREADS / 32) {
+                const int c = i < n1 ? c1 + i : i - n1;
+                if (c < n_chunks) {                                     // the tail R - n_chunks*fs is in no chunk
+                    const double v = warp_chunk_ms(B, s, V, fs, c, lane);
+                    if (lane == 0) ms[c] = v;
+                }
+            }
+            __syncthreads();
+            const double p25 = block_percentile25_rms(ms, n_chunks, sel, tid);
+            if (tid == 0) {
+                const double nt = __dmul_rn(p25, 1.5);                 // wakeword.py:485
+                st.thr = nt > prm.min_threshold ? nt : prm.min_threshold;   // max(new, MIN_THRESHOLD)  :486
+            }
+            st.chunks_valid = 1;
+            __syncthreads();
+        }
+
+        // ---- is_silent (wakeword.py:488-496): RMS of the last min(1600, R) samples < threshold
+        int silent = 1;
+        double rms = 0.0;
+        if (fs > 0) {
+            const int nrec = min(TICK, B.R);
+            // before `nrec` samples exist the reference's ring holds zeros there
+            const long long a0 = V - nrec;
+            const int len = (int)(a0 < 0 ? V : nrec);
+            const long long a1 = a0 < 0 ? 0 : a0;
+            // split the window over the CTA's warps
+            const int per = (len + GATE_THREADS / 32 - 1) / (GATE_THREADS / 32);
+            const int per8 = (per + 7) & ~7;
+            const int b = warp * per8;
+            const int l = max(0, min(per8, len - b));
+            const double part = warp_sumsq(B, s, a1 + b, l, lane);
+            if (lane == 0) piece[warp] = part;
+            __syncthreads();
+            if (tid == 0) {
+                double ss = 0.0;
+                for (int w = 0; w < GATE_THREADS / 32; w++) ss += piece[w];
+                if (B.fmt == 1) ss *= (1.0 / 1073741824.0);
+                rms = sqrt(ss / (double)nrec);
+                recent_ss = rms;
+            }
+            __syncthreads();
+            rms = recent_ss;
+            silent = rms < st.thr;
+        }
+
+        // ---- state machine, thread 0 (wakeword.py:1036-1157)
+        if (tid == 0) {
+            const double now = __dmul_rn((double)k, 0.1);
+            st.last_rms = rms;
+            if (full && !st.started) {                                  // _wait_for_buffer done -> _detect_word entry
+                st.started = 1;
+                st.state = silent ? ST_IN_SILENCE : ST_WAITING;        // :1048, 1055-1057
+                st.start_time = now;                                    // :1052
+                if (silent) st.silence_start = now;
+            } else if (st.started) {
+                // loop top of the previous iteration's end: timeout check uses time() before the sleep (:1061)
+                const double prev = __dmul_rn((double)(k - 1), 0.1);
+                if (prm.timeout > 0.0 && __dsub_rn(prev, st.start_time) > prm.timeout) {
+                    // TimeoutError -> listen loop re-enters _detect_word at `prev` (:1205-1211)
+                    const int idx = atomicAdd(B.ev_count, 1);
+                    if (idx < B.max_events) {
+                        EventRec e{};
+                        e.stream = s; e.kind = EV_TIMEOUT; e.tick = k - 1; e.score = __int_as_float(0x7fc00000);
+                        B.events[idx] = e;
+                    } else { atomicAdd(B.ev_count + 1, 1); atomicSub(B.ev_count, 1); }
+                    st.n_timeouts++;
+                    st.state = st.last_silent ? ST_IN_SILENCE : ST_WAITING;
+                    st.start_time = prev;
+                    if (st.last_silent) st.silence_start = prev;
+                }
+                switch (st.state) {
+                    case ST_WAITING:                                    // :1069-1072
+                        if (silent) { st.state = ST_IN_SILENCE; st.silence_start = now; }
+                        break;
+                    case ST_IN_SILENCE:                                 // :1074-1081
+                        if (!silent) {
+                            if (__dsub_rn(now, st.silence_start) >= prm.pre_speech_silence) {
+                                st.state = ST_IN_SOUND; st.sound_start = now;
+                            } else st.state = ST_WAITING;
+                        }
+                        break;
+                    case ST_IN_SOUND: {                                 // :1083-1094
+                        const double dur = __dsub_rn(now, st.sound_start);
+                        if (!silent) { if (dur > prm.speech_duration_max) st.state = ST_WAITING; }
+                        else if (prm.speech_duration_min <= dur && dur <= prm.speech_duration_max) {
+                            st.state = ST_AFTER_SOUND; st.sound_end = now;
+                        } else st.state = ST_WAITING;
+                        break;
+                    }
+                    case ST_AFTER_SOUND:                                // :1096-1157
+                        if (silent) {
+                            if (__dsub_rn(now, st.sound_end) >= prm.post_speech_silence) {
+                                const double es = __dsub_rn(__dsub_rn(st.sound_start, now), 0.05);   // :1102
+                                const double ee = __dadd_rn(__dsub_rn(st.sound_end, now), 0.05);     // :1103
+                                long long n_back = (long long)__dmul_rn(fabs(es), 16000.0);          // :500
+                                const long long n_drop = (long long)__dmul_rn(fabs(ee), 16000.0);    // :1108
+                                if (n_back > B.R) n_back = B.R;                                      // :501-502
+                                const long long len = n_back - n_drop;
+                                if (len >= 1 && len <= MAX_SEG) {                                    // :1114-1118
+                                    const int idx = atomicAdd(B.ev_count, 1);
+                                    if (idx < B.max_events) {
+                                        EventRec e{};
+                                        e.stream = s; e.kind = EV_PENDING; e.tick = k;
+                                        e.seg_start = V - n_back; e.seg_len = (int)len;
+                                        e.tmpl = -1; e.score = __int_as_float(0x7fc00000); e.matched = 0;
+                                        B.events[idx] = e;
+                                        st.n_events++;
+                                        evflag = 16u;
+                                    } else { atomicAdd(B.ev_count + 1, 1); atomicSub(B.ev_count, 1); }
+                                }
+                                st.state = ST_WAITING;                  // :1117, 1155
+                            }
+                        } else st.state = ST_WAITING;                   // :1157
+                        break;
+                }
+            }
+            st.last_silent = silent;
+            st.tick = k;
+            st.visible = V;
+            if (tr.silent) {
+                const size_t o = (size_t)s * n_ticks + j;
+                tr.silent[o] = (unsigned char)silent;
+                tr.state[o] = (unsigned char)(st.started ? st.state : 255);
+                tr.thr[o] = st.thr;
+                tr.rms[o] = rms;
+            }
+        } else {
+            st.tick = k;
+            st.visible = V;
+        }
+        __syncthreads();
+    }
+
+    if (use_chunks)
+        for (int i = tid; i < n_chunks; i += GATE_THREADS) g_ms[i] = ms[i];
+    if (tid == 0) {
+        B.st[s] = st;
+        StreamResult r = B.results[s];
+        r.flags = (r.flags & 1u) | (st.last_silent ? 2u : 0u) | ((unsigned)st.state << 2) | evflag |
+                  ((unsigned)st.n_events << 8);
+        B.results[s] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------ K3 (queue form)
+// Persistent CTAs drain the segments K2 queued: PCM straight from the stream's device ring ->
+// fused MFCC + template match -> score written back into the event record and the per-stream result.
+__global__ void __launch_bounds__(SEG_THREADS, 1)
+segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, int n_tmpl_slots) {
+    extern __shared__ float smem[];
+    const SegSmem m = seg_carve(smem, SEG_SMEM_FRAMES);
+    LaneConsts lc;
+    seg_prologue(T, m, lc);
+    __shared__ float sc_s[EWK_MAX_TEMPLATES];
+    const int tid = threadIdx.x;
+    const int n = min(B.ev_count[0], B.max_events);
+    const size_t esz = B.fmt == 1 ? 2 : 4;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const EventRec e = B.events[i];
+        if (e.kind != EV_PENDING) continue;                             // uniform across the CTA
+        SegDesc sd;
+        sd.base = (const char*)B.ring + (size_t)e.stream * B.P * esz;
+        sd.start = e.seg_start % B.P; sd.ring = B.P; sd.len = e.seg_len; sd.fmt = B.fmt;
+        sd.ws_frame_off = 0; sd.frames_off = 0;
+        const float* feat = segment_features(sd, m, lc, SEG_SMEM_FRAMES, nullptr, nullptr);
+        const StreamParams& prm = B.prm[e.stream];
+        const int t0 = max(0, prm.template_first);
+        const int nt = max(0, min(prm.template_count, n_tmpl_slots - t0));
+        if (tid < nt) {
+            const TemplateFeat& tf = tmpl[t0 + tid];
+            sc_s[tid] = tf.valid ? similarity_score(tf.mean, tf.std, feat, feat + N_MFCC) : __int_as_float(0x7fc00000);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // best score over the stream's template set (NaN never wins: NaN >= x is false, as in wakeword.py:638-639)
+            float best = __int_as_float(0x7fc00000);
+            int arg = nt > 0 ? t0 : -1;
+            for (int k = 0; k < nt; k++)
+                if (!(sc_s[k] != sc_s[k]) && (best != best || sc_s[k] > best)) { best = sc_s[k]; arg = t0 + k; }
+            const int ok = best >= prm.similarity_threshold ? 1 : 0;
+            EventRec* o = B.events + i;
+            o->score = best; o->tmpl = arg; o->matched = ok; o->kind = EV_SCORED;
+            StreamResult r = B.results[e.stream];
+            r.score = best;
+            r.flags = (r.flags & ~1u) | (unsigned)ok;
+            B.results[e.stream] = r;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace ewk

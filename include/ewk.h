@@ -87,6 +87,90 @@ int ewk_similarity_batch(ewk_ctx* ctx, int slot, const void* pcm, int pcm_format
                          const int64_t* offsets, const int64_t* lens, int n_seg, float threshold,
                          float* scores, uint8_t* matched, float* features);
 
+/* ---- level 1: SoundBuffer (wakeword.py:405-517) + _detect_word timing (wakeword.py:1036-1159) --- */
+typedef struct ewk_stream_params {
+    float similarity_threshold;     /* WakeWord(similarity_threshold=75.0)              wakeword.py:676  */
+    int32_t frame_size;             /* PortAudio callback length; 0: length of the first push  :457-458 */
+    double pre_speech_silence;      /* 0.8                                                :38, 677       */
+    double speech_duration_min;     /* auto from the template WAV (fallback 0.3)          :39, 678       */
+    double speech_duration_max;     /* 2 x min (fallback 2.0)                             :40, 679       */
+    double post_speech_silence;     /* 0.4                                                :41, 680       */
+    double timeout;                 /* seconds before _detect_word raises and the listen loop re-enters
+                                       it (:1061-1062, 1205-1211); <= 0: never                          */
+    double min_threshold;           /* SoundBuffer.MIN_THRESHOLD = 0.005                  :409           */
+    int32_t template_first;         /* the stream is scored against template slots                      */
+    int32_t template_count;         /*   [template_first, template_first + template_count), best wins   */
+    int32_t live;                   /* 1: a tick sees every pushed sample (SoundBuffer facade driven by
+                                       wall-clock polls); 0: audio clock, tick k sees
+                                       floor(1600 k / frame_size) * frame_size samples                  */
+    int32_t reserved;
+} ewk_stream_params;
+
+typedef struct ewk_event {
+    int32_t stream;
+    int32_t kind;          /* 2: level-2 evaluation of a level-1 candidate (wakeword.py:1121); 1: timeout */
+    int64_t tick;          /* tick index k (time = k * 0.1 s) at which the reference would have acted     */
+    int64_t seg_start;     /* absolute sample index of the first sample of the extracted word_audio       */
+    int32_t seg_len;       /* len(word_audio)                                       wakeword.py:1109-1111 */
+    int32_t template_slot; /* best-scoring template slot                                                  */
+    float score;           /* WordMatcher.calculate_similarity                      wakeword.py:591-625   */
+    int32_t matched;       /* score >= similarity_threshold                         wakeword.py:638-639   */
+} ewk_event;
+
+typedef struct ewk_stream_status {
+    int64_t written;            /* samples pushed                                                       */
+    int64_t visible;            /* samples the last tick saw                                            */
+    int64_t tick;               /* ticks processed                                                      */
+    double silence_threshold;   /* SoundBuffer.silence_threshold                     wakeword.py:431,486 */
+    double last_rms;            /* RMS of the last 0.1 s at the last tick            wakeword.py:495     */
+    int32_t frame_size;         /* SoundBuffer.frame_size                                               */
+    int32_t state;              /* 0 waiting, 1 in_silence, 2 in_sound, 3 after_sound                   */
+    int32_t started;            /* buffer was full and _detect_word is running                          */
+    int32_t is_silent;          /* SoundBuffer.is_silent() at the last tick          wakeword.py:488-496 */
+    int32_t n_timeouts;
+    int32_t n_events;
+} ewk_stream_status;
+
+typedef struct ewk_stream_result {  /* dense per-stream record, 8 bytes: what multi-GPU runs gather      */
+    float score;                    /* latest level-2 score of the stream (NaN before the first)         */
+    uint32_t flags;                 /* bit0 matched | bit1 silent | bits2-3 state | bit4 event in the last
+                                       ewk_tick | bits 8..31 events so far                               */
+} ewk_stream_result;
+
+/* defaults of the reference (wakeword.py:31-48, 408-409, 676) with audio-clock ticks */
+int ewk_default_stream_params(ewk_stream_params* out);
+/* stream == -1 applies to every stream. */
+int ewk_set_stream_params(ewk_ctx* ctx, int stream, const ewk_stream_params* p);
+/* SoundBuffer._add_sound_to_buffer (wakeword.py:454-465) for n_streams streams at once: n samples per
+ * stream, stream s reads pcm + s*stride (in samples, format = the ring's).  `where` tells whether pcm is
+ * a host pointer (pinned memory makes the copy asynchronous) or a device pointer. */
+int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pcm, int64_t n, int64_t stride, int where);
+/* n_ticks polls of WakeWord._detect_word (wakeword.py:1064-1157) for every stream: adaptive threshold,
+ * is_silent, timing state machine, segment cut, then the fused MFCC+match kernel on every candidate.
+ * Asynchronous; results are read with ewk_poll / ewk_stream_results. */
+int ewk_tick(ewk_ctx* ctx, int n_ticks);
+/* Same, also recording per-tick traces [n_streams][n_ticks] (any pointer may be NULL; host memory). */
+int ewk_tick_trace(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state, double* thr, double* rms);
+/* Drain the event queue into out[cap] (sorted by tick, then stream); returns the number of events
+ * (>= 0) or a negative status.  *dropped (may be NULL) counts events lost to a full queue. */
+int ewk_poll(ewk_ctx* ctx, ewk_event* out, int cap, int* dropped);
+int ewk_stream_status_get(ewk_ctx* ctx, int stream, ewk_stream_status* out);
+/* SoundBuffer.return_last_n_seconds (wakeword.py:498-513): the last n_samples visible samples. */
+int ewk_read_last(ewk_ctx* ctx, int stream, int64_t n_samples, float* out);
+/* word_audio of an event (wakeword.py:1105-1111) for the level-3 hand-off; EWK_ERR_STATE if overwritten. */
+int ewk_read_segment(ewk_ctx* ctx, int stream, int64_t seg_start, int64_t seg_len, float* out);
+/* Copy the dense per-stream results [n_streams] to host memory. */
+int ewk_stream_results(ewk_ctx* ctx, ewk_stream_result* out);
+/* Device pointer of that array (ewk_stream_result[n_streams]); or make the kernels write into a
+ * caller-owned device buffer instead (e.g. a registered NCCL send buffer). */
+int ewk_results_device_ptr(ewk_ctx* ctx, void** out);
+int ewk_set_results_buffer(ewk_ctx* ctx, void* device_ptr);
+/* Pinned host memory for asynchronous pushes. */
+int ewk_host_alloc(void** out, int64_t bytes);
+int ewk_host_free(void* p);
+/* Kernel launches issued by this context so far (for bench accounting). */
+int64_t ewk_launch_count(const ewk_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif
