@@ -231,6 +231,8 @@ def _declare_stream_protos(lib):
         "ewk_host_alloc": (C.c_int, [_p(vp), i64]),
         "ewk_host_free": (C.c_int, [vp]),
         "ewk_launch_count": (C.c_int64, [vp]),
+        "ewk_profile": (C.c_int, [vp, i32]),
+        "ewk_profile_read": (C.c_int, [vp, _p(C.c_double), _p(C.c_int64)]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -368,7 +370,17 @@ def _bank_methods():
     def launch_count(self):
         return int(self.lib.ewk_launch_count(self.h))
 
-    for f in (set_stream_params, push, tick, poll, status, read_last, read_segment, results, results_device_ptr,
+    def profile(self, enable=True):
+        self._ck(self.lib.ewk_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        ms = (C.c_double * 8)()
+        n = (C.c_int64 * 8)()
+        self._ck(self.lib.ewk_profile_read(self.h, ms, n))
+        names = ["ring_push", "tick_gate", "segment_queue", "segment_batch", "dense_score"]
+        return {names[i]: {"ms": ms[i], "launches": int(n[i])} for i in range(len(names))}
+
+    for f in (profile, profile_read, set_stream_params, push, tick, poll, status, read_last, read_segment, results, results_device_ptr,
               set_results_buffer, set_cuda_stream, launch_count):
         setattr(Context, f.__name__, f)
 

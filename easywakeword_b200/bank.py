@@ -1,0 +1,139 @@
+"""WakeWordBank — the batched ("multiroom") form of the reference's detector.
+
+The reference runs N rooms as N independent WakeWord objects and N threads
+(/root/reference/examples/multiroom_async.py:14-35).  Here N streams share one device context:
+rings in HBM, and per 100 ms tick of audio one K2 launch (adaptive threshold, is_silent, timing state
+machine for every stream) plus one persistent K3 launch (fused MFCC + template match on every candidate
+segment).  Host code only pushes PCM, ticks, and polls events; level 3 (Whisper) is handed
+`read_segment(event)` audio on the host, exactly where the reference calls `_transcribe_audio`
+(wakeword.py:1126-1128).
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .wakeword import WakeWord, analyze_reference_audio_duration, load_wav_16k
+
+TICK_SAMPLES = 1600
+EV_TIMEOUT, EV_SCORED = _lib.EV_TIMEOUT, _lib.EV_SCORED
+
+
+class WakeWordBank:
+    """N independent 16 kHz streams, one GPU.
+
+    templates: list of float32 arrays or WAV paths (slot i = templates[i]); every stream is scored
+    against all of them (best score wins) unless set_stream(..., template_first=, template_count=).
+    Timing defaults are the reference's (wakeword.py:38-41); speech_duration_min/max default to the
+    auto-calculated values of the first template (tests/test_wakeword_simulated.py:687-775)."""
+
+    def __init__(self, n_streams: int, templates: Sequence, *, device: int = 0, buffer_seconds: int = 10,
+                 pcm_dtype=np.int16, frame_size: int = TICK_SAMPLES, similarity_threshold: float = 75.0,
+                 pre_speech_silence: float = 0.8, speech_duration_min: Optional[float] = None,
+                 speech_duration_max: Optional[float] = None, post_speech_silence: float = 0.4,
+                 timeout: float = 30.0, max_push_seconds: float = 1.0, max_events: int = 0,
+                 cuda_stream: Optional[int] = None):
+        if n_streams < 1:
+            raise ValueError("n_streams must be at least 1")
+        if buffer_seconds <= 0:
+            raise ValueError("buffer_seconds must be positive")
+        if not templates:
+            raise ValueError("at least one template is required")
+        self.n_streams = n_streams
+        self.pcm_dtype = np.dtype(pcm_dtype)
+        if self.pcm_dtype not in (np.dtype(np.int16), np.dtype(np.float32)):
+            raise ValueError("pcm_dtype must be int16 or float32")
+        fmt = _lib.PCM_I16 if self.pcm_dtype == np.int16 else _lib.PCM_F32
+        slack = int(max_push_seconds * 16000) + 2 * max(frame_size, TICK_SAMPLES)
+        self.ctx = _lib.Context(device=device, n_streams=n_streams, ring_samples=buffer_seconds * 16000,
+                                slack_samples=slack, pcm_format=fmt, max_templates=max(1, len(templates)),
+                                max_events=max_events or max(4096, 2 * n_streams))
+        if cuda_stream is not None:
+            self.ctx.set_cuda_stream(cuda_stream)
+        self.templates = []
+        for slot, t in enumerate(templates):
+            audio = load_wav_16k(t) if isinstance(t, (str, bytes)) or hasattr(t, "__fspath__") else \
+                np.ascontiguousarray(t, dtype=np.float32)
+            self.ctx.set_template(slot, audio)
+            self.templates.append(audio)
+        if speech_duration_min is None:
+            d = analyze_reference_audio_duration(self.templates[0])
+            speech_duration_min = float(d) if d is not None else 0.3
+            if speech_duration_max is None:
+                speech_duration_max = 2.0 * speech_duration_min if d is not None else 2.0
+        elif speech_duration_max is None:
+            speech_duration_max = 2.0 * speech_duration_min
+        self.params = dict(frame_size=frame_size, similarity_threshold=similarity_threshold,
+                           pre_speech_silence=pre_speech_silence, speech_duration_min=speech_duration_min,
+                           speech_duration_max=speech_duration_max, post_speech_silence=post_speech_silence,
+                           timeout=float(timeout), template_first=0, template_count=len(templates))
+        self.ctx.set_stream_params(-1, **self.params)
+        self.ticks = 0
+        self.samples_pushed = 0
+
+    # ---- configuration
+    def set_stream(self, stream: int, **overrides):
+        """Per-stream parameters (any field of ewk_stream_params)."""
+        p = dict(self.params)
+        p.update(overrides)
+        self.ctx.set_stream_params(stream, **p)
+
+    # ---- data plane
+    def push(self, pcm, where=_lib.HOST):
+        """pcm[n_streams, n] in the bank's dtype: n new samples for every stream (K1 / direct H2D)."""
+        self.ctx.push(pcm, stream0=0, where=where)
+        self.samples_pushed += pcm[2] if isinstance(pcm, tuple) else pcm.shape[-1]
+
+    def tick(self, n_ticks: int = 1, trace: bool = False):
+        """n_ticks x 100 ms of the reference's poll loop for every stream (K2 + K3)."""
+        self.ticks += n_ticks
+        return self.ctx.tick(n_ticks, trace=trace)
+
+    def step(self, pcm, where=_lib.HOST):
+        """push + as many ticks as the pushed audio covers."""
+        n = pcm[2] if isinstance(pcm, tuple) else pcm.shape[-1]
+        self.push(pcm, where)
+        due = self.samples_pushed // TICK_SAMPLES - self.ticks
+        if due > 0:
+            self.tick(due)
+
+    def poll(self) -> np.ndarray:
+        """Structured array of events since the last poll, sorted by (tick, stream):
+        kind 2 = level-2 evaluation (score, matched), kind 1 = timeout."""
+        return self.ctx.poll()
+
+    def results(self) -> np.ndarray:
+        return self.ctx.results()
+
+    def read_segment(self, event) -> np.ndarray:
+        """word_audio of a level-2 event as float32 (what level 3 transcribes)."""
+        return self.ctx.read_segment(int(event["stream"]), int(event["seg_start"]), int(event["seg_len"]))
+
+    def status(self, stream: int):
+        return self.ctx.status(stream)
+
+    # ---- convenience: the reference's callback surface over the whole bank
+    def run(self, blocks: Iterable[np.ndarray], on_match: Optional[Callable] = None, transcriber=None,
+            textword: str = "", numberofwords: int = 1):
+        """Feed an iterable of [n_streams, n] blocks; for every level-2 match call
+        on_match(stream, tick, score, text) where text is the level-3 confirmation (None without a
+        transcriber).  Returns the list of all events."""
+        log = []
+        for blk in blocks:
+            self.step(blk)
+            ev = self.poll()
+            for e in ev:
+                log.append(e.copy())
+                if e["kind"] != EV_SCORED or not e["matched"] or on_match is None:
+                    continue
+                text = None
+                if transcriber is not None:
+                    audio = WakeWord.prepare_for_transcription(self.read_segment(e).astype(np.float64))
+                    text = transcriber.transcribe(audio)
+                on_match(int(e["stream"]), int(e["tick"]), float(e["score"]), text)
+        return log
+
+    def close(self):
+        self.ctx.close()

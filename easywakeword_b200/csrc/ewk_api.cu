@@ -163,9 +163,12 @@ int ewk_ctx::launch_segments(const SegDesc* d_segs, int n_seg, int max_frames, l
         CK(b_ws.ensure(sizeof(float) * (size_t)spill_frames * (LM_STRIDE + N_MFCC)));
         ws = (float*)b_ws.p;
     }
+    cudaEvent_t pe = prof_begin(3);
     segment_mfcc_match_kernel<<<n_seg, SEG_THREADS, seg_smem_bytes(cap), stream>>>(
         d_tables, d_segs, cap, ws, d_tmpl, n_tmpl, tmpl_first, threshold, d_feat, d_frames, d_scores, d_matched);
+    prof_end(pe, 3);
     CK(cudaGetLastError());
+    launches++;
     return EWK_OK;
 }
 
@@ -390,6 +393,9 @@ void ewk_ctx::release_streams() {
     bank = BankView{};
     own_results = nullptr;
     b_stage.free(); b_trace.free(); b_read.free();
+    for (auto& p : prof_pairs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : prof_free) cudaEventDestroy(e);
+    prof_pairs.clear(); prof_free.clear();
 }
 
 static int need_streams(ewk_ctx* ctx, const char* who) {
@@ -478,8 +484,10 @@ extern "C" int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pc
         }
         const int per = esz == 2 ? 8 : 4;
         dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (n / per + 255) / 256)), (unsigned)n_streams);
+        cudaEvent_t pe = ctx->prof_begin(0);
         if (B.fmt == 1) ring_push_kernel<short><<<grid, 256, 0, ctx->stream>>>(B, stream0, (const short*)d_src, d_stride, (int)n);
         else ring_push_kernel<float><<<grid, 256, 0, ctx->stream>>>(B, stream0, (const float*)d_src, d_stride, (int)n);
+        ctx->prof_end(pe, 0);
         CK(cudaGetLastError());
         ctx->launches++;
     }
@@ -507,11 +515,15 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         tr.silent = (unsigned char*)(base + cells * 16);
         tr.state = (unsigned char*)(base + cells * 17);
     }
+    cudaEvent_t pe = ctx->prof_begin(1);
     tick_gate_kernel<<<B.n_streams, GATE_THREADS, sizeof(double) * (size_t)B.chunk_cap, ctx->stream>>>(B, n_ticks, tr);
+    ctx->prof_end(pe, 1);
     CK(cudaGetLastError());
     const int grid = std::max(1, ctx->sm_count);
+    pe = ctx->prof_begin(2);
     segment_queue_kernel<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ctx->stream>>>(
         ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
+    ctx->prof_end(pe, 2);
     CK(cudaGetLastError());
     ctx->launches += 2;
     // host mirrors (audio clock): V after these ticks, given what has been pushed
@@ -683,4 +695,57 @@ extern "C" int ewk_host_alloc(void** out, int64_t bytes) {
 extern "C" int ewk_host_free(void* p) {
     if (!p) return EWK_ERR_ARG;
     return cudaFreeHost(p) == cudaSuccess ? EWK_OK : EWK_ERR_CUDA;
+}
+
+// ==========================================================================================
+// per-kernel event timing
+// ==========================================================================================
+cudaEvent_t ewk_ctx::prof_begin(int) {
+    if (!prof_on) return nullptr;
+    cudaEvent_t e;
+    if (!prof_free.empty()) { e = prof_free.back(); prof_free.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    cudaEventRecord(e, stream);
+    return e;
+}
+
+void ewk_ctx::prof_end(cudaEvent_t a, int cls) {
+    if (!a) return;
+    cudaEvent_t b;
+    if (!prof_free.empty()) { b = prof_free.back(); prof_free.pop_back(); }
+    else if (cudaEventCreate(&b) != cudaSuccess) { prof_free.push_back(a); return; }
+    cudaEventRecord(b, stream);
+    prof_pairs.push_back({a, b, cls});
+}
+
+int ewk_ctx::prof_collect() {
+    ewk_ctx* ctx = this;
+    CK(cudaStreamSynchronize(stream));
+    for (auto& p : prof_pairs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { prof_ms[p.cls] += ms; prof_n[p.cls]++; }
+        prof_free.push_back(p.a);
+        prof_free.push_back(p.b);
+    }
+    prof_pairs.clear();
+    return EWK_OK;
+}
+
+extern "C" int ewk_profile(ewk_ctx* ctx, int enable) {
+    if (!ctx) return EWK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ctx->prof_collect();
+    if (rc) return rc;
+    for (int i = 0; i < 8; i++) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
+    ctx->prof_on = enable != 0;
+    return EWK_OK;
+}
+
+extern "C" int ewk_profile_read(ewk_ctx* ctx, double* ms, int64_t* launches) {
+    if (!ctx || !ms || !launches) return EWK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ctx->prof_collect();
+    if (rc) return rc;
+    for (int i = 0; i < 8; i++) { ms[i] = ctx->prof_ms[i]; launches[i] = ctx->prof_n[i]; ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
+    return EWK_OK;
 }

@@ -55,6 +55,16 @@ struct ewk_ctx {
     std::vector<long long> h_written;      // host mirror of StreamState.written
     std::vector<long long> h_visible_lb;   // lower bound of StreamState.visible (audio-clock overrun check)
     std::vector<long long> h_tick;
+    // per-kernel event timing (ewk_profile)
+    bool prof_on = false;
+    struct ProfPair { cudaEvent_t a, b; int cls; };
+    std::vector<ProfPair> prof_pairs;
+    std::vector<cudaEvent_t> prof_free;
+    double prof_ms[8] = {0};
+    long long prof_n[8] = {0};
+    cudaEvent_t prof_begin(int cls);
+    void prof_end(cudaEvent_t a, int cls);
+    int prof_collect();
     int init_streams();
     void release_streams();
     int launch_segments(const ewk::SegDesc* d_segs, int n_seg, int max_frames, long long spill_frames, int n_tmpl,

@@ -170,6 +170,13 @@ int ewk_host_alloc(void** out, int64_t bytes);
 int ewk_host_free(void* p);
 /* Kernel launches issued by this context so far (for bench accounting). */
 int64_t ewk_launch_count(const ewk_ctx* ctx);
+/* Per-kernel device timing with CUDA events on the context's stream.  ewk_profile(ctx, 1) starts
+ * bracketing every kernel launch with an event pair; ewk_profile_read synchronises and returns, per
+ * kernel class (0 ring_push, 1 tick_gate, 2 segment_queue, 3 segment_batch, 4 dense_score), the summed
+ * milliseconds and the number of launches since profiling was enabled, then resets the sums. */
+enum { EWK_PROF_CLASSES = 8 };
+int ewk_profile(ewk_ctx* ctx, int enable);
+int ewk_profile_read(ewk_ctx* ctx, double* ms, int64_t* launches);
 
 #ifdef __cplusplus
 }

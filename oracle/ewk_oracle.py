@@ -100,10 +100,10 @@ class WordMatcherOracle:
 class SoundBufferOracle:
     """Restates SoundBuffer (wakeword.py:405-517) minus the PortAudio stream.
 
-    The per-sample Python loop of _add_sound_to_buffer (:461-465) is written as slice
-    assignments (same stores, same order); _adjust_silence_threshold (:472-486) keeps the
-    reference's expression per chunk unless fast=True, which batches the chunk RMS with one
-    reshape (bit-identical: numpy reduces each contiguous row with the same pairwise sum).
+    fast=False follows the reference statement by statement (per-sample ring loop :461-465,
+    per-chunk RMS loop :479-482) and is what the CPU baseline times; fast=True writes the ring
+    with slice assignments and batches the chunk RMS with one reshape — bit-identical results
+    (numpy reduces each contiguous row with the same pairwise sum), checked in tests.
     """
 
     FREQUENCY = FREQUENCY
@@ -125,6 +125,16 @@ class SoundBufferOracle:
             self.frame_size = len(new_data)
         n = len(new_data)
         R = self.buffer_length
+        if not self.fast:                # the reference's own per-sample loop (:461-465)
+            for sample in new_data:
+                self.data[self.pointer] = sample
+                self.pointer = (self.pointer + 1) % R
+                if self.samples_collected < R:
+                    self.samples_collected += 1
+            if self.samples_collected < R:
+                return
+            self._adjust_silence_threshold()
+            return
         if n >= R:                       # only the last R samples survive the loop
             keep = new_data[n - R:]
             start = (self.pointer + n - R) % R
@@ -203,7 +213,7 @@ def segment_bounds(sound_start_time, sound_end_time, current_time):
 
 
 def detect_stream(stream, template, *, block=512, buffer_seconds=10, max_ticks=None,
-                  restart_on_timeout=True, fast=False, matcher=None, keep_audio=False, **params):
+                  restart_on_timeout=True, fast=False, matcher=None, keep_audio=False, timing=None, **params):
     """SoundBuffer + WordMatcher + WakeWord._wait_for_buffer/_detect_word (wakeword.py:1002-1007,
     1036-1159, listen loop 1202-1211) over one stream under the audio clock.
 
@@ -257,6 +267,9 @@ def detect_stream(stream, template, *, block=512, buffer_seconds=10, max_ticks=N
         while not buf.is_buffer_full():                                 # :1002-1007
             sleep()
         full_tick = k
+        if timing is not None:
+            import time as _time
+            timing["t_full"] = _time.perf_counter()
         while True:                                                     # listen loop :1205-1211
             state = WAITING                                             # :1048
             silence_start_time = sound_start_time = sound_end_time = None
@@ -319,6 +332,10 @@ def detect_stream(stream, template, *, block=512, buffer_seconds=10, max_ticks=N
                 break
     except _Exhausted:
         pass
+    if timing is not None:
+        import time as _time
+        timing["t_end"] = _time.perf_counter()
+        timing["steady_ticks"] = k - (full_tick or k)
     return {
         "full_tick": full_tick,
         "trace_tick": np.asarray(t_tick, dtype=np.int64),
