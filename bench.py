@@ -187,7 +187,9 @@ def run_ours(args):
     pool_host = torch.from_numpy(pool_pin.array)
     pool_dev = pool_host.to(dev, non_blocking=False)
 
-    stream = torch.cuda.current_stream(dev)
+    # a real (non-legacy) stream: libewk launches on it and torch.cuda.Event times it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     bank = WakeWordBank(n, [word], device=local_rank, buffer_seconds=RING_SECONDS, pcm_dtype=np.int16,
                         max_push_seconds=STEP_SECONDS, cuda_stream=stream.cuda_stream, max_events=1 << 17, **PARAMS)
     ctx = bank.ctx

@@ -358,7 +358,7 @@ int ewk_ctx::init_streams() {
     CK(cudaMemsetAsync(bank.ring, 0, esz * (size_t)n * bank.P, stream));          // np.zeros   wakeword.py:428
     CK(cudaMalloc(&bank.st, sizeof(StreamState) * (size_t)n));
     CK(cudaMalloc(&bank.prm, sizeof(StreamParams) * (size_t)n));
-    CK(cudaMalloc(&bank.chunk_ms, sizeof(double) * (size_t)n * chunk_cap));
+    CK(cudaMalloc(&bank.chunk_ms, sizeof(double) * (size_t)n * 2 * chunk_cap));   // per stream: ms[cap] ++ sorted[cap]
     CK(cudaMalloc(&bank.events, sizeof(EventRec) * (size_t)bank.max_events));
     CK(cudaMalloc(&bank.ev_count, sizeof(int) * 4));
     CK(cudaMemsetAsync(bank.ev_count, 0, sizeof(int) * 4, stream));
@@ -381,6 +381,7 @@ int ewk_ctx::init_streams() {
     h_written.assign(n, 0);
     h_visible_lb.assign(n, 0);
     h_tick.assign(n, 0);
+    h_frame_size.assign(n, 0);
     CK(cudaFuncSetAttribute(segment_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
     return EWK_OK;
@@ -396,6 +397,15 @@ void ewk_ctx::release_streams() {
     for (auto& p : prof_pairs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : prof_free) cudaEventDestroy(e);
     prof_pairs.clear(); prof_free.clear();
+}
+
+int ewk_ctx::gate_chunks() const {
+    int m = 1;
+    for (int s = 0; s < bank.n_streams; s++) {
+        const int fs = h_frame_size[s] > 0 ? h_frame_size[s] : h_prm[s].frame_size;
+        if (fs > 0) m = std::max(m, std::min(bank.chunk_cap, bank.R / fs));
+    }
+    return m;
 }
 
 static int need_streams(ewk_ctx* ctx, const char* who) {
@@ -494,7 +504,10 @@ extern "C" int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pc
     ring_commit_kernel<<<(n_streams + 255) / 256, 256, 0, ctx->stream>>>(B, stream0, n_streams, (int)n);
     CK(cudaGetLastError());
     ctx->launches++;
-    for (int s = stream0; s < stream0 + n_streams; s++) ctx->h_written[s] += n;
+    for (int s = stream0; s < stream0 + n_streams; s++) {
+        ctx->h_written[s] += n;
+        if (ctx->h_frame_size[s] == 0) ctx->h_frame_size[s] = ctx->h_prm[s].frame_size > 0 ? ctx->h_prm[s].frame_size : (int)n;
+    }
     return EWK_OK;
 }
 
@@ -515,8 +528,14 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         tr.silent = (unsigned char*)(base + cells * 16);
         tr.state = (unsigned char*)(base + cells * 17);
     }
+    const int smem_chunks = ctx->gate_chunks();
     cudaEvent_t pe = ctx->prof_begin(1);
-    tick_gate_kernel<<<B.n_streams, GATE_THREADS, sizeof(double) * (size_t)B.chunk_cap, ctx->stream>>>(B, n_ticks, tr);
+    for (int done = 0; done < n_ticks; done += GATE_MAX_TICKS) {
+        const int nt = std::min(GATE_MAX_TICKS, n_ticks - done);
+        tick_gate_kernel<<<B.n_streams, GATE_THREADS, sizeof(double) * 3 * (size_t)smem_chunks, ctx->stream>>>(
+            B, nt, tr, n_ticks, done, smem_chunks);
+        ctx->launches++;
+    }
     ctx->prof_end(pe, 1);
     CK(cudaGetLastError());
     const int grid = std::max(1, ctx->sm_count);
@@ -525,13 +544,13 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
     ctx->prof_end(pe, 2);
     CK(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 1;
     // host mirrors (audio clock): V after these ticks, given what has been pushed
     for (int s = 0; s < B.n_streams; s++) {
         ctx->h_tick[s] += n_ticks;
         const StreamParams& p = ctx->h_prm[s];
         if (p.live) { ctx->h_visible_lb[s] = ctx->h_written[s]; continue; }
-        const int fs = p.frame_size;       // unknown (first-push latch) -> keep the conservative bound
+        const int fs = ctx->h_frame_size[s];
         if (fs > 0) {
             const long long v = std::min((ctx->h_tick[s] * TICK / fs) * fs, (ctx->h_written[s] / fs) * fs);
             ctx->h_visible_lb[s] = std::max(ctx->h_visible_lb[s], v);

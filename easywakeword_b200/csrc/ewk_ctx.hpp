@@ -55,6 +55,8 @@ struct ewk_ctx {
     std::vector<long long> h_written;      // host mirror of StreamState.written
     std::vector<long long> h_visible_lb;   // lower bound of StreamState.visible (audio-clock overrun check)
     std::vector<long long> h_tick;
+    std::vector<int> h_frame_size;         // latched frame size per stream (0: no push yet)
+    int gate_chunks() const;               // largest R / frame_size in use
     // per-kernel event timing (ewk_profile)
     bool prof_on = false;
     struct ProfPair { cudaEvent_t a, b; int cls; };

@@ -135,41 +135,73 @@ __global__ void ring_commit_kernel(BankView B, int stream0, int n_streams, int n
 // ------------------------------------------------------------------------------------ K2 helpers
 // Sum of squares of absolute samples [a0, a0+len) of one stream, in double.  int16 sums are in
 // integer units (exact); the caller scales by 2^-30.  Whole warp cooperates; result in every lane.
+// The aligned body issues four independent 16-byte loads per lane before reducing.
+__device__ __forceinline__ long long sq8(const int4 q) {
+    const int w[4] = {q.x, q.y, q.z, q.w};
+    long long out = 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int lo = (short)(w[u] & 0xffff), hi = w[u] >> 16;
+        // two squares of 15-bit magnitudes fit in 31 bits; accumulate pairs in 64 bits
+        out += (long long)(unsigned)(lo * lo) + (long long)(unsigned)(hi * hi);
+    }
+    return out;
+}
+
 __device__ __forceinline__ double warp_sumsq(const BankView& B, int s, long long a0, int len, int lane) {
     double acc = 0.0;
     if (len <= 0) return 0.0;
-    int p0 = (int)(a0 % B.P);
+    const int p0 = (int)(a0 % B.P);
     if (B.fmt == 1) {
         const short* ring = (const short*)B.ring + (size_t)s * B.P;
-        // 16-byte body when aligned and not wrapping; scalar head/tail otherwise
         int i = 0;
+        long long iacc = 0;
         if ((p0 & 7) == 0 && p0 + len <= B.P) {
             const int nv = len >> 3;
             const int4* v = reinterpret_cast<const int4*>(ring + p0);
-            long long iacc = 0;
-            for (int k = lane; k < nv; k += 32) {
-                const int4 q = __ldg(v + k);
-                const int w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int lo = (short)(w[u] & 0xffff), hi = w[u] >> 16;
-                    iacc += (long long)(lo * lo) + (long long)(hi * hi);
-                }
+            int k = lane;
+            for (; k + 96 < nv; k += 128) {
+                const int4 q0 = __ldg(v + k), q1 = __ldg(v + k + 32), q2 = __ldg(v + k + 64), q3 = __ldg(v + k + 96);
+                iacc += sq8(q0) + sq8(q1) + sq8(q2) + sq8(q3);
             }
-            acc = (double)iacc;
+            for (; k < nv; k += 32) iacc += sq8(__ldg(v + k));
             i = nv << 3;
         }
-        long long iacc = 0;
         for (int k = i + lane; k < len; k += 32) {
             int p = p0 + k;
             if (p >= B.P) p -= B.P;
             const int q = ring[p];
             iacc += (long long)(q * q);
         }
-        acc += (double)iacc;
+        acc = (double)iacc;
     } else {
         const float* ring = (const float*)B.ring + (size_t)s * B.P;
-        for (int k = lane; k < len; k += 32) {
+        int i = 0;
+        if ((p0 & 3) == 0 && p0 + len <= B.P) {
+            const int nv = len >> 2;
+            const float4* v = reinterpret_cast<const float4*>(ring + p0);
+            double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = lane;
+            for (; k + 96 < nv; k += 128) {
+                const float4 q0 = __ldg(v + k), q1 = __ldg(v + k + 32), q2 = __ldg(v + k + 64), q3 = __ldg(v + k + 96);
+                acc = fma((double)q0.x, (double)q0.x, acc); acc = fma((double)q0.y, (double)q0.y, acc);
+                acc = fma((double)q0.z, (double)q0.z, acc); acc = fma((double)q0.w, (double)q0.w, acc);
+                a1 = fma((double)q1.x, (double)q1.x, a1); a1 = fma((double)q1.y, (double)q1.y, a1);
+                a1 = fma((double)q1.z, (double)q1.z, a1); a1 = fma((double)q1.w, (double)q1.w, a1);
+                a2 = fma((double)q2.x, (double)q2.x, a2); a2 = fma((double)q2.y, (double)q2.y, a2);
+                a2 = fma((double)q2.z, (double)q2.z, a2); a2 = fma((double)q2.w, (double)q2.w, a2);
+                a3 = fma((double)q3.x, (double)q3.x, a3); a3 = fma((double)q3.y, (double)q3.y, a3);
+                a3 = fma((double)q3.z, (double)q3.z, a3); a3 = fma((double)q3.w, (double)q3.w, a3);
+            }
+            for (; k < nv; k += 32) {
+                const float4 q0 = __ldg(v + k);
+                acc = fma((double)q0.x, (double)q0.x, acc); acc = fma((double)q0.y, (double)q0.y, acc);
+                acc = fma((double)q0.z, (double)q0.z, acc); acc = fma((double)q0.w, (double)q0.w, acc);
+            }
+            acc += (a1 + a2) + a3;
+            i = nv << 2;
+        }
+        for (int k = i + lane; k < len; k += 32) {
             int p = p0 + k;
             if (p >= B.P) p -= B.P;
             const double x = (double)ring[p];
@@ -195,24 +227,74 @@ __device__ __forceinline__ double warp_chunk_ms(const BankView& B, int s, long l
     return ss / (double)fs;                           // np.mean(frame**2)            wakeword.py:481
 }
 
-// np.percentile(rms, 25) with numpy's default 'linear' method and its _lerp, on sqrt(ms[0..n)).
-// Block-wide rank counting; result valid in thread 0.  sel[2] is shared scratch.
-__device__ __forceinline__ double block_percentile25_rms(const double* ms, int n, double* sel, int tid) {
-    const double vi = (double)n * 0.25 - 0.25;        // n*q + (alpha + q*(1-alpha-beta)) - 1, alpha=beta=1
-    const int k_lo = (int)floor(vi);
-    const int k_hi = min(k_lo + 1, n - 1);
+constexpr int GATE_WARPS = GATE_THREADS / 32;
+constexpr int GATE_MAX_TICKS = 32;     // ticks per launch (the host splits longer requests)
+constexpr int GATE_MAXP = 12;          // chunk pieces planned per tick; more -> the tick is "heavy"
+
+// block-wide sum of a small per-thread int pair (packed lo/hi 16+16 bits is too narrow: use two ints)
+__device__ __forceinline__ int2 block_sum2(int a, int b, int* red, int tid) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); }
+    __syncthreads();                                   // red[] free again
+    if ((tid & 31) == 0) { red[(tid >> 5) * 2] = a; red[(tid >> 5) * 2 + 1] = b; }
+    __syncthreads();
+    int ra = 0, rb = 0;
+#pragma unroll
+    for (int w = 0; w < GATE_WARPS; w++) { ra += red[w * 2]; rb += red[w * 2 + 1]; }
+    return make_int2(ra, rb);
+}
+
+// sorted[] <- ascending order of ms[0..n) (rank by counting; ties broken by index).  Block-wide.
+__device__ __forceinline__ void block_sort_build(const double* ms, double* sorted, int n, int tid) {
     for (int i = tid; i < n; i += GATE_THREADS) {
-        const long long vi_bits = __double_as_longlong(ms[i]);
+        const long long vi = __double_as_longlong(ms[i]);
         int r = 0;
         for (int j = 0; j < n; j++) {
             const long long vj = __double_as_longlong(ms[j]);
-            r += (vj < vi_bits) || (vj == vi_bits && j < i);
+            r += (vj < vi) || (vj == vi && j < i);
         }
-        if (r == k_lo) sel[0] = ms[i];
-        if (r == k_hi) sel[1] = ms[i];
+        sorted[r] = ms[i];
     }
     __syncthreads();
-    const double a = sqrt(sel[0]), b = sqrt(sel[1]);
+}
+
+// Replace one occurrence of `oldv` by `newv` in the ascending array S[0..n) (block-wide; T is a
+// second buffer; returns with the result in S).  Non-negative doubles order like their bit patterns.
+__device__ __forceinline__ void block_sorted_replace(double*& S, double*& T, int n, double oldv, double newv,
+                                                     int* red, int tid) {
+    const long long bo = __double_as_longlong(oldv), bn = __double_as_longlong(newv);
+    if (bo == bn) return;
+    int lo = 0, ln = 0;
+    for (int i = tid; i < n; i += GATE_THREADS) {
+        const long long v = __double_as_longlong(S[i]);
+        lo += v < bo;
+        ln += v < bn;
+    }
+    const int2 c = block_sum2(lo, ln, red, tid);
+    const int pos_old = c.x;
+    const int pos_new = c.y - (bo < bn ? 1 : 0);       // index in the array with `oldv` removed
+    for (int i = tid; i < n; i += GATE_THREADS) {
+        double v;
+        if (i == pos_new) v = newv;
+        else {
+            // index i of the new array <- index of the old array
+            int r = i > pos_new ? i - 1 : i;           // position in the "removed" array
+            int src = r >= pos_old ? r + 1 : r;
+            v = S[src];
+        }
+        T[i] = v;
+    }
+    __syncthreads();
+    double* t = S; S = T; T = t;
+}
+
+// np.percentile(rms, 25), numpy's default 'linear' method and its _lerp, from the ascending
+// mean-square array (sqrt is monotone: order statistics of the RMS are sqrt of those of the ms).
+__device__ __forceinline__ double percentile25_rms_sorted(const double* S, int n) {
+    const double vi = (double)n * 0.25 - 0.25;        // n*q + (alpha + q*(1-alpha-beta)) - 1, alpha=beta=1
+    const int k_lo = (int)floor(vi);
+    const int k_hi = min(k_lo + 1, n - 1);
+    const double a = sqrt(S[k_lo]), b = sqrt(S[k_hi]);
     const double t = vi - (double)k_lo;
     const double diff = __dsub_rn(b, a);
     double r = __dadd_rn(a, __dmul_rn(diff, t));
@@ -220,99 +302,158 @@ __device__ __forceinline__ double block_percentile25_rms(const double* ms, int n
     return r;
 }
 
+struct GatePlan {
+    long long V[GATE_MAX_TICKS];                    // samples visible at each tick
+    double pv[GATE_MAX_TICKS][GATE_MAXP + 1];       // piece values; [GATE_MAXP] = recent-window sum of squares
+    short pc[GATE_MAX_TICKS][GATE_MAXP];            // chunk index of each piece
+    unsigned char np[GATE_MAX_TICKS];               // chunk pieces; 255: heavy tick (all chunks, done in phase 2)
+    unsigned char alias[GATE_MAX_TICKS];            // recent window == piece 0 (frame_size 1600, aligned)
+    unsigned char full[GATE_MAX_TICKS];
+    int flat0[GATE_MAX_TICKS + 1];                  // prefix offsets of (tick, piece) work items
+};
+
 // ------------------------------------------------------------------------------------ K2
-// One CTA per stream, n_ticks sequential ticks.
-__global__ void __launch_bounds__(GATE_THREADS)
-tick_gate_kernel(BankView B, int n_ticks, TraceView tr) {
+// One CTA per stream.  Phase 0 plans which sample ranges each of the n_ticks ticks needs; phase 1
+// sums them all in parallel (the only HBM traffic, every new sample read once with 16-byte loads);
+// phase 2 replays the ticks in order: chunk updates into an incrementally maintained sorted array,
+// percentile, threshold, is_silent, state machine.
+__global__ void __launch_bounds__(GATE_THREADS, 8)
+tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int trace_off, int smem_chunks) {
     extern __shared__ double sm_d[];
-    double* ms = sm_d;                               // [chunk_cap]
-    __shared__ double piece[GATE_THREADS / 32];
-    __shared__ double sel[2];
-    __shared__ double recent_ss;
+    double* ms = sm_d;                               // [n_chunks] storage order
+    double* SA = ms + smem_chunks;                   // sorted buffers
+    double* SB = SA + smem_chunks;
+    __shared__ GatePlan plan;
+    __shared__ int red[2 * GATE_WARPS];
 
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     StreamState st = B.st[s];
     const StreamParams prm = B.prm[s];
     const int fs = st.frame_size;
     const int n_chunks = fs > 0 ? B.R / fs : 0;
-    double* g_ms = B.chunk_ms + (size_t)s * B.chunk_cap;
-    const bool use_chunks = n_chunks > 0 && n_chunks <= B.chunk_cap;
+    double* g_ms = B.chunk_ms + (size_t)s * 2 * B.chunk_cap;
+    double* g_sorted = g_ms + B.chunk_cap;
+    const bool use_chunks = n_chunks > 0 && n_chunks <= B.chunk_cap && n_chunks <= smem_chunks;
     if (use_chunks && st.chunks_valid)
-        for (int i = tid; i < n_chunks; i += GATE_THREADS) ms[i] = g_ms[i];
-    __syncthreads();
-    unsigned evflag = 0;
+        for (int i = tid; i < n_chunks; i += GATE_THREADS) { ms[i] = g_ms[i]; SA[i] = g_sorted[i]; }
 
+    // ---- phase 0: plan (thread 0)
+    if (tid == 0) {
+        long long Vp = st.visible;
+        long long k = st.tick;
+        int valid = st.chunks_valid;
+        int flat = 0;
+        for (int j = 0; j < n_ticks; j++) {
+            k++;
+            long long V = Vp;
+            if (fs > 0) {
+                const long long avail = (st.written / fs) * fs;
+                V = prm.live ? st.written : min((k * TICK / fs) * fs, avail);
+                if (V < Vp) V = Vp;
+            }
+            plan.V[j] = V;
+            const bool full = fs > 0 && V >= B.R;                       // is_buffer_full   wakeword.py:515-517
+            plan.full[j] = full;
+            int np = 0;
+            plan.alias[j] = 0;
+            if (full && use_chunks && V > Vp) {
+                const long long dv = V - Vp;
+                if (!valid || dv >= B.R) np = 255;
+                else {
+                    // storage-order chunks touched by the new samples: logical positions [q0, q0+dv) mod R
+                    const int q0 = (int)(Vp % B.R);
+                    const long long e = q0 + dv;
+                    const int e1 = (int)min(e, (long long)B.R);
+                    const int c1 = q0 / fs;
+                    const int n1 = (e1 - 1) / fs - c1 + 1;
+                    const int n2 = e > B.R ? (int)((e - B.R - 1) / fs) + 1 : 0;
+                    for (int i = 0; i < n1 + n2 && np != 255; i++) {
+                        const int c = i < n1 ? c1 + i : i - n1;
+                        if (c >= n_chunks) continue;                    // the tail R - n_chunks*fs is in no chunk
+                        if (np == GATE_MAXP) { np = 255; break; }
+                        plan.pc[j][np++] = (short)c;
+                    }
+                    if (np == 1 && fs == TICK && dv == TICK && (q0 % TICK) == 0 && B.R >= TICK) plan.alias[j] = 1;
+                }
+                valid = 1;
+            }
+            plan.np[j] = (unsigned char)np;
+            plan.flat0[j] = flat;
+            flat += (np == 255 ? 0 : np) + (fs > 0 && !plan.alias[j] ? 1 : 0);
+            Vp = V;
+        }
+        plan.flat0[n_ticks] = flat;
+    }
+    __syncthreads();
+
+    // ---- phase 1: every planned range, one warp per piece
+    const int nrec = min(TICK, B.R);
+    {
+        const int total = plan.flat0[n_ticks];
+        int j = 0;
+        for (int f = warp; f < total; f += GATE_WARPS) {
+            while (plan.flat0[j + 1] <= f) j++;
+            const int i = f - plan.flat0[j];
+            const int np = plan.np[j] == 255 ? 0 : plan.np[j];
+            const long long V = plan.V[j];
+            if (i < np) {
+                const double v = warp_chunk_ms(B, s, V, fs, plan.pc[j][i], lane);
+                if (lane == 0) plan.pv[j][i] = v;
+            } else {
+                // RMS window of is_silent: the last min(1600, R) samples; zeros before the stream began
+                const long long a0 = V - nrec;
+                const double ss = warp_sumsq(B, s, a0 < 0 ? 0 : a0, (int)(a0 < 0 ? V : nrec), lane);
+                if (lane == 0) plan.pv[j][GATE_MAXP] = ss;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: replay the ticks in order
+    unsigned evflag = 0;
+    int valid = st.chunks_valid;
     for (int j = 0; j < n_ticks; j++) {
         const long long k = st.tick + 1;
-        long long V = st.visible;
-        if (fs > 0) {
-            const long long avail = (st.written / fs) * fs;
-            V = prm.live ? st.written : min((k * TICK / fs) * fs, avail);
-            if (V < st.visible) V = st.visible;
-        }
-        const bool full = fs > 0 && V >= B.R;                          // is_buffer_full   wakeword.py:515-517
-
-        // ---- adaptive threshold (wakeword.py:467-486): only once the ring has been filled
-        if (full && use_chunks && V > st.visible) {
-            const long long dv = V - st.visible;
-            // storage-order chunks touched by the new samples: logical positions [q0, q0+dv) mod R
-            int c1 = 0, n1 = n_chunks, n2 = 0;
-            if (st.chunks_valid && dv < B.R) {
-                const int q0 = (int)(st.visible % B.R);
-                const long long e = q0 + dv;                            // exclusive end, unwrapped
-                const int e1 = (int)min(e, (long long)B.R);
-                c1 = q0 / fs;
-                n1 = (e1 - 1) / fs - c1 + 1;
-                if (e > B.R) n2 = (int)((e - B.R - 1) / fs) + 1;        // wrapped part starts at chunk 0
-            }
-            for (int i = warp; i < n1 + n2; i += GATE_THREADS / 32) {
-                const int c = i < n1 ? c1 + i : i - n1;
-                if (c < n_chunks) {                                     // the tail R - n_chunks*fs is in no chunk
-                    const double v = warp_chunk_ms(B, s, V, fs, c, lane);
-                    if (lane == 0) ms[c] = v;
-                }
+        const long long V = plan.V[j];
+        const bool full = plan.full[j];
+        const int np = plan.np[j];
+        if (np == 255) {
+            // heavy tick (first full ring, or a jump of a whole ring): every chunk from samples, then sort
+            for (int c = warp; c < n_chunks; c += GATE_WARPS) {
+                const double v = warp_chunk_ms(B, s, V, fs, c, lane);
+                if (lane == 0) ms[c] = v;
             }
             __syncthreads();
-            const double p25 = block_percentile25_rms(ms, n_chunks, sel, tid);
-            if (tid == 0) {
-                const double nt = __dmul_rn(p25, 1.5);                 // wakeword.py:485
+            block_sort_build(ms, SA, n_chunks, tid);
+            valid = 1;
+        } else {
+            for (int i = 0; i < np; i++) {
+                const int c = plan.pc[j][i];
+                const double nv = plan.pv[j][i];
+                const double ov = ms[c];
+                __syncthreads();
+                block_sorted_replace(SA, SB, n_chunks, ov, nv, red, tid);
+                if (tid == 0) ms[c] = nv;
+                __syncthreads();
+            }
+        }
+        if (tid == 0) {
+            if (np != 0) {
+                const double p25 = percentile25_rms_sorted(SA, n_chunks);
+                const double nt = __dmul_rn(p25, 1.5);                  // wakeword.py:485
                 st.thr = nt > prm.min_threshold ? nt : prm.min_threshold;   // max(new, MIN_THRESHOLD)  :486
             }
-            st.chunks_valid = 1;
-            __syncthreads();
-        }
-
-        // ---- is_silent (wakeword.py:488-496): RMS of the last min(1600, R) samples < threshold
-        int silent = 1;
-        double rms = 0.0;
-        if (fs > 0) {
-            const int nrec = min(TICK, B.R);
-            // before `nrec` samples exist the reference's ring holds zeros there
-            const long long a0 = V - nrec;
-            const int len = (int)(a0 < 0 ? V : nrec);
-            const long long a1 = a0 < 0 ? 0 : a0;
-            // split the window over the CTA's warps
-            const int per = (len + GATE_THREADS / 32 - 1) / (GATE_THREADS / 32);
-            const int per8 = (per + 7) & ~7;
-            const int b = warp * per8;
-            const int l = max(0, min(per8, len - b));
-            const double part = warp_sumsq(B, s, a1 + b, l, lane);
-            if (lane == 0) piece[warp] = part;
-            __syncthreads();
-            if (tid == 0) {
-                double ss = 0.0;
-                for (int w = 0; w < GATE_THREADS / 32; w++) ss += piece[w];
-                if (B.fmt == 1) ss *= (1.0 / 1073741824.0);
+            // ---- is_silent (wakeword.py:488-496)
+            int silent = 1;
+            double rms = 0.0;
+            if (fs > 0) {
+                double ss;
+                if (plan.alias[j]) ss = plan.pv[j][0] * (double)fs;     // same 1600 samples as the chunk
+                else { ss = plan.pv[j][GATE_MAXP]; if (B.fmt == 1) ss *= (1.0 / 1073741824.0); }
                 rms = sqrt(ss / (double)nrec);
-                recent_ss = rms;
+                silent = rms < st.thr;
             }
-            __syncthreads();
-            rms = recent_ss;
-            silent = rms < st.thr;
-        }
-
-        // ---- state machine, thread 0 (wakeword.py:1036-1157)
-        if (tid == 0) {
+            // ---- state machine (wakeword.py:1036-1157)
             const double now = __dmul_rn((double)k, 0.1);
             st.last_rms = rms;
             if (full && !st.started) {                                  // _wait_for_buffer done -> _detect_word entry
@@ -321,10 +462,10 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr) {
                 st.start_time = now;                                    // :1052
                 if (silent) st.silence_start = now;
             } else if (st.started) {
-                // loop top of the previous iteration's end: timeout check uses time() before the sleep (:1061)
+                // loop top: the timeout check uses time() before the sleep (:1061), i.e. the previous tick's time
                 const double prev = __dmul_rn((double)(k - 1), 0.1);
                 if (prm.timeout > 0.0 && __dsub_rn(prev, st.start_time) > prm.timeout) {
-                    // TimeoutError -> listen loop re-enters _detect_word at `prev` (:1205-1211)
+                    // TimeoutError -> the listen loop re-enters _detect_word at `prev` (:1205-1211)
                     const int idx = atomicAdd(B.ev_count, 1);
                     if (idx < B.max_events) {
                         EventRec e{};
@@ -383,25 +524,23 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr) {
                 }
             }
             st.last_silent = silent;
-            st.tick = k;
-            st.visible = V;
             if (tr.silent) {
-                const size_t o = (size_t)s * n_ticks + j;
+                const size_t o = (size_t)s * trace_stride + trace_off + j;
                 tr.silent[o] = (unsigned char)silent;
                 tr.state[o] = (unsigned char)(st.started ? st.state : 255);
                 tr.thr[o] = st.thr;
                 tr.rms[o] = rms;
             }
-        } else {
-            st.tick = k;
-            st.visible = V;
         }
-        __syncthreads();
+        st.tick = k;
+        st.visible = V;
     }
+    __syncthreads();
 
-    if (use_chunks)
-        for (int i = tid; i < n_chunks; i += GATE_THREADS) g_ms[i] = ms[i];
+    if (use_chunks && valid)
+        for (int i = tid; i < n_chunks; i += GATE_THREADS) { g_ms[i] = ms[i]; g_sorted[i] = SA[i]; }
     if (tid == 0) {
+        st.chunks_valid = valid;
         B.st[s] = st;
         StreamResult r = B.results[s];
         r.flags = (r.flags & 1u) | (st.last_silent ? 2u : 0u) | ((unsigned)st.state << 2) | evflag |

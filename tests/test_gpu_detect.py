@@ -119,7 +119,7 @@ def test_push_granularity_does_not_change_decisions(golden_detect, word):
 
 def test_read_last_and_segment(word):
     from easywakeword_b200 import _lib
-    ctx = _lib.Context(device=0, n_streams=2, ring_samples=16000, slack_samples=8000, pcm_format=_lib.PCM_F32)
+    ctx = _lib.Context(device=0, n_streams=2, ring_samples=16000, slack_samples=16000, pcm_format=_lib.PCM_F32)
     ctx.set_stream_params(-1, frame_size=1600)
     rng = np.random.default_rng(0)
     x = rng.standard_normal((2, 40000)).astype(np.float32) * 0.01
