@@ -160,7 +160,7 @@ int ewk_ctx::launch_segments(const SegDesc* d_segs, int n_seg, int max_frames, l
     const int cap = std::min(max_frames, SEG_SMEM_FRAMES);
     float* ws = nullptr;
     if (spill_frames > 0) {
-        CK(b_ws.ensure(sizeof(float) * (size_t)spill_frames * (LM_STRIDE + N_MFCC)));
+        CK(b_ws.ensure(sizeof(float) * (size_t)spill_frames * FR_STRIDE));
         ws = (float*)b_ws.p;
     }
     cudaEvent_t pe = prof_begin(3);
@@ -538,7 +538,7 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     }
     ctx->prof_end(pe, 1);
     CK(cudaGetLastError());
-    const int grid = std::max(1, ctx->sm_count);
+    const int grid = std::max(1, 3 * ctx->sm_count);
     pe = ctx->prof_begin(2);
     segment_queue_kernel<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ctx->stream>>>(
         ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);

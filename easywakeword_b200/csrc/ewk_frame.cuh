@@ -1,13 +1,17 @@
-// Warp-level MFCC frame pipeline for sm_100a: one warp turns one 512-sample frame into 128 log-mel
-// values.  Restates (not ports) what the reference reaches through librosa.feature.mfcc
+// Warp-level MFCC frame pipeline for sm_100a: one warp turns one 512-sample frame into 20 MFCCs.
+// Restates (not ports) what the reference reaches through librosa.feature.mfcc
 // (/root/reference/easywakeword/wakeword.py:561-563): periodic-Hann window, 512-point real FFT,
-// |X|^2, Slaney mel filterbank (128 bands, sparse: 504 non-zeros), 10*log10(max(1e-10, .)).
+// |X|^2, Slaney mel filterbank (128 bands, sparse: 504 non-zeros), 10*log10(max(1e-10, .)),
+// power_to_db floor, ortho DCT-II (first 20 coefficients).
 //
 // FFT: the 512 real samples are packed as 256 complex points z[n] = x[2n] + i x[2n+1]; the warp runs
 // a 256-point complex FFT as radix 8 x 8 x 4 with 8 points per lane in registers and two
 // conflict-free shared-memory transposes, then untangles Z[k], Z[256-k] (one shuffle pair per bin)
-// into the 257 real-FFT bins.  All twiddles and the lane's 16 window taps live in registers for the
-// whole kernel (they depend only on the lane), so the per-frame loop loads nothing but PCM.
+// into the 257 real-FFT bins.  Mel: each lane owns four bands (lane + 32 j).  DCT: each lane forms
+// the partial sums of its four bands for all 20 coefficients (80 FMAs, weights as 16-byte shared
+// loads) and a halving shuffle butterfly (21 exchanges) leaves coefficient k in one lane.
+// Window taps, twiddles, mel weights and the DCT matrix live in shared memory (one copy per CTA) so
+// the kernel stays under ~80 registers and several CTAs fit on an SM.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,6 +28,7 @@ constexpr int SCR_PLANE = 320;            // floats per re / im transpose plane 
 constexpr int SCR_P = 264;                // power spectrum, 257 bins padded
 constexpr int SCR_WARP = 2 * SCR_PLANE + SCR_P;   // floats of scratch per warp (3616 B)
 constexpr unsigned FULL = 0xffffffffu;
+constexpr float TEN_LOG10_2 = 3.01029995663981195f;   // 10 * log10(2)
 
 // Read-only tables, built on the host in double precision (ewk_tables.hpp) and copied once.
 struct DeviceTables {
@@ -37,29 +42,39 @@ struct DeviceTables {
     float dct_t[N_MELS * N_MFCC]; // ortho DCT-II, transposed: dct_t[b*20 + k]
 };
 
-struct LaneConsts {
-    float2 hw[8];    // window taps for samples (2*lane + 64a, +1)
-    float2 tw1[8];   // W256^(lane * k)
-    float2 tw2[8];   // W32^((lane & 3) * k)
-    float2 tw3[8];   // W512^(lane + 32 m)
-    int mstart[4], mlen[4], moff[4];   // the lane's four mel bands: lane + 32 j
+// Per-CTA shared copy, laid out for conflict-free lane-indexed access.
+struct FrameTables {
+    float2 hw[8 * 32];            // hw[a*32 + lane]   = hann[2 lane + 64 a], hann[2 lane + 64 a + 1]
+    float2 tw1[8 * 32];           // tw1[k*32 + lane]  = W256^(lane k)
+    float2 tw3[8 * 32];           // tw3[m*32 + lane]  = W512^(lane + 32 m)
+    float2 tw2[8 * 4];            // tw2[k*4 + c]      = W32^(c k)
+    float melw[MEL_NNZ_CAP];
+    float4 dct[N_MELS * N_MFCC / 4];   // dct_t rows of 20 floats, read as 5 float4
 };
 
-__device__ __forceinline__ void init_lane_consts(LaneConsts& lc, const DeviceTables* __restrict__ T, int lane) {
-#pragma unroll
-    for (int a = 0; a < 8; a++) lc.hw[a] = make_float2(T->hann[2 * lane + 64 * a], T->hann[2 * lane + 64 * a + 1]);
-#pragma unroll
-    for (int k = 0; k < 8; k++) lc.tw1[k] = T->w256[(lane * k) & 255];
-    const int c = lane & 3;
-#pragma unroll
-    for (int k = 0; k < 8; k++) lc.tw2[k] = T->w256[(8 * c * k) & 255];
-#pragma unroll
-    for (int m = 0; m < 8; m++) lc.tw3[m] = T->w512[lane + 32 * m];
+__device__ __forceinline__ void load_frame_tables(FrameTables& ft, const DeviceTables* __restrict__ T, int tid, int nthr) {
+    for (int i = tid; i < 256; i += nthr) {
+        const int a = i >> 5, lane = i & 31;
+        ft.hw[i] = make_float2(T->hann[2 * lane + 64 * a], T->hann[2 * lane + 64 * a + 1]);
+        ft.tw1[i] = T->w256[(lane * a) & 255];
+        ft.tw3[i] = T->w512[lane + 32 * a];
+    }
+    for (int i = tid; i < 32; i += nthr) ft.tw2[i] = T->w256[(8 * (i & 3) * (i >> 2)) & 255];
+    for (int i = tid; i < MEL_NNZ_CAP; i += nthr) ft.melw[i] = T->mel_w[i];
+    const float4* d = reinterpret_cast<const float4*>(T->dct_t);
+    for (int i = tid; i < N_MELS * N_MFCC / 4; i += nthr) ft.dct[i] = d[i];
+}
+
+struct LaneMel {                  // the lane's four mel bands: lane + 32 j
+    int start[4], len[4], off[4];
+};
+
+__device__ __forceinline__ void init_lane_mel(LaneMel& lm, const DeviceTables* __restrict__ T, int lane) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        lc.mstart[j] = T->mel_start[lane + 32 * j];
-        lc.mlen[j] = T->mel_len[lane + 32 * j];
-        lc.moff[j] = T->mel_off[lane + 32 * j];
+        lm.start[j] = T->mel_start[lane + 32 * j];
+        lm.len[j] = T->mel_len[lane + 32 * j];
+        lm.off[j] = T->mel_off[lane + 32 * j];
     }
 }
 
@@ -91,23 +106,24 @@ __device__ __forceinline__ void fft8(float2 (&v)[8]) {
 }
 
 // One warp: 512 windowed real samples -> power spectrum P[0..256] in shared memory.
-// ld(i) returns the PCM samples (i, i+1) of the frame, i even in [0, 512), already zero outside
-// the signal.  scr: SCR_WARP floats private to the warp.
+// ld(a) returns the PCM samples (2 lane + 64 a, +1) of the frame, already zero outside the signal.
+// scr: SCR_WARP floats private to the warp.
 template <class Ld>
-__device__ __forceinline__ void warp_power_spectrum(Ld&& ld, const LaneConsts& lc, float* scr, int lane) {
+__device__ __forceinline__ void warp_power_spectrum(Ld&& ld, const FrameTables& ft, float* scr, int lane) {
     float* sre = scr;
     float* sim = scr + SCR_PLANE;
     float* P = scr + 2 * SCR_PLANE;
     float2 v[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) {
-        const float2 s = ld(2 * lane + 64 * a);
-        v[a] = make_float2(s.x * lc.hw[a].x, s.y * lc.hw[a].y);
+        const float2 s = ld(a);
+        const float2 h = ft.hw[a * 32 + lane];
+        v[a] = make_float2(s.x * h.x, s.y * h.y);
     }
     // radix-8 over a  (n = 32a + lane)
     fft8(v);
 #pragma unroll
-    for (int k = 1; k < 8; k++) v[k] = cmul(v[k], lc.tw1[k]);
+    for (int k = 1; k < 8; k++) v[k] = cmul(v[k], ft.tw1[k * 32 + lane]);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 8; k++) { sre[k * 36 + lane] = v[k].x; sim[k * 36 + lane] = v[k].y; }
@@ -118,7 +134,7 @@ __device__ __forceinline__ void warp_power_spectrum(Ld&& ld, const LaneConsts& l
     for (int b = 0; b < 8; b++) v[b] = make_float2(sre[ka * 36 + 4 * b + c], sim[ka * 36 + 4 * b + c]);
     fft8(v);
 #pragma unroll
-    for (int k = 1; k < 8; k++) v[k] = cmul(v[k], lc.tw2[k]);
+    for (int k = 1; k < 8; k++) v[k] = cmul(v[k], ft.tw2[k * 4 + c]);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 8; k++) { sre[k * 40 + c * 8 + ka] = v[k].x; sim[k * 40 + c * 8 + ka] = v[k].y; }
@@ -144,7 +160,7 @@ __device__ __forceinline__ void warp_power_spectrum(Ld&& ld, const LaneConsts& l
         if (lane == 0) { pr = o[(8 - m) & 7].x; pi = o[(8 - m) & 7].y; }
         const float er = o[m].x + pr, ei = o[m].y - pi;     // 2E
         const float qr = o[m].y + pi, qi = pr - o[m].x;     // 2O
-        const float2 w = lc.tw3[m];
+        const float2 w = ft.tw3[m * 32 + lane];
         const float xr = er + (w.x * qr - w.y * qi);
         const float xi = ei + (w.x * qi + w.y * qr);
         P[lane + 32 * m] = 0.25f * (xr * xr + xi * xi);
@@ -154,17 +170,95 @@ __device__ __forceinline__ void warp_power_spectrum(Ld&& ld, const LaneConsts& l
 }
 
 // One warp: P[0..256] -> the lane's four log-mel values (bands lane + 32 j), 10*log10(max(1e-10, S)).
-__device__ __forceinline__ void warp_log_mel(const float* __restrict__ P, const float* __restrict__ melw,
-                                             const LaneConsts& lc, float (&out)[4]) {
+__device__ __forceinline__ void warp_log_mel(const float* __restrict__ P, const FrameTables& ft,
+                                             const LaneMel& lm, float (&out)[4]) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const float* p = P + lc.mstart[j];
-        const float* w = melw + lc.moff[j];
+        const float* p = P + lm.start[j];
+        const float* w = ft.melw + lm.off[j];
         float acc = 0.f;
-        const int n = lc.mlen[j];
+        const int n = lm.len[j];
         for (int i = 0; i < n; i++) acc = fmaf(w[i], p[i], acc);
-        out[j] = 10.0f * log10f(fmaxf(acc, 1e-10f));
+        out[j] = TEN_LOG10_2 * __log2f(fmaxf(acc, 1e-10f));
     }
+}
+
+// Which coefficient the lane holds after warp_dct20 (or -1).
+__device__ __forceinline__ int dct_lane_coef(int lane) {
+    const int w = lane & 7;                       // (b2 b1 b0)
+    const int within = w == 0 ? 0 : w == 1 ? 1 : w == 2 ? 2 : w == 4 ? 3 : w == 5 ? 4 : -1;
+    return within < 0 ? -1 : 10 * ((lane >> 4) & 1) + 5 * ((lane >> 3) & 1) + within;
+}
+
+// One warp: log-mel x[4] per lane (bands lane + 32 j, already floored) -> ortho DCT-II coefficient
+// dct_lane_coef(lane) returned in the lanes that own one.
+__device__ __forceinline__ float warp_dct20(const float (&x)[4], const FrameTables& ft, int lane) {
+    float acc[N_MFCC];
+#pragma unroll
+    for (int k = 0; k < N_MFCC; k++) acc[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float4* row = ft.dct + (lane + 32 * j) * (N_MFCC / 4);
+#pragma unroll
+        for (int q = 0; q < N_MFCC / 4; q++) {
+            const float4 w = row[q];
+            acc[4 * q + 0] = fmaf(w.x, x[j], acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(w.y, x[j], acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(w.z, x[j], acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(w.w, x[j], acc[4 * q + 3]);
+        }
+    }
+    // halving butterfly: 20 -> 10 -> 5 -> (6) 3 -> (4) 2 -> 1 values per lane
+    float a10[10], a5[6], a3[4], a2[2];
+    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const float send = u16 ? acc[i] : acc[i + 10], keep = u16 ? acc[i + 10] : acc[i];
+        a10[i] = keep + __shfl_xor_sync(FULL, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const float send = u8 ? a10[i] : a10[i + 5], keep = u8 ? a10[i + 5] : a10[i];
+        a5[i] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+    a5[5] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float send = u4 ? a5[i] : a5[i + 3], keep = u4 ? a5[i + 3] : a5[i];
+        a3[i] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+    a3[3] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const float send = u2 ? a3[i] : a3[i + 2], keep = u2 ? a3[i + 2] : a3[i];
+        a2[i] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+    const float send = u1 ? a2[0] : a2[1], keep = u1 ? a2[1] : a2[0];
+    return keep + __shfl_xor_sync(FULL, send, 1);
+}
+
+// One warp, one frame: PCM -> 20 MFCCs written to out[0..19]; returns the frame's log-mel min / max
+// (before flooring) in every lane.  floor_db = -INFINITY disables the power_to_db floor.
+template <class Ld>
+__device__ __forceinline__ void warp_frame_mfcc(Ld&& ld, const FrameTables& ft, const LaneMel& lm, float* scr, int lane,
+                                                float floor_db, float* __restrict__ out, float& fmin_o, float& fmax_o) {
+    warp_power_spectrum(ld, ft, scr, lane);
+    float v[4];
+    warp_log_mel(scr + 2 * SCR_PLANE, ft, lm, v);
+    float mn = fminf(fminf(v[0], v[1]), fminf(v[2], v[3]));
+    float mx = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = fmaxf(v[j], floor_db);
+    const float cft = warp_dct20(v, ft, lane);
+    const int k = dct_lane_coef(lane);
+    if (k >= 0) out[k] = cft;
+    fmin_o = mn;
+    fmax_o = mx;
 }
 
 }  // namespace ewk

@@ -17,7 +17,6 @@ namespace ewk {
 
 constexpr int SEG_THREADS = 256;
 constexpr int SEG_WARPS = SEG_THREADS / 32;
-constexpr int LM_STRIDE = 129;                 // log-mel row stride (conflict-free column walks)
 constexpr int SEG_SMEM_FRAMES = 301;           // 1 + 48000/160
 constexpr int FEAT = 2 * N_MFCC;               // mean[20] ++ std[20]
 
@@ -51,6 +50,17 @@ struct PcmReader {
         if (ring) { if (p >= ring) p -= ring; }
         return q ? (float)q[p] * (1.0f / 32768.0f) : f[p];
     }
+    // Frame starting at segment-relative f0: can lanes read sample pairs (2 lane + 64 a, +1) with one
+    // aligned 4- / 8-byte load each, without bounds or wrap checks?  Returns the buffer position of
+    // the frame's first sample, or -1.
+    __device__ __forceinline__ long long fast_base(int f0) const {
+        if (f0 < 0 || f0 + N_FFT > len) return -1;
+        long long p = start + f0;
+        if (ring) { if (p >= ring) p -= ring; if (p + N_FFT > ring) return -1; }
+        if (p & 1) return -1;
+        if (q ? ((size_t)q & 3) : ((size_t)f & 7)) return -1;
+        return p;
+    }
 };
 
 // scipy.spatial.distance.cosine + the reference's mixing and rescale (wakeword.py:615-623), in the
@@ -80,48 +90,79 @@ __device__ __forceinline__ float similarity_score(const float* ref_mean, const f
     return __fdiv_rn(__fmul_rn(p, sqrtf(p)), 10.0f);      // p**1.5 / 100**0.5
 }
 
-// Dynamic shared memory layout (floats):
-//   melw[512] | dct_t[128*20] | scratch[SEG_WARPS*SCR_WARP] | red[64] | logmel[cap*129] | mfcc[cap*20]
+// Dynamic shared memory layout:
+//   FrameTables | scratch[SEG_WARPS*SCR_WARP] | red[64] | mfcc[cap*20] | fmin[cap] | fmax[cap]
+constexpr int FR_STRIDE = N_MFCC + 2;          // per-frame record in the global spill: mfcc[20], min, max
 __host__ __device__ inline size_t seg_smem_bytes(int cap_frames) {
-    return sizeof(float) * ((size_t)MEL_NNZ_CAP + N_MELS * N_MFCC + SEG_WARPS * SCR_WARP + 64 +
-                            (size_t)cap_frames * (LM_STRIDE + N_MFCC));
+    return sizeof(FrameTables) + sizeof(float) * ((size_t)SEG_WARPS * SCR_WARP + 64 + (size_t)cap_frames * FR_STRIDE);
 }
 
 struct SegSmem {
-    float *melw, *dct, *scratch, *red, *lm, *mf;
+    FrameTables* ft;
+    float *scratch, *red, *mf, *fmin, *fmax;
 };
 
 __device__ __forceinline__ SegSmem seg_carve(float* smem, int cap_frames) {
     SegSmem m;
-    m.melw = smem;
-    m.dct = m.melw + MEL_NNZ_CAP;
-    m.scratch = m.dct + N_MELS * N_MFCC;
+    m.ft = reinterpret_cast<FrameTables*>(smem);
+    m.scratch = smem + sizeof(FrameTables) / sizeof(float);
     m.red = m.scratch + SEG_WARPS * SCR_WARP;
-    m.lm = m.red + 64;
-    m.mf = m.lm + (size_t)cap_frames * LM_STRIDE;
+    m.mf = m.red + 64;
+    m.fmin = m.mf + (size_t)cap_frames * N_MFCC;
+    m.fmax = m.fmin + cap_frames;
     return m;
 }
 
-// once per CTA: tables into shared memory, per-lane constants into registers
-__device__ __forceinline__ void seg_prologue(const DeviceTables* __restrict__ T, const SegSmem& m, LaneConsts& lc) {
-    for (int i = threadIdx.x; i < MEL_NNZ_CAP; i += SEG_THREADS) m.melw[i] = T->mel_w[i];
-    for (int i = threadIdx.x; i < N_MELS * N_MFCC; i += SEG_THREADS) m.dct[i] = T->dct_t[i];
-    init_lane_consts(lc, T, threadIdx.x & 31);
+// once per CTA: tables into shared memory, the lane's mel band descriptors into registers
+__device__ __forceinline__ void seg_prologue(const DeviceTables* __restrict__ T, const SegSmem& m, LaneMel& lmel) {
+    load_frame_tables(*m.ft, T, threadIdx.x, SEG_THREADS);
+    init_lane_mel(lmel, T, threadIdx.x & 31);
     __syncthreads();
+}
+
+// One frame of the segment by one warp: MFCC[20] -> mf_row, log-mel min / max returned.
+__device__ __forceinline__ void segment_frame(const PcmReader& rd, int t, const SegSmem& m, const LaneMel& lmel,
+                                              float* scr, int lane, float floor_db, float* mf_row,
+                                              float& mn, float& mx) {
+    const int f0 = t * HOP - N_FFT / 2;
+    const long long base = rd.fast_base(f0);
+    if (base >= 0) {
+        if (rd.q) {
+            const unsigned* w = reinterpret_cast<const unsigned*>(rd.q + base);
+            warp_frame_mfcc([&](int a) {
+                const unsigned u = __ldg(w + lane + 32 * a);
+                return make_float2((float)(short)(u & 0xffff) * (1.0f / 32768.0f), (float)((int)u >> 16) * (1.0f / 32768.0f));
+            }, *m.ft, lmel, scr, lane, floor_db, mf_row, mn, mx);
+        } else {
+            const float2* w = reinterpret_cast<const float2*>(rd.f + base);
+            warp_frame_mfcc([&](int a) { return __ldg(w + lane + 32 * a); }, *m.ft, lmel, scr, lane, floor_db, mf_row, mn, mx);
+        }
+    } else {
+        warp_frame_mfcc([&](int a) {
+            const int i = f0 + 2 * lane + 64 * a;
+            return make_float2(rd.at(i), rd.at(i + 1));
+        }, *m.ft, lmel, scr, lane, floor_db, mf_row, mn, mx);
+    }
 }
 
 // Phases A-D for one segment by the whole CTA.  Returns a shared-memory pointer to mean[20] ++ std[20]
 // (valid until the next call).  All threads must call it.
-__device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegSmem& m, const LaneConsts& lc,
+//   A  every frame -> MFCC without the power_to_db floor, plus the frame's log-mel min / max
+//   B  block max -> floor = max - 80 (librosa.power_to_db(top_db=80) couples all frames of a segment)
+//   C  only frames whose min lies below the floor are recomputed with it (none in the common case)
+//   D  mean / std over frames (two-pass, ddof 0)
+__device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegSmem& m, const LaneMel& lmel,
                                                    int cap_frames, float* __restrict__ ws,
                                                    float* __restrict__ frames_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = 1 + sd.len / HOP;
-    float* lm = m.lm;
     float* mf = m.mf;
+    float* fmn = m.fmin;
+    float* fmx = m.fmax;
     if (F > cap_frames) {
-        lm = ws + (size_t)sd.ws_frame_off * (LM_STRIDE + N_MFCC);
-        mf = lm + (size_t)F * LM_STRIDE;
+        mf = ws + (size_t)sd.ws_frame_off * FR_STRIDE;
+        fmn = mf + (size_t)F * N_MFCC;
+        fmx = fmn + F;
     }
     PcmReader rd;
     rd.f = sd.fmt == 0 ? (const float*)sd.base : nullptr;
@@ -132,52 +173,28 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
     float* scr = m.scratch + warp * SCR_WARP;
     float vmax = -INFINITY;
     for (int t = warp; t < F; t += SEG_WARPS) {
-        const int f0 = t * HOP - N_FFT / 2;
-        warp_power_spectrum([&](int i) { return make_float2(rd.at(f0 + i), rd.at(f0 + i + 1)); }, lc, scr, lane);
-        float v[4];
-        warp_log_mel(scr + 2 * SCR_PLANE, m.melw, lc, v);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            lm[(size_t)t * LM_STRIDE + lane + 32 * j] = v[j];
-            vmax = fmaxf(vmax, v[j]);
-        }
+        float mn, mx;
+        segment_frame(rd, t, m, lmel, scr, lane, -INFINITY, mf + (size_t)t * N_MFCC, mn, mx);
+        if (lane == 0) { fmn[t] = mn; fmx[t] = mx; }
+        vmax = fmaxf(vmax, mx);
     }
     // ---- phase B
-#pragma unroll
-    for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
     if (lane == 0) m.red[warp] = vmax;
     __syncthreads();
     float gmax = m.red[0];
 #pragma unroll
     for (int w = 1; w < SEG_WARPS; w++) gmax = fmaxf(gmax, m.red[w]);
     const float floor_db = gmax - 80.0f;       // librosa.power_to_db(top_db=80)
-    __syncthreads();
-
-    // ---- phase C: thread = (frame, half of the coefficients)
-    for (int it = tid; it < 2 * F; it += SEG_THREADS) {
-        const int t = it >> 1, g = it & 1;
-        const float* row = lm + (size_t)t * LM_STRIDE;
-        float acc[10];
-#pragma unroll
-        for (int k = 0; k < 10; k++) acc[k] = 0.f;
-        for (int b = 0; b < N_MELS; b++) {
-            const float x = fmaxf(row[b], floor_db);
-            const float2* d = reinterpret_cast<const float2*>(m.dct + b * N_MFCC + 10 * g);
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const float2 w = d[k];
-                acc[2 * k] = fmaf(w.x, x, acc[2 * k]);
-                acc[2 * k + 1] = fmaf(w.y, x, acc[2 * k + 1]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 10; k++) mf[(size_t)t * N_MFCC + 10 * g + k] = acc[k];
-        if (frames_out) {
-#pragma unroll
-            for (int k = 0; k < 10; k++) frames_out[(sd.frames_off + t) * N_MFCC + 10 * g + k] = acc[k];
+    // ---- phase C
+    for (int t = warp; t < F; t += SEG_WARPS) {
+        if (fmn[t] < floor_db) {               // warp-uniform
+            float mn, mx;
+            segment_frame(rd, t, m, lmel, scr, lane, floor_db, mf + (size_t)t * N_MFCC, mn, mx);
         }
     }
     __syncthreads();
+    if (frames_out)
+        for (int i = tid; i < F * N_MFCC; i += SEG_THREADS) frames_out[sd.frames_off * N_MFCC + i] = mf[i];
 
     // ---- phase D: mean / std over frames; thread = (slice of frames, coefficient)
     constexpr int SL = 12;                       // 12 * 20 = 240 active threads
@@ -215,9 +232,9 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
 }
 
 // K3, batch form: one CTA per caller-described segment (extract_mfcc / calculate_similarity / matches).
-__global__ void __launch_bounds__(SEG_THREADS, 1)
+__global__ void __launch_bounds__(SEG_THREADS, 3)
 segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __restrict__ segs,
-                          int cap_frames, float* __restrict__ ws,           // global spill [frames][129+20]
+                          int cap_frames, float* __restrict__ ws,           // global spill [frames][22]
                           const TemplateFeat* __restrict__ tmpl, int n_tmpl, int tmpl_first,
                           float threshold,
                           float* __restrict__ feat_out,                      // [n_seg][40] or null
@@ -225,13 +242,13 @@ segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __r
                           float* __restrict__ scores,                        // [n_seg][n_tmpl] or null
                           unsigned char* __restrict__ matched)               // [n_seg][n_tmpl] or null
 {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const SegSmem m = seg_carve(smem, cap_frames);
-    LaneConsts lc;
-    seg_prologue(T, m, lc);
+    LaneMel lmel;
+    seg_prologue(T, m, lmel);
     const int tid = threadIdx.x;
     const SegDesc sd = segs[blockIdx.x];
-    const float* feat = segment_features(sd, m, lc, cap_frames, ws, frames_out);
+    const float* feat = segment_features(sd, m, lmel, cap_frames, ws, frames_out);
     if (feat_out && tid < FEAT) feat_out[(size_t)blockIdx.x * FEAT + tid] = feat[tid];
     if (scores && tid < n_tmpl) {
         const TemplateFeat& tf = tmpl[tmpl_first + tid];
