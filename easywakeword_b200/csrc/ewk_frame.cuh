@@ -106,19 +106,17 @@ __device__ __forceinline__ void fft8(float2 (&v)[8]) {
 }
 
 // One warp: 512 windowed real samples -> power spectrum P[0..256] in shared memory.
-// ld(a) returns the PCM samples (2 lane + 64 a, +1) of the frame, already zero outside the signal.
+// x[a] holds the PCM samples (2 lane + 64 a, +1) of the frame, already zero outside the signal.
 // scr: SCR_WARP floats private to the warp.
-template <class Ld>
-__device__ __forceinline__ void warp_power_spectrum(Ld&& ld, const FrameTables& ft, float* scr, int lane) {
+__device__ __forceinline__ void warp_power_spectrum(const float2 (&x)[8], const FrameTables& ft, float* scr, int lane) {
     float* sre = scr;
     float* sim = scr + SCR_PLANE;
     float* P = scr + 2 * SCR_PLANE;
     float2 v[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) {
-        const float2 s = ld(a);
         const float2 h = ft.hw[a * 32 + lane];
-        v[a] = make_float2(s.x * h.x, s.y * h.y);
+        v[a] = make_float2(x[a].x * h.x, x[a].y * h.y);
     }
     // radix-8 over a  (n = 32a + lane)
     fft8(v);
@@ -239,10 +237,10 @@ __device__ __forceinline__ float warp_dct20(const float (&x)[4], const FrameTabl
 
 // One warp, one frame: PCM -> 20 MFCCs written to out[0..19]; returns the frame's log-mel min / max
 // (before flooring) in every lane.  floor_db = -INFINITY disables the power_to_db floor.
-template <class Ld>
-__device__ __forceinline__ void warp_frame_mfcc(Ld&& ld, const FrameTables& ft, const LaneMel& lm, float* scr, int lane,
-                                                float floor_db, float* __restrict__ out, float& fmin_o, float& fmax_o) {
-    warp_power_spectrum(ld, ft, scr, lane);
+__device__ __forceinline__ void warp_frame_mfcc(const float2 (&x)[8], const FrameTables& ft, const LaneMel& lm, float* scr,
+                                                int lane, float floor_db, float* __restrict__ out, float& fmin_o,
+                                                float& fmax_o) {
+    warp_power_spectrum(x, ft, scr, lane);
     float v[4];
     warp_log_mel(scr + 2 * SCR_PLANE, ft, lm, v);
     float mn = fminf(fminf(v[0], v[1]), fminf(v[2], v[3]));

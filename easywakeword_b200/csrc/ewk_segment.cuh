@@ -120,28 +120,30 @@ __device__ __forceinline__ void seg_prologue(const DeviceTables* __restrict__ T,
     __syncthreads();
 }
 
-// One frame of the segment by one warp: MFCC[20] -> mf_row, log-mel min / max returned.
-__device__ __forceinline__ void segment_frame(const PcmReader& rd, int t, const SegSmem& m, const LaneMel& lmel,
-                                              float* scr, int lane, float floor_db, float* mf_row,
-                                              float& mn, float& mx) {
+// The lane's eight sample pairs (2 lane + 64 a, +1) of frame t, zero outside the segment
+// (librosa center=True, pad_mode='constant').
+__device__ __forceinline__ void load_frame_pairs(const PcmReader& rd, int t, int lane, float2 (&x)[8]) {
     const int f0 = t * HOP - N_FFT / 2;
     const long long base = rd.fast_base(f0);
     if (base >= 0) {
         if (rd.q) {
             const unsigned* w = reinterpret_cast<const unsigned*>(rd.q + base);
-            warp_frame_mfcc([&](int a) {
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
                 const unsigned u = __ldg(w + lane + 32 * a);
-                return make_float2((float)(short)(u & 0xffff) * (1.0f / 32768.0f), (float)((int)u >> 16) * (1.0f / 32768.0f));
-            }, *m.ft, lmel, scr, lane, floor_db, mf_row, mn, mx);
+                x[a] = make_float2((float)(short)(u & 0xffff) * (1.0f / 32768.0f), (float)((int)u >> 16) * (1.0f / 32768.0f));
+            }
         } else {
             const float2* w = reinterpret_cast<const float2*>(rd.f + base);
-            warp_frame_mfcc([&](int a) { return __ldg(w + lane + 32 * a); }, *m.ft, lmel, scr, lane, floor_db, mf_row, mn, mx);
+#pragma unroll
+            for (int a = 0; a < 8; a++) x[a] = __ldg(w + lane + 32 * a);
         }
     } else {
-        warp_frame_mfcc([&](int a) {
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
             const int i = f0 + 2 * lane + 64 * a;
-            return make_float2(rd.at(i), rd.at(i + 1));
-        }, *m.ft, lmel, scr, lane, floor_db, mf_row, mn, mx);
+            x[a] = make_float2(rd.at(i), rd.at(i + 1));
+        }
     }
 }
 
@@ -169,27 +171,27 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
     rd.q = sd.fmt == 1 ? (const short*)sd.base : nullptr;
     rd.ring = sd.ring; rd.len = sd.len; rd.start = sd.start;
 
-    // ---- phase A
+    // ---- phases A, B, C: one frame loop (a single instance of the frame pipeline in the code)
     float* scr = m.scratch + warp * SCR_WARP;
-    float vmax = -INFINITY;
-    for (int t = warp; t < F; t += SEG_WARPS) {
-        float mn, mx;
-        segment_frame(rd, t, m, lmel, scr, lane, -INFINITY, mf + (size_t)t * N_MFCC, mn, mx);
-        if (lane == 0) { fmn[t] = mn; fmx[t] = mx; }
-        vmax = fmaxf(vmax, mx);
-    }
-    // ---- phase B
-    if (lane == 0) m.red[warp] = vmax;
-    __syncthreads();
-    float gmax = m.red[0];
-#pragma unroll
-    for (int w = 1; w < SEG_WARPS; w++) gmax = fmaxf(gmax, m.red[w]);
-    const float floor_db = gmax - 80.0f;       // librosa.power_to_db(top_db=80)
-    // ---- phase C
-    for (int t = warp; t < F; t += SEG_WARPS) {
-        if (fmn[t] < floor_db) {               // warp-uniform
+    float floor_db = -INFINITY;
+    for (int pass = 0; pass < 2; pass++) {
+        float vmax = -INFINITY;
+        for (int t = warp; t < F; t += SEG_WARPS) {
+            if (pass && !(fmn[t] < floor_db)) continue;      // warp-uniform: only floored frames are redone
+            float2 x[8];
+            load_frame_pairs(rd, t, lane, x);
             float mn, mx;
-            segment_frame(rd, t, m, lmel, scr, lane, floor_db, mf + (size_t)t * N_MFCC, mn, mx);
+            warp_frame_mfcc(x, *m.ft, lmel, scr, lane, floor_db, mf + (size_t)t * N_MFCC, mn, mx);
+            if (!pass && lane == 0) { fmn[t] = mn; fmx[t] = mx; }
+            vmax = fmaxf(vmax, mx);
+        }
+        if (!pass) {
+            if (lane == 0) m.red[warp] = vmax;
+            __syncthreads();
+            float gmax = m.red[0];
+#pragma unroll
+            for (int w = 1; w < SEG_WARPS; w++) gmax = fmaxf(gmax, m.red[w]);
+            floor_db = gmax - 80.0f;                          // librosa.power_to_db(top_db=80)
         }
     }
     __syncthreads();

@@ -148,7 +148,7 @@ __device__ __forceinline__ long long sq8(const int4 q) {
     return out;
 }
 
-__device__ __forceinline__ double warp_sumsq(const BankView& B, int s, long long a0, int len, int lane) {
+__device__ __noinline__ double warp_sumsq(const BankView& B, int s, long long a0, int len, int lane) {
     double acc = 0.0;
     if (len <= 0) return 0.0;
     const int p0 = (int)(a0 % B.P);
