@@ -1,0 +1,100 @@
+"""Multi-GPU sharding of a stream bank: one process per GPU, contiguous blocks of stream ids per rank,
+no data-path collective (streams are independent — the reference's multiroom shape is N independent
+detectors, /root/reference/examples/multiroom_async.py:14-35).  The only exchange is the gather of the
+dense 8-byte per-stream result records (score f32, flags u32) that K2/K3 write on the device:
+`torch.distributed.all_gather_into_tensor` over NCCL/NVLink on GPUs, gloo on CPU tensors in tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_total: int, world: int, rank: int) -> tuple[int, int]:
+    """[first, last) global stream ids owned by `rank`: contiguous, sizes differ by at most one."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    base, rem = divmod(n_total, world)
+    first = rank * base + min(rank, rem)
+    return first, first + base + (1 if rank < rem else 0)
+
+
+def owner_of(stream: int, n_total: int, world: int) -> tuple[int, int]:
+    """(rank, local index) of a global stream id."""
+    base, rem = divmod(n_total, world)
+    cut = rem * (base + 1)
+    if stream < cut:
+        return stream // (base + 1), stream % (base + 1)
+    return rem + (stream - cut) // base, (stream - cut) % base
+
+
+def padded_shard(n_total: int, world: int) -> int:
+    """Per-rank record count used for the fixed-size all-gather (ceil(n_total / world))."""
+    return -(-n_total // world)
+
+
+class ResultGather:
+    """Gathers per-stream result records from every rank into global stream order.
+
+    local records: int32 tensor [padded_shard, 2] on the rank's device (bank kernels write the first
+    n_local rows in place when it is installed with Context.set_results_buffer)."""
+
+    def __init__(self, n_total: int, world: int, rank: int, device="cpu"):
+        import torch
+        self.torch = torch
+        self.n_total, self.world, self.rank = n_total, world, rank
+        self.first, self.last = shard_range(n_total, world, rank)
+        self.n_local = self.last - self.first
+        self.pad = padded_shard(n_total, world)
+        self.local = torch.zeros(self.pad, 2, dtype=torch.int32, device=device)
+        self.gathered = torch.zeros(world * self.pad, 2, dtype=torch.int32, device=device)
+        # rows of `gathered` in global stream order
+        idx = []
+        for r in range(world):
+            a, b = shard_range(n_total, world, r)
+            idx.extend(range(r * self.pad, r * self.pad + (b - a)))
+        self.index = torch.tensor(idx, dtype=torch.long, device=device)
+
+    def gather(self):
+        """-> int32 tensor [n_total, 2] (score bits, flags) in global stream order, on every rank."""
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.local)
+        else:
+            self.gathered.copy_(self.local)
+        return self.gathered.index_select(0, self.index)
+
+    @staticmethod
+    def decode(records) -> np.ndarray:
+        """int32 [n, 2] -> structured array (score f32, flags u32) like Context.results()."""
+        a = records.detach().cpu().numpy().astype(np.int32)
+        out = np.empty(len(a), dtype=[("score", "<f4"), ("flags", "<u4")])
+        out["score"] = a[:, 0].view(np.float32)
+        out["flags"] = a[:, 1].view(np.uint32)
+        return out
+
+
+class ShardedBank:
+    """A WakeWordBank over the rank's shard of `n_total` streams plus the result gather."""
+
+    def __init__(self, n_total: int, templates, *, world: int, rank: int, device: int, **bank_kwargs):
+        import torch
+        from .bank import WakeWordBank
+        self.first, self.last = shard_range(n_total, world, rank)
+        self.bank = WakeWordBank(self.last - self.first, templates, device=device, **bank_kwargs)
+        self.gatherer = ResultGather(n_total, world, rank, device=torch.device("cuda", device))
+        self.bank.ctx.set_results_buffer(self.gatherer.local.data_ptr())
+
+    def step(self, pcm_local, where=0):
+        self.bank.step(pcm_local, where)
+
+    def gather(self):
+        return self.gatherer.gather()
+
+    def poll_global(self):
+        """Local events with global stream ids."""
+        ev = self.bank.poll()
+        ev["stream"] += self.first
+        return ev
+
+    def close(self):
+        self.bank.close()

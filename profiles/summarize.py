@@ -1,0 +1,65 @@
+"""Turn ncu exports brought back in gpurun_out/ into the small text summaries committed under profiles/.
+
+    python profiles/summarize.py launches gpurun_out/launches.csv > profiles/r01_launches.txt
+    python profiles/summarize.py raw gpurun_out/prof_x.ncu-rep   > profiles/r01_x_raw.txt
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.avg.per_cycle_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__warps_eligible.avg.per_cycle_active"]
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    idx = {n: i for i, n in enumerate(rows[h])}
+    agg = collections.OrderedDict()
+    for r in rows[h + 1:]:
+        if len(r) < len(rows[h]):
+            continue
+        v = float(r[idx["Metric Value"]].replace(",", ""))
+        u = r[idx["Metric Unit"]]
+        us = v / 1000 if u.startswith("n") else v * 1000 if u.startswith("m") else v
+        agg.setdefault(r[idx["Kernel Name"]].split("(")[0], []).append(us)
+    tot = sum(sum(v) for v in agg.values())
+    print(f"# ncu --metrics gpu__time_duration.sum --clock-control none  ({path}); cold-cache serialised launches: compare SHARES")
+    print(f"{'kernel':48s} {'n':>5s} {'mean_us':>10s} {'median_us':>10s} {'sum_us':>11s} {'share':>7s}")
+    for k, v in agg.items():
+        sv = sorted(v)
+        print(f"{k[-48:]:48s} {len(v):5d} {sum(v)/len(v):10.1f} {sv[len(v)//2]:10.1f} {sum(v):11.1f} {sum(v)/tot:7.3f}")
+
+
+def raw(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, units = rows[0], rows[1]
+    print(f"# ncu --set full --clock-control none  ({path})")
+    for r in rows[2:]:
+        print(f"== launch id {r[h.index('ID')]}  {r[h.index('Kernel Name')][:70]}")
+        for k in KEYS:
+            if k in h:
+                i = h.index(k)
+                print(f"  {k:82s} {r[i]:>16s} {units[i]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
