@@ -532,8 +532,8 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     cudaEvent_t pe = ctx->prof_begin(1);
     for (int done = 0; done < n_ticks; done += GATE_MAX_TICKS) {
         const int nt = std::min(GATE_MAX_TICKS, n_ticks - done);
-        tick_gate_kernel<<<B.n_streams, GATE_THREADS, sizeof(double) * 3 * (size_t)smem_chunks, ctx->stream>>>(
-            B, nt, tr, n_ticks, done, smem_chunks);
+        tick_gate_kernel<<<(B.n_streams + GATE_WARPS - 1) / GATE_WARPS, GATE_THREADS,
+                           sizeof(double) * 3 * (size_t)smem_chunks * GATE_WARPS, ctx->stream>>>(B, nt, tr, n_ticks, done, smem_chunks);
         ctx->launches++;
     }
     ctx->prof_end(pe, 1);

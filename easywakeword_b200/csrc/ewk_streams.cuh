@@ -133,77 +133,84 @@ __global__ void ring_commit_kernel(BankView B, int stream0, int n_streams, int n
 }
 
 // ------------------------------------------------------------------------------------ K2 helpers
-// Sum of squares of absolute samples [a0, a0+len) of one stream, in double.  int16 sums are in
-// integer units (exact); the caller scales by 2^-30.  Whole warp cooperates; result in every lane.
-// The aligned body issues four independent 16-byte loads per lane before reducing.
+constexpr int GATE_WARPS = GATE_THREADS / 32;
+constexpr int GATE_MAX_TICKS = 16;     // ticks per launch (the host splits longer requests)
+constexpr int GATE_MAXP = 12;          // chunk pieces planned per tick; more -> the tick is "heavy"
+
 __device__ __forceinline__ long long sq8(const int4 q) {
     const int w[4] = {q.x, q.y, q.z, q.w};
     long long out = 0;
 #pragma unroll
     for (int u = 0; u < 4; u++) {
         const int lo = (short)(w[u] & 0xffff), hi = w[u] >> 16;
-        // two squares of 15-bit magnitudes fit in 31 bits; accumulate pairs in 64 bits
         out += (long long)(unsigned)(lo * lo) + (long long)(unsigned)(hi * hi);
     }
     return out;
 }
 
-__device__ __noinline__ double warp_sumsq(const BankView& B, int s, long long a0, int len, int lane) {
+__device__ __forceinline__ double sq4(const float4 q, double acc) {
+    acc = fma((double)q.x, (double)q.x, acc); acc = fma((double)q.y, (double)q.y, acc);
+    acc = fma((double)q.z, (double)q.z, acc); acc = fma((double)q.w, (double)q.w, acc);
+    return acc;
+}
+
+// Sum of squares of absolute samples [a0, a0+len) of one stream, in double; whole warp cooperates,
+// result in every lane.  int16 sums are exact integers (the caller scales by 2^-30).  The aligned
+// body keeps up to eight independent 16-byte loads per lane in flight (a 0.1 s tick of int16 PCM is
+// 200 such loads per warp), which is what lets a single resident wave of warps saturate HBM.
+__device__ __noinline__ double warp_sumsq(const void* ring_s, int P, int fmt, long long a0, int len, int lane) {
     double acc = 0.0;
     if (len <= 0) return 0.0;
-    const int p0 = (int)(a0 % B.P);
-    if (B.fmt == 1) {
-        const short* ring = (const short*)B.ring + (size_t)s * B.P;
+    const int p0 = (int)(a0 % P);
+    if (fmt == 1) {
+        const short* ring = (const short*)ring_s;
         int i = 0;
         long long iacc = 0;
-        if ((p0 & 7) == 0 && p0 + len <= B.P) {
+        if ((p0 & 7) == 0 && p0 + len <= P) {
             const int nv = len >> 3;
             const int4* v = reinterpret_cast<const int4*>(ring + p0);
-            int k = lane;
-            for (; k + 96 < nv; k += 128) {
-                const int4 q0 = __ldg(v + k), q1 = __ldg(v + k + 32), q2 = __ldg(v + k + 64), q3 = __ldg(v + k + 96);
-                iacc += sq8(q0) + sq8(q1) + sq8(q2) + sq8(q3);
+            for (int k0 = 0; k0 < nv; k0 += 256) {
+                int4 q[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int k = k0 + lane + 32 * u;
+                    q[u] = k < nv ? __ldg(v + k) : make_int4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) iacc += sq8(q[u]);
             }
-            for (; k < nv; k += 32) iacc += sq8(__ldg(v + k));
             i = nv << 3;
         }
         for (int k = i + lane; k < len; k += 32) {
             int p = p0 + k;
-            if (p >= B.P) p -= B.P;
+            if (p >= P) p -= P;
             const int q = ring[p];
             iacc += (long long)(q * q);
         }
         acc = (double)iacc;
     } else {
-        const float* ring = (const float*)B.ring + (size_t)s * B.P;
+        const float* ring = (const float*)ring_s;
         int i = 0;
-        if ((p0 & 3) == 0 && p0 + len <= B.P) {
+        if ((p0 & 3) == 0 && p0 + len <= P) {
             const int nv = len >> 2;
             const float4* v = reinterpret_cast<const float4*>(ring + p0);
-            double a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int k = lane;
-            for (; k + 96 < nv; k += 128) {
-                const float4 q0 = __ldg(v + k), q1 = __ldg(v + k + 32), q2 = __ldg(v + k + 64), q3 = __ldg(v + k + 96);
-                acc = fma((double)q0.x, (double)q0.x, acc); acc = fma((double)q0.y, (double)q0.y, acc);
-                acc = fma((double)q0.z, (double)q0.z, acc); acc = fma((double)q0.w, (double)q0.w, acc);
-                a1 = fma((double)q1.x, (double)q1.x, a1); a1 = fma((double)q1.y, (double)q1.y, a1);
-                a1 = fma((double)q1.z, (double)q1.z, a1); a1 = fma((double)q1.w, (double)q1.w, a1);
-                a2 = fma((double)q2.x, (double)q2.x, a2); a2 = fma((double)q2.y, (double)q2.y, a2);
-                a2 = fma((double)q2.z, (double)q2.z, a2); a2 = fma((double)q2.w, (double)q2.w, a2);
-                a3 = fma((double)q3.x, (double)q3.x, a3); a3 = fma((double)q3.y, (double)q3.y, a3);
-                a3 = fma((double)q3.z, (double)q3.z, a3); a3 = fma((double)q3.w, (double)q3.w, a3);
+            double a1 = 0.0;
+            for (int k0 = 0; k0 < nv; k0 += 256) {
+                float4 q[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int k = k0 + lane + 32 * u;
+                    q[u] = k < nv ? __ldg(v + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) { acc = sq4(q[u], acc); a1 = sq4(q[u + 1], a1); }
             }
-            for (; k < nv; k += 32) {
-                const float4 q0 = __ldg(v + k);
-                acc = fma((double)q0.x, (double)q0.x, acc); acc = fma((double)q0.y, (double)q0.y, acc);
-                acc = fma((double)q0.z, (double)q0.z, acc); acc = fma((double)q0.w, (double)q0.w, acc);
-            }
-            acc += (a1 + a2) + a3;
+            acc += a1;
             i = nv << 2;
         }
         for (int k = i + lane; k < len; k += 32) {
             int p = p0 + k;
-            if (p >= B.P) p -= B.P;
+            if (p >= P) p -= P;
             const double x = (double)ring[p];
             acc = fma(x, x, acc);
         }
@@ -216,37 +223,21 @@ __device__ __noinline__ double warp_sumsq(const BankView& B, int s, long long a0
 // mean square of storage-order chunk c as the reference's ring holds it when V samples are visible:
 // logical position p < V % R was written in the current lap, p >= V % R in the previous one.
 __device__ __forceinline__ double warp_chunk_ms(const BankView& B, int s, long long V, int fs, int c, int lane) {
+    const void* ring_s = (const char*)B.ring + (size_t)s * B.P * (B.fmt == 1 ? 2 : 4);
     const long long lap = V / B.R;
     const int q = (int)(V % B.R);
     const int lo = c * fs, hi = lo + fs;
     const int split = min(max(q, lo), hi);            // [lo, split) current lap, [split, hi) previous lap
     double ss = 0.0;
-    if (split > lo) ss += warp_sumsq(B, s, lap * B.R + lo, split - lo, lane);
-    if (hi > split) ss += warp_sumsq(B, s, (lap - 1) * B.R + split, hi - split, lane);
+    if (split > lo) ss += warp_sumsq(ring_s, B.P, B.fmt, lap * B.R + lo, split - lo, lane);
+    if (hi > split) ss += warp_sumsq(ring_s, B.P, B.fmt, (lap - 1) * B.R + split, hi - split, lane);
     if (B.fmt == 1) ss *= (1.0 / 1073741824.0);       // (q/32768)^2, exact power of two
     return ss / (double)fs;                           // np.mean(frame**2)            wakeword.py:481
 }
 
-constexpr int GATE_WARPS = GATE_THREADS / 32;
-constexpr int GATE_MAX_TICKS = 32;     // ticks per launch (the host splits longer requests)
-constexpr int GATE_MAXP = 12;          // chunk pieces planned per tick; more -> the tick is "heavy"
-
-// block-wide sum of a small per-thread int pair (packed lo/hi 16+16 bits is too narrow: use two ints)
-__device__ __forceinline__ int2 block_sum2(int a, int b, int* red, int tid) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); }
-    __syncthreads();                                   // red[] free again
-    if ((tid & 31) == 0) { red[(tid >> 5) * 2] = a; red[(tid >> 5) * 2 + 1] = b; }
-    __syncthreads();
-    int ra = 0, rb = 0;
-#pragma unroll
-    for (int w = 0; w < GATE_WARPS; w++) { ra += red[w * 2]; rb += red[w * 2 + 1]; }
-    return make_int2(ra, rb);
-}
-
-// sorted[] <- ascending order of ms[0..n) (rank by counting; ties broken by index).  Block-wide.
-__device__ __forceinline__ void block_sort_build(const double* ms, double* sorted, int n, int tid) {
-    for (int i = tid; i < n; i += GATE_THREADS) {
+// sorted[] <- ascending order of ms[0..n) (rank by counting; ties broken by index).  One warp.
+__device__ __forceinline__ void warp_sort_build(const double* ms, double* sorted, int n, int lane) {
+    for (int i = lane; i < n; i += 32) {
         const long long vi = __double_as_longlong(ms[i]);
         int r = 0;
         for (int j = 0; j < n; j++) {
@@ -255,36 +246,33 @@ __device__ __forceinline__ void block_sort_build(const double* ms, double* sorte
         }
         sorted[r] = ms[i];
     }
-    __syncthreads();
+    __syncwarp();
 }
 
-// Replace one occurrence of `oldv` by `newv` in the ascending array S[0..n) (block-wide; T is a
-// second buffer; returns with the result in S).  Non-negative doubles order like their bit patterns.
-__device__ __forceinline__ void block_sorted_replace(double*& S, double*& T, int n, double oldv, double newv,
-                                                     int* red, int tid) {
+// Replace one occurrence of `oldv` by `newv` in the ascending array S[0..n) (one warp; T is a second
+// buffer; returns with the result in S).  Non-negative doubles order like their bit patterns.
+__device__ __forceinline__ void warp_sorted_replace(double*& S, double*& T, int n, double oldv, double newv, int lane) {
     const long long bo = __double_as_longlong(oldv), bn = __double_as_longlong(newv);
     if (bo == bn) return;
     int lo = 0, ln = 0;
-    for (int i = tid; i < n; i += GATE_THREADS) {
-        const long long v = __double_as_longlong(S[i]);
-        lo += v < bo;
-        ln += v < bn;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const long long v = i < n ? __double_as_longlong(S[i]) : 0x7fffffffffffffffLL;
+        lo += __popc(__ballot_sync(FULL, v < bo));
+        ln += __popc(__ballot_sync(FULL, v < bn));
     }
-    const int2 c = block_sum2(lo, ln, red, tid);
-    const int pos_old = c.x;
-    const int pos_new = c.y - (bo < bn ? 1 : 0);       // index in the array with `oldv` removed
-    for (int i = tid; i < n; i += GATE_THREADS) {
+    const int pos_old = lo;
+    const int pos_new = ln - (bo < bn ? 1 : 0);        // index in the array with `oldv` removed
+    for (int i = lane; i < n; i += 32) {
         double v;
         if (i == pos_new) v = newv;
         else {
-            // index i of the new array <- index of the old array
-            int r = i > pos_new ? i - 1 : i;           // position in the "removed" array
-            int src = r >= pos_old ? r + 1 : r;
-            v = S[src];
+            const int r = i > pos_new ? i - 1 : i;     // position in the "removed" array
+            v = S[r >= pos_old ? r + 1 : r];
         }
         T[i] = v;
     }
-    __syncthreads();
+    __syncwarp();
     double* t = S; S = T; T = t;
 }
 
@@ -302,63 +290,149 @@ __device__ __forceinline__ double percentile25_rms_sorted(const double* S, int n
     return r;
 }
 
-struct GatePlan {
+struct GatePlan {                                   // one per warp (= per stream)
     long long V[GATE_MAX_TICKS];                    // samples visible at each tick
     double pv[GATE_MAX_TICKS][GATE_MAXP + 1];       // piece values; [GATE_MAXP] = recent-window sum of squares
     short pc[GATE_MAX_TICKS][GATE_MAXP];            // chunk index of each piece
     unsigned char np[GATE_MAX_TICKS];               // chunk pieces; 255: heavy tick (all chunks, done in phase 2)
     unsigned char alias[GATE_MAX_TICKS];            // recent window == piece 0 (frame_size 1600, aligned)
     unsigned char full[GATE_MAX_TICKS];
-    int flat0[GATE_MAX_TICKS + 1];                  // prefix offsets of (tick, piece) work items
 };
 
+// The 4-state timing machine + segment cut of WakeWord._detect_word for one tick (lane 0 only).
+__device__ __forceinline__ unsigned gate_state_step(const BankView& B, int s, StreamState& st, const StreamParams& prm,
+                                                    long long k, long long V, bool full, int silent) {
+    unsigned evflag = 0;
+    const double now = __dmul_rn((double)k, 0.1);
+    if (full && !st.started) {                                  // _wait_for_buffer done -> _detect_word entry
+        st.started = 1;
+        st.state = silent ? ST_IN_SILENCE : ST_WAITING;        // wakeword.py:1048, 1055-1057
+        st.start_time = now;                                    // :1052
+        if (silent) st.silence_start = now;
+        return 0;
+    }
+    if (!st.started) return 0;
+    // loop top: the timeout check uses time() before the sleep (:1061), i.e. the previous tick's time
+    const double prev = __dmul_rn((double)(k - 1), 0.1);
+    if (prm.timeout > 0.0 && __dsub_rn(prev, st.start_time) > prm.timeout) {
+        // TimeoutError -> the listen loop re-enters _detect_word at `prev` (:1205-1211)
+        const int idx = atomicAdd(B.ev_count, 1);
+        if (idx < B.max_events) {
+            EventRec e{};
+            e.stream = s; e.kind = EV_TIMEOUT; e.tick = k - 1; e.score = __int_as_float(0x7fc00000);
+            B.events[idx] = e;
+        } else { atomicAdd(B.ev_count + 1, 1); atomicSub(B.ev_count, 1); }
+        st.n_timeouts++;
+        st.state = st.last_silent ? ST_IN_SILENCE : ST_WAITING;
+        st.start_time = prev;
+        if (st.last_silent) st.silence_start = prev;
+    }
+    switch (st.state) {
+        case ST_WAITING:                                        // :1069-1072
+            if (silent) { st.state = ST_IN_SILENCE; st.silence_start = now; }
+            break;
+        case ST_IN_SILENCE:                                     // :1074-1081
+            if (!silent) {
+                if (__dsub_rn(now, st.silence_start) >= prm.pre_speech_silence) {
+                    st.state = ST_IN_SOUND; st.sound_start = now;
+                } else st.state = ST_WAITING;
+            }
+            break;
+        case ST_IN_SOUND: {                                     // :1083-1094
+            const double dur = __dsub_rn(now, st.sound_start);
+            if (!silent) { if (dur > prm.speech_duration_max) st.state = ST_WAITING; }
+            else if (prm.speech_duration_min <= dur && dur <= prm.speech_duration_max) {
+                st.state = ST_AFTER_SOUND; st.sound_end = now;
+            } else st.state = ST_WAITING;
+            break;
+        }
+        case ST_AFTER_SOUND:                                    // :1096-1157
+            if (silent) {
+                if (__dsub_rn(now, st.sound_end) >= prm.post_speech_silence) {
+                    const double es = __dsub_rn(__dsub_rn(st.sound_start, now), 0.05);   // :1102
+                    const double ee = __dadd_rn(__dsub_rn(st.sound_end, now), 0.05);     // :1103
+                    long long n_back = (long long)__dmul_rn(fabs(es), 16000.0);          // :500
+                    const long long n_drop = (long long)__dmul_rn(fabs(ee), 16000.0);    // :1108
+                    if (n_back > B.R) n_back = B.R;                                      // :501-502
+                    const long long len = n_back - n_drop;
+                    if (len >= 1 && len <= MAX_SEG) {                                    // :1114-1118
+                        const int idx = atomicAdd(B.ev_count, 1);
+                        if (idx < B.max_events) {
+                            EventRec e{};
+                            e.stream = s; e.kind = EV_PENDING; e.tick = k;
+                            e.seg_start = V - n_back; e.seg_len = (int)len;
+                            e.tmpl = -1; e.score = __int_as_float(0x7fc00000); e.matched = 0;
+                            B.events[idx] = e;
+                            st.n_events++;
+                            evflag = 16u;
+                        } else { atomicAdd(B.ev_count + 1, 1); atomicSub(B.ev_count, 1); }
+                    }
+                    st.state = ST_WAITING;                      // :1117, 1155
+                }
+            } else st.state = ST_WAITING;                       // :1157
+            break;
+    }
+    return evflag;
+}
+
 // ------------------------------------------------------------------------------------ K2
-// One CTA per stream.  Phase 0 plans which sample ranges each of the n_ticks ticks needs; phase 1
-// sums them all in parallel (the only HBM traffic, every new sample read once with 16-byte loads);
-// phase 2 replays the ticks in order: chunk updates into an incrementally maintained sorted array,
-// percentile, threshold, is_silent, state machine.
+// One WARP per stream, GATE_WARPS streams per CTA, no block-level barrier: a bank of 4096 streams is a
+// single resident wave of warps.  Phase 0: lane j plans tick j (which sample ranges it needs);
+// phase 1: the warp sums every planned range (the only HBM traffic: each new sample is read once,
+// 16-byte loads, eight in flight per lane); phase 2: the ticks are replayed in order — chunk updates
+// into an incrementally maintained sorted array, percentile, threshold, is_silent, state machine.
 __global__ void __launch_bounds__(GATE_THREADS, 8)
 tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int trace_off, int smem_chunks) {
     extern __shared__ double sm_d[];
-    double* ms = sm_d;                               // [n_chunks] storage order
-    double* SA = ms + smem_chunks;                   // sorted buffers
+    __shared__ GatePlan plans[GATE_WARPS];
+    __shared__ StreamState st_s[GATE_WARPS];
+    __shared__ StreamParams prm_s[GATE_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x * GATE_WARPS + warp;
+    if (s >= B.n_streams) return;
+    double* ms = sm_d + (size_t)warp * 3 * smem_chunks;   // [n_chunks] storage order
+    double* SA = ms + smem_chunks;                       // sorted buffers
     double* SB = SA + smem_chunks;
-    __shared__ GatePlan plan;
-    __shared__ int red[2 * GATE_WARPS];
+    GatePlan& plan = plans[warp];
 
-    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    StreamState st = B.st[s];
-    const StreamParams prm = B.prm[s];
+    // per-stream state and parameters live in shared memory (only lane 0 mutates them)
+    StreamState& st = st_s[warp];
+    const StreamParams& prm = prm_s[warp];
+    if (lane == 0) { st_s[warp] = B.st[s]; prm_s[warp] = B.prm[s]; }
+    __syncwarp();
     const int fs = st.frame_size;
+    const long long tick0 = st.tick, visible0 = st.visible, written0 = st.written;
+    const int valid0 = st.chunks_valid;
     const int n_chunks = fs > 0 ? B.R / fs : 0;
     double* g_ms = B.chunk_ms + (size_t)s * 2 * B.chunk_cap;
     double* g_sorted = g_ms + B.chunk_cap;
     const bool use_chunks = n_chunks > 0 && n_chunks <= B.chunk_cap && n_chunks <= smem_chunks;
-    if (use_chunks && st.chunks_valid)
-        for (int i = tid; i < n_chunks; i += GATE_THREADS) { ms[i] = g_ms[i]; SA[i] = g_sorted[i]; }
+    if (use_chunks && valid0)
+        for (int i = lane; i < n_chunks; i += 32) { ms[i] = g_ms[i]; SA[i] = g_sorted[i]; }
 
-    // ---- phase 0: plan (thread 0)
-    if (tid == 0) {
-        long long Vp = st.visible;
-        long long k = st.tick;
-        int valid = st.chunks_valid;
-        int flat = 0;
-        for (int j = 0; j < n_ticks; j++) {
-            k++;
-            long long V = Vp;
-            if (fs > 0) {
-                const long long avail = (st.written / fs) * fs;
-                V = prm.live ? st.written : min((k * TICK / fs) * fs, avail);
-                if (V < Vp) V = Vp;
+    // ---- phase 0: lane j plans tick j
+    {
+        const int j = lane;
+        long long V = visible0, Vp = visible0;
+        if (fs > 0 && j < n_ticks) {
+            const long long avail = (written0 / fs) * fs;
+            const long long k = tick0 + j + 1;
+            V = prm.live ? written0 : min((k * TICK / fs) * fs, avail);
+            if (V < visible0) V = visible0;
+            if (j > 0) {
+                Vp = prm.live ? written0 : min(((k - 1) * TICK / fs) * fs, avail);
+                if (Vp < visible0) Vp = visible0;
             }
-            plan.V[j] = V;
-            const bool full = fs > 0 && V >= B.R;                       // is_buffer_full   wakeword.py:515-517
-            plan.full[j] = full;
-            int np = 0;
-            plan.alias[j] = 0;
-            if (full && use_chunks && V > Vp) {
+        }
+        const bool full = fs > 0 && V >= B.R;                           // is_buffer_full   wakeword.py:515-517
+        const bool upd = j < n_ticks && full && use_chunks && V > Vp;
+        const unsigned updmask = __ballot_sync(FULL, upd);
+        const bool valid_before = valid0 || (updmask & ((1u << j) - 1u));
+        if (j < n_ticks) {
+            int np = 0, alias = 0;
+            if (upd) {
                 const long long dv = V - Vp;
-                if (!valid || dv >= B.R) np = 255;
+                if (!valid_before || dv >= B.R) np = 255;
                 else {
                     // storage-order chunks touched by the new samples: logical positions [q0, q0+dv) mod R
                     const int q0 = (int)(Vp % B.R);
@@ -367,77 +441,71 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
                     const int c1 = q0 / fs;
                     const int n1 = (e1 - 1) / fs - c1 + 1;
                     const int n2 = e > B.R ? (int)((e - B.R - 1) / fs) + 1 : 0;
-                    for (int i = 0; i < n1 + n2 && np != 255; i++) {
+                    for (int i = 0; i < n1 + n2; i++) {
                         const int c = i < n1 ? c1 + i : i - n1;
                         if (c >= n_chunks) continue;                    // the tail R - n_chunks*fs is in no chunk
                         if (np == GATE_MAXP) { np = 255; break; }
                         plan.pc[j][np++] = (short)c;
                     }
-                    if (np == 1 && fs == TICK && dv == TICK && (q0 % TICK) == 0 && B.R >= TICK) plan.alias[j] = 1;
+                    if (np == 1 && fs == TICK && dv == TICK && (q0 % TICK) == 0 && B.R >= TICK) alias = 1;
                 }
-                valid = 1;
             }
+            plan.V[j] = V;
+            plan.full[j] = full;
             plan.np[j] = (unsigned char)np;
-            plan.flat0[j] = flat;
-            flat += (np == 255 ? 0 : np) + (fs > 0 && !plan.alias[j] ? 1 : 0);
-            Vp = V;
+            plan.alias[j] = (unsigned char)alias;
         }
-        plan.flat0[n_ticks] = flat;
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- phase 1: every planned range, one warp per piece
+    // ---- phase 1: every planned range
     const int nrec = min(TICK, B.R);
-    {
-        const int total = plan.flat0[n_ticks];
-        int j = 0;
-        for (int f = warp; f < total; f += GATE_WARPS) {
-            while (plan.flat0[j + 1] <= f) j++;
-            const int i = f - plan.flat0[j];
-            const int np = plan.np[j] == 255 ? 0 : plan.np[j];
-            const long long V = plan.V[j];
-            if (i < np) {
-                const double v = warp_chunk_ms(B, s, V, fs, plan.pc[j][i], lane);
-                if (lane == 0) plan.pv[j][i] = v;
-            } else {
-                // RMS window of is_silent: the last min(1600, R) samples; zeros before the stream began
-                const long long a0 = V - nrec;
-                const double ss = warp_sumsq(B, s, a0 < 0 ? 0 : a0, (int)(a0 < 0 ? V : nrec), lane);
-                if (lane == 0) plan.pv[j][GATE_MAXP] = ss;
-            }
+    for (int j = 0; j < n_ticks; j++) {
+        const long long V = plan.V[j];
+        const int np = plan.np[j] == 255 ? 0 : plan.np[j];
+        for (int i = 0; i < np; i++) {
+            const double v = warp_chunk_ms(B, s, V, fs, plan.pc[j][i], lane);
+            if (lane == 0) plan.pv[j][i] = v;
+        }
+        if (fs > 0 && !plan.alias[j]) {
+            // RMS window of is_silent: the last min(1600, R) samples; zeros before the stream began
+            const long long a0 = V - nrec;
+            const double ss = warp_sumsq((const char*)B.ring + (size_t)s * B.P * (B.fmt == 1 ? 2 : 4), B.P, B.fmt,
+                                         a0 < 0 ? 0 : a0, (int)(a0 < 0 ? V : nrec), lane);
+            if (lane == 0) plan.pv[j][GATE_MAXP] = ss;
         }
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- phase 2: replay the ticks in order
     unsigned evflag = 0;
-    int valid = st.chunks_valid;
+    int valid = valid0;
     for (int j = 0; j < n_ticks; j++) {
-        const long long k = st.tick + 1;
+        const long long k = tick0 + j + 1;
         const long long V = plan.V[j];
         const bool full = plan.full[j];
         const int np = plan.np[j];
         if (np == 255) {
             // heavy tick (first full ring, or a jump of a whole ring): every chunk from samples, then sort
-            for (int c = warp; c < n_chunks; c += GATE_WARPS) {
+            for (int c = 0; c < n_chunks; c++) {
                 const double v = warp_chunk_ms(B, s, V, fs, c, lane);
                 if (lane == 0) ms[c] = v;
             }
-            __syncthreads();
-            block_sort_build(ms, SA, n_chunks, tid);
+            __syncwarp();
+            warp_sort_build(ms, SA, n_chunks, lane);
             valid = 1;
         } else {
             for (int i = 0; i < np; i++) {
                 const int c = plan.pc[j][i];
                 const double nv = plan.pv[j][i];
                 const double ov = ms[c];
-                __syncthreads();
-                block_sorted_replace(SA, SB, n_chunks, ov, nv, red, tid);
-                if (tid == 0) ms[c] = nv;
-                __syncthreads();
+                __syncwarp();
+                warp_sorted_replace(SA, SB, n_chunks, ov, nv, lane);
+                if (lane == 0) ms[c] = nv;
+                __syncwarp();
             }
         }
-        if (tid == 0) {
+        if (lane == 0) {
             if (np != 0) {
                 const double p25 = percentile25_rms_sorted(SA, n_chunks);
                 const double nt = __dmul_rn(p25, 1.5);                  // wakeword.py:485
@@ -453,76 +521,8 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
                 rms = sqrt(ss / (double)nrec);
                 silent = rms < st.thr;
             }
-            // ---- state machine (wakeword.py:1036-1157)
-            const double now = __dmul_rn((double)k, 0.1);
             st.last_rms = rms;
-            if (full && !st.started) {                                  // _wait_for_buffer done -> _detect_word entry
-                st.started = 1;
-                st.state = silent ? ST_IN_SILENCE : ST_WAITING;        // :1048, 1055-1057
-                st.start_time = now;                                    // :1052
-                if (silent) st.silence_start = now;
-            } else if (st.started) {
-                // loop top: the timeout check uses time() before the sleep (:1061), i.e. the previous tick's time
-                const double prev = __dmul_rn((double)(k - 1), 0.1);
-                if (prm.timeout > 0.0 && __dsub_rn(prev, st.start_time) > prm.timeout) {
-                    // TimeoutError -> the listen loop re-enters _detect_word at `prev` (:1205-1211)
-                    const int idx = atomicAdd(B.ev_count, 1);
-                    if (idx < B.max_events) {
-                        EventRec e{};
-                        e.stream = s; e.kind = EV_TIMEOUT; e.tick = k - 1; e.score = __int_as_float(0x7fc00000);
-                        B.events[idx] = e;
-                    } else { atomicAdd(B.ev_count + 1, 1); atomicSub(B.ev_count, 1); }
-                    st.n_timeouts++;
-                    st.state = st.last_silent ? ST_IN_SILENCE : ST_WAITING;
-                    st.start_time = prev;
-                    if (st.last_silent) st.silence_start = prev;
-                }
-                switch (st.state) {
-                    case ST_WAITING:                                    // :1069-1072
-                        if (silent) { st.state = ST_IN_SILENCE; st.silence_start = now; }
-                        break;
-                    case ST_IN_SILENCE:                                 // :1074-1081
-                        if (!silent) {
-                            if (__dsub_rn(now, st.silence_start) >= prm.pre_speech_silence) {
-                                st.state = ST_IN_SOUND; st.sound_start = now;
-                            } else st.state = ST_WAITING;
-                        }
-                        break;
-                    case ST_IN_SOUND: {                                 // :1083-1094
-                        const double dur = __dsub_rn(now, st.sound_start);
-                        if (!silent) { if (dur > prm.speech_duration_max) st.state = ST_WAITING; }
-                        else if (prm.speech_duration_min <= dur && dur <= prm.speech_duration_max) {
-                            st.state = ST_AFTER_SOUND; st.sound_end = now;
-                        } else st.state = ST_WAITING;
-                        break;
-                    }
-                    case ST_AFTER_SOUND:                                // :1096-1157
-                        if (silent) {
-                            if (__dsub_rn(now, st.sound_end) >= prm.post_speech_silence) {
-                                const double es = __dsub_rn(__dsub_rn(st.sound_start, now), 0.05);   // :1102
-                                const double ee = __dadd_rn(__dsub_rn(st.sound_end, now), 0.05);     // :1103
-                                long long n_back = (long long)__dmul_rn(fabs(es), 16000.0);          // :500
-                                const long long n_drop = (long long)__dmul_rn(fabs(ee), 16000.0);    // :1108
-                                if (n_back > B.R) n_back = B.R;                                      // :501-502
-                                const long long len = n_back - n_drop;
-                                if (len >= 1 && len <= MAX_SEG) {                                    // :1114-1118
-                                    const int idx = atomicAdd(B.ev_count, 1);
-                                    if (idx < B.max_events) {
-                                        EventRec e{};
-                                        e.stream = s; e.kind = EV_PENDING; e.tick = k;
-                                        e.seg_start = V - n_back; e.seg_len = (int)len;
-                                        e.tmpl = -1; e.score = __int_as_float(0x7fc00000); e.matched = 0;
-                                        B.events[idx] = e;
-                                        st.n_events++;
-                                        evflag = 16u;
-                                    } else { atomicAdd(B.ev_count + 1, 1); atomicSub(B.ev_count, 1); }
-                                }
-                                st.state = ST_WAITING;                  // :1117, 1155
-                            }
-                        } else st.state = ST_WAITING;                   // :1157
-                        break;
-                }
-            }
+            evflag |= gate_state_step(B, s, st, prm, k, V, full, silent);
             st.last_silent = silent;
             if (tr.silent) {
                 const size_t o = (size_t)s * trace_stride + trace_off + j;
@@ -532,14 +532,13 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
                 tr.rms[o] = rms;
             }
         }
-        st.tick = k;
-        st.visible = V;
+        if (lane == 0) { st.tick = k; st.visible = V; }
     }
-    __syncthreads();
+    __syncwarp();
 
     if (use_chunks && valid)
-        for (int i = tid; i < n_chunks; i += GATE_THREADS) { g_ms[i] = ms[i]; g_sorted[i] = SA[i]; }
-    if (tid == 0) {
+        for (int i = lane; i < n_chunks; i += 32) { g_ms[i] = ms[i]; g_sorted[i] = SA[i]; }
+    if (lane == 0) {
         st.chunks_valid = valid;
         B.st[s] = st;
         StreamResult r = B.results[s];
