@@ -384,6 +384,8 @@ int ewk_ctx::init_streams() {
     h_frame_size.assign(n, 0);
     CK(cudaFuncSetAttribute(segment_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
+    CK(cudaFuncSetAttribute(tick_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(sizeof(double) * 3 * (size_t)chunk_cap * GATE_WARPS)));
     return EWK_OK;
 }
 
