@@ -226,6 +226,7 @@ def _declare_stream_protos(lib):
         "ewk_read_last": (C.c_int, [vp, i32, i64, f32p]),
         "ewk_read_segment": (C.c_int, [vp, i32, i64, i64, f32p]),
         "ewk_stream_results": (C.c_int, [vp, vp]),
+        "ewk_dense_scores": (C.c_int, [vp, i64, i32, i32, i32, vp, i32]),
         "ewk_results_device_ptr": (C.c_int, [vp, _p(vp)]),
         "ewk_set_results_buffer": (C.c_int, [vp, vp]),
         "ewk_host_alloc": (C.c_int, [_p(vp), i64]),
@@ -351,6 +352,17 @@ def _bank_methods():
         self._ck(self.lib.ewk_read_segment(self.h, stream, int(seg_start), int(seg_len), f32ptr(out)))
         return out
 
+    def dense_scores(self, hop0, n_hops, template_first=0, template_count=1, out_device_ptr=None):
+        """[n_streams, n_hops, template_count] float32 scores for hops [hop0, hop0 + n_hops)."""
+        if out_device_ptr is not None:
+            self._ck(self.lib.ewk_dense_scores(self.h, int(hop0), int(n_hops), template_first, template_count,
+                                               C.c_void_p(out_device_ptr), DEVICE))
+            return None
+        out = np.empty((self.cfg.n_streams, int(n_hops), template_count), np.float32)
+        self._ck(self.lib.ewk_dense_scores(self.h, int(hop0), int(n_hops), template_first, template_count,
+                                           out.ctypes.data, HOST))
+        return out
+
     def results(self):
         out = np.empty(self.cfg.n_streams, dtype=RESULT_DTYPE)
         self._ck(self.lib.ewk_stream_results(self.h, out.ctypes.data))
@@ -380,7 +392,7 @@ def _bank_methods():
         names = ["ring_push", "tick_gate", "segment_queue", "segment_batch", "dense_score"]
         return {names[i]: {"ms": ms[i], "launches": int(n[i])} for i in range(len(names))}
 
-    for f in (profile, profile_read, set_stream_params, push, tick, poll, status, read_last, read_segment, results, results_device_ptr,
+    for f in (dense_scores, profile, profile_read, set_stream_params, push, tick, poll, status, read_last, read_segment, results, results_device_ptr,
               set_results_buffer, set_cuda_stream, launch_count):
         setattr(Context, f.__name__, f)
 

@@ -107,6 +107,12 @@ class WakeWordBank:
     def results(self) -> np.ndarray:
         return self.ctx.results()
 
+    def dense_scores(self, hop0: int, n_hops: int, template_first: int = 0, template_count: Optional[int] = None):
+        """Per-hop scores [n_streams, n_hops, T] for hops [hop0, hop0 + n_hops) (hop h = 160*h samples
+        pushed): calculate_similarity of the latest template-length window complete at each hop (K4)."""
+        T = len(self.templates) - template_first if template_count is None else template_count
+        return self.ctx.dense_scores(hop0, n_hops, template_first, T)
+
     def read_segment(self, event) -> np.ndarray:
         """word_audio of a level-2 event as float32 (what level 3 transcribes)."""
         return self.ctx.read_segment(int(event["stream"]), int(event["seg_start"]), int(event["seg_len"]))

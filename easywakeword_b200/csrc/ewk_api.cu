@@ -395,7 +395,7 @@ void ewk_ctx::release_streams() {
         if (p) cudaFree(p);
     bank = BankView{};
     own_results = nullptr;
-    b_stage.free(); b_trace.free(); b_read.free();
+    b_stage.free(); b_trace.free(); b_read.free(); b_dense.free();
     for (auto& p : prof_pairs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : prof_free) cudaEventDestroy(e);
     prof_pairs.clear(); prof_free.clear();
@@ -673,6 +673,69 @@ extern "C" int ewk_read_segment(ewk_ctx* ctx, int stream, int64_t seg_start, int
     if (ctx->h_written[stream] - seg_start > B.P) { ctx->fail("ewk_read_segment: segment already overwritten in the ring"); return EWK_ERR_STATE; }
     CK(cudaSetDevice(ctx->device));
     return read_abs(ctx, stream, seg_start, seg_len, out);
+}
+
+extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl_first, int tmpl_count, float* out, int where) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_dense_scores");
+    if (rc) return rc;
+    BankView& B = ctx->bank;
+    if (!out || hop0 < 0 || n_hops < 1 || tmpl_count < 1 || tmpl_count > DENSE_MAX_T || tmpl_first < 0 ||
+        tmpl_first + tmpl_count > ctx->cfg.max_templates) {
+        ctx->fail("ewk_dense_scores: bad arguments (hop0=%lld n_hops=%d templates [%d, %d))", (long long)hop0, n_hops,
+                  tmpl_first, tmpl_first + tmpl_count);
+        return EWK_ERR_ARG;
+    }
+    DenseArgs A{};
+    A.hop0 = hop0; A.n_hops = n_hops; A.T = tmpl_count;
+    int max_n = 0;
+    for (int k = 0; k < tmpl_count; k++) {
+        const TemplateFeat& tf = ctx->h_tmpl[tmpl_first + k];
+        if (!tf.valid) { ctx->fail("No reference word set. Call set_reference() first."); return EWK_ERR_NO_TEMPLATE; }
+        const int L = (int)tf.n_samples;
+        if (tf.n_samples < DENSE_MIN_L || tf.n_samples > (long long)HOP * (DENSE_MAX_F - 1)) {
+            ctx->fail("ewk_dense_scores: template %d has %lld samples; dense scoring needs %d..%d", tmpl_first + k,
+                      (long long)tf.n_samples, DENSE_MIN_L, HOP * (DENSE_MAX_F - 1));
+            return EWK_ERR_ARG;
+        }
+        DenseTmplDev& t = A.t[k];
+        t.L = L; t.n = (L + HOP - 1) / HOP; t.F = 1 + L / HOP; t.t_hi = (L - N_FFT / 2) / HOP; t.r = t.F - 1 - t.t_hi;
+        t.slot = tmpl_first + k;
+        max_n = std::max(max_n, t.n);
+    }
+    A.DG = DH + max_n + 8;
+    // the audio of every requested window must be resident
+    const long long need_hi = 160LL * (hop0 + n_hops - 1);
+    const long long need_lo = std::max<long long>(0, 160LL * (hop0 - max_n) - N_FFT / 2);
+    for (int s = 0; s < B.n_streams; s++) {
+        if (ctx->h_written[s] < need_hi) {
+            ctx->fail("ewk_dense_scores: stream %d has %lld samples, hop %lld needs %lld", s, ctx->h_written[s],
+                      (long long)(hop0 + n_hops - 1), need_hi);
+            return EWK_ERR_STATE;
+        }
+        if (ctx->h_written[s] - need_lo > B.P) {
+            ctx->fail("ewk_dense_scores: stream %d no longer holds sample %lld (ring of %d)", s, need_lo, B.P);
+            return EWK_ERR_STATE;
+        }
+    }
+    CK(cudaSetDevice(ctx->device));
+    const size_t n_out = (size_t)B.n_streams * n_hops * tmpl_count;
+    float* d_out = out;
+    if (where == EWK_HOST) { CK(ctx->b_dense.ensure(sizeof(float) * n_out)); d_out = (float*)ctx->b_dense.p; }
+    A.out = d_out;
+    const size_t smem = dense_smem_bytes(A.DG, A.T);
+    if (smem > 227 * 1024) { ctx->fail("ewk_dense_scores: templates too long for shared memory (%zu B)", smem); return EWK_ERR_ARG; }
+    CK(cudaFuncSetAttribute(dense_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t pe = ctx->prof_begin(4);
+    dense_score_kernel<<<B.n_streams, DENSE_THREADS, smem, ctx->stream>>>(ctx->d_tables, B, ctx->d_tmpl, A);
+    ctx->prof_end(pe, 4);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (where == EWK_HOST) {
+        CK(cudaMemcpyAsync(out, d_out, sizeof(float) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return EWK_OK;
 }
 
 extern "C" int ewk_stream_results(ewk_ctx* ctx, ewk_stream_result* out) {

@@ -8,6 +8,7 @@
 #include "ewk_frame.cuh"
 #include "ewk_segment.cuh"
 #include "ewk_streams.cuh"
+#include "ewk_dense.cuh"
 #include "ewk_tables.hpp"
 
 #define EWK_MAX_TEMPLATES 64
@@ -48,7 +49,7 @@ struct ewk_ctx {
     // stream bank
     ewk::BankView bank{};
     void* own_results = nullptr;
-    ewk::DevBuf b_stage, b_trace, b_read;
+    ewk::DevBuf b_stage, b_trace, b_read, b_dense;
     int chunk_cap = 0;
     long long launches = 0;
     std::vector<ewk::StreamParams> h_prm;

@@ -122,8 +122,7 @@ __device__ __forceinline__ void seg_prologue(const DeviceTables* __restrict__ T,
 
 // The lane's eight sample pairs (2 lane + 64 a, +1) of frame t, zero outside the segment
 // (librosa center=True, pad_mode='constant').
-__device__ __forceinline__ void load_frame_pairs(const PcmReader& rd, int t, int lane, float2 (&x)[8]) {
-    const int f0 = t * HOP - N_FFT / 2;
+__device__ __forceinline__ void load_frame_pairs_at(const PcmReader& rd, int f0, int lane, float2 (&x)[8]) {
     const long long base = rd.fast_base(f0);
     if (base >= 0) {
         if (rd.q) {
@@ -145,6 +144,10 @@ __device__ __forceinline__ void load_frame_pairs(const PcmReader& rd, int t, int
             x[a] = make_float2(rd.at(i), rd.at(i + 1));
         }
     }
+}
+
+__device__ __forceinline__ void load_frame_pairs(const PcmReader& rd, int t, int lane, float2 (&x)[8]) {
+    load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
 }
 
 // Phases A-D for one segment by the whole CTA.  Returns a shared-memory pointer to mean[20] ++ std[20]

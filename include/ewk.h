@@ -159,6 +159,18 @@ int ewk_stream_status_get(ewk_ctx* ctx, int stream, ewk_stream_status* out);
 int ewk_read_last(ewk_ctx* ctx, int stream, int64_t n_samples, float* out);
 /* word_audio of an event (wakeword.py:1105-1111) for the level-3 hand-off; EWK_ERR_STATE if overwritten. */
 int ewk_read_segment(ewk_ctx* ctx, int stream, int64_t seg_start, int64_t seg_len, float* out);
+/* Dense per-hop scoring (usage shape of examples/tune_threshold.py:86-116 at hop
+ * granularity): for every stream, every hop h in [hop0, hop0 + n_hops) (hop h <-> 160*h samples pushed)
+ * and every template slot k in [template_first, template_first + template_count), the value
+ * WordMatcher.calculate_similarity (wakeword.py:591-625) returns for the window
+ *     x[160*(h - n_k) : 160*(h - n_k) + L_k],  n_k = ceil(L_k / 160)
+ * i.e. the latest template-length window that starts on the hop grid and is complete at hop h
+ * (window-local zero-pad centring and top_db floor).  out[(stream * n_hops + (h - hop0)) * template_count
+ * + k], NaN where the window starts before the stream.  The audio must have been pushed and still be in
+ * the ring (EWK_ERR_STATE otherwise).  Templates must have 640 <= L_k <= 35680 samples; template_count <= 4.
+ * `where` tells whether `out` is host or device memory. */
+int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int template_first, int template_count,
+                     float* out, int where);
 /* Copy the dense per-stream results [n_streams] to host memory. */
 int ewk_stream_results(ewk_ctx* ctx, ewk_stream_result* out);
 /* Device pointer of that array (ewk_stream_result[n_streams]); or make the kernels write into a

@@ -1,0 +1,94 @@
+"""GPU parity: K4 dense per-hop scoring through the C-ABI vs goldens produced by the reference's
+WordMatcher.calculate_similarity on every dense window (strided), and vs the oracle on extra hops.
+Tolerance: 0.01 on the 0-100 scale (BASELINE.json)."""
+import numpy as np
+import pytest
+
+from easywakeword_b200 import synth
+from helpers import sha
+
+pytestmark = pytest.mark.gpu
+SCORE_ATOL = 0.01
+
+
+def make_ctx(n_streams, fmt, templates):
+    from easywakeword_b200 import _lib
+    ctx = _lib.Context(device=0, n_streams=n_streams, ring_samples=200000, slack_samples=16000,
+                       pcm_format=_lib.PCM_I16 if fmt == "i16" else _lib.PCM_F32, max_templates=4)
+    for i, t in enumerate(templates):
+        ctx.set_template(i, t)
+    ctx.set_stream_params(-1, frame_size=1600, template_count=len(templates))
+    return ctx
+
+
+@pytest.mark.parametrize("fmt", ["i16", "f32"])
+def test_dense_scores_match_reference_goldens(fmt, golden_dense, word):
+    g = golden_dense
+    tpls = [word, g["tpl2"]]
+    xs = []
+    for si in range(2):
+        x, _ = synth.stream(int(g[f"s{si}_seed"]), 12.0, word, gain=(1.0, 4.0), zero_gaps=int(g[f"s{si}_zero_gaps"]))
+        x = synth.from_int16(synth.to_int16(x))
+        assert sha(x) == str(g[f"s{si}_sha"])
+        xs.append(x)
+    ctx = make_ctx(2, fmt, tpls)
+    pcm = np.stack([synth.to_int16(x) if fmt == "i16" else x for x in xs])
+    ctx.push(pcm)
+    sc = ctx.dense_scores(200, 1000, 0, 2)          # hops 200 .. 1199
+    assert sc.shape == (2, 1000, 2)
+    worst = 0.0
+    for si in range(2):
+        hops = g[f"s{si}_hops"]
+        ref = g[f"s{si}_scores"]
+        got = sc[si, hops - 200, :].astype(np.float64)
+        assert not np.isnan(got).any()
+        worst = max(worst, float(np.abs(got - ref).max()))
+        assert np.abs(got - ref).max() <= SCORE_ATOL, (si, float(np.abs(got - ref).max()))
+    print(f"[{fmt}] worst |dense score - reference| = {worst:.2e} over {2 * len(hops) * 2} windows")
+    # chunking of the request must not matter (sub-chunk boundaries, history recomputation)
+    a = ctx.dense_scores(200, 37, 0, 2)
+    b = ctx.dense_scores(237, 100, 0, 2)
+    assert np.array_equal(a, sc[:, :37]) and np.array_equal(b, sc[:, 37:137])
+    one = ctx.dense_scores(300, 64, 1, 1)
+    assert np.array_equal(one[:, :, 0], sc[:, 100:164, 1])
+    ctx.close()
+
+
+def test_dense_vs_oracle_extra_hops_and_early_windows(word):
+    """Hops the goldens do not cover (incl. digital-silence stretches: the floored-frame path) and windows that
+    would start before the stream (NaN)."""
+    from oracle import ewk_oracle as O
+    x, _ = synth.stream(3100, 6.0, word, gain=(2.0, 4.0), zero_gaps=5, noise_sigma=0.0005)
+    x = synth.from_int16(synth.to_int16(x))
+    ctx = make_ctx(1, "i16", [word])
+    ctx.push(synth.to_int16(x).reshape(1, -1))
+    sc = ctx.dense_scores(0, 600, 0, 1)[0, :, 0]
+    n_back, _ = O.dense_window(len(word))
+    assert np.isnan(sc[:n_back]).all() and not np.isnan(sc[n_back:]).any()
+    hops = np.arange(n_back, 600, 11)
+    ref = O.dense_scores(x, [word], hops)[:, 0]
+    assert np.abs(sc[hops] - ref).max() <= SCORE_ATOL, float(np.abs(sc[hops] - ref).max())
+    ctx.close()
+
+
+def test_dense_self_window_is_exactly_100(word):
+    """A window that is exactly the template scores 100.0 (the reference's self-match tests)."""
+    x = np.concatenate([np.zeros(160 * 50, np.float32), word, np.zeros(160 * 20 + 97, np.float32)])
+    ctx = make_ctx(1, "f32", [word])
+    ctx.push(x.reshape(1, -1))
+    from oracle import ewk_oracle as O
+    n_back, _ = O.dense_window(len(word))
+    sc = ctx.dense_scores(50 + n_back, 1, 0, 1)
+    assert sc[0, 0, 0] == 100.0
+    ctx.close()
+
+
+def test_dense_argument_errors(word):
+    ctx = make_ctx(1, "i16", [word])
+    ctx.push(np.zeros((1, 16000), np.int16))
+    with pytest.raises(Exception):
+        ctx.dense_scores(0, 200, 0, 1)         # hop 199 not pushed yet
+    ctx.clear_template(0)
+    with pytest.raises(ValueError, match="No reference word set"):
+        ctx.dense_scores(0, 50, 0, 1)
+    ctx.close()
