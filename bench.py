@@ -257,6 +257,37 @@ def run_ours(args):
     ctx.profile(False)
     bank.poll()
 
+    # dense mode (A9): per-hop scoring of every stream, same push, K4 instead of K2/K3
+    dense_out = torch.empty(n * 100, dtype=torch.float32, device=dev)
+    def dense_step():
+        j = step_no[0] % POOL_SECONDS
+        step_no[0] += 1
+        bank.push(slice_ptr(pool_dev, j), where=_lib.DEVICE)
+        hop_end = bank.samples_pushed // 160
+        ctx.dense_scores(hop_end - 100, 100, 0, 1, out_device_ptr=dense_out.data_ptr())
+    # no ticks in this arm: let pushes run free of the gate's "un-gated audio" guard
+    ctx.set_stream_params(-1, live=1, **PARAMS)
+    dense_steps = max(2, K // 2)
+    for _ in range(2):
+        dense_step()
+    barrier()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record(stream)
+    for _ in range(dense_steps):
+        dense_step()
+    d1.record(stream)
+    barrier()
+    ms_dense = d0.elapsed_time(d1)
+    if world > 1:
+        t = torch.tensor([ms_dense], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dense = float(t.item())
+    ctx.profile(True)
+    for _ in range(2):
+        dense_step()
+    prof_dense = ctx.profile_read()
+    ctx.profile(False)
+
     audio_per_step = n * STEP_SECONDS * world
     value = audio_per_step * K / (ms_dev * 1e-3)
     e2e_val = audio_per_step * K / (ms_e2e * 1e-3)
@@ -316,6 +347,13 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "dense": {"what": "A9 per-hop scoring: 100 hops x 4096 streams per step, 4 FFT frames per hop (1 stream-grid + 3 "
+                              "window-edge), K1 ring_push + K4 dense_score, scores left on the device",
+                      "value": audio_per_step * dense_steps / (ms_dense * 1e-3), "unit": UNIT,
+                      "ms_per_step": ms_dense / dense_steps,
+                      "kernel_ms": prof_dense["dense_score"]["ms"] / max(1, prof_dense["dense_score"]["launches"]),
+                      "windows_per_s": n * 100 * world * dense_steps / (ms_dense * 1e-3),
+                      "hbm_frac": (n * STEP_SAMPLES * 2 + n * 400) * dense_steps / (ms_dense * 1e-3) / 1e9 / hbm_peak},
             "level2_events_per_step": ev_per_step,
             "kernel_ms_per_step": {k: v["ms"] / max(1, K) for k, v in kern.items()},
         }

@@ -53,10 +53,11 @@ __host__ __device__ inline size_t dense_smem_bytes(int DG, int T) {
 }
 
 // frame `t` of the window of template `tp` starting at grid index j: pointer to its ROW
+// (jb = j mod DG, so that the ring index is one add and one conditional subtract)
 __device__ __forceinline__ const float* dense_row(const float* G, const float* edge_kh, const DenseTmplDev& tp, int DG,
-                                                  long long j, int t) {
+                                                  int jb, int t) {
     if (t < 2) return edge_kh + t * ROW;
-    if (t <= tp.t_hi) return G + (size_t)((j + t) % DG) * ROW;
+    if (t <= tp.t_hi) { int r = jb + t; if (r >= DG) r -= DG; return G + r * ROW; }
     return edge_kh + (2 + t - tp.t_hi - 1) * ROW;
 }
 
@@ -102,26 +103,36 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
         if (g_lo < 2) g_lo = 2;                                   // grid frame g needs samples from 160 g - 256 >= 0
         const long long g_from = max(g_lo, g_done);
         const int n_g = (int)max(0LL, g_hi - g_from + 1);
-        const int n_e = A.T * nh * 4;
+        int n_e = 0;
+        for (int k = 0; k < A.T; k++) n_e += nh * (2 + A.t[k].r);
+        // 32-bit bases for this sub-chunk: ring position of sample 160*hs and ring row of grid frame g_from
+        const int hs_pos = (int)((160 * hs) % B.P);
+        const int gfrom_row = n_g > 0 ? (int)(g_from % A.DG) : 0;
+        const int gfrom_rel = (int)(g_from - hs);                  // grid index relative to hs
         for (int job = warp; job < n_g + n_e; job += DENSE_WARPS) {
             float* row;
             int f0;
             if (job < n_g) {
-                const long long g = g_from + job;
-                const long long a0 = 160 * g - N_FFT / 2;         // absolute first sample, unmasked
-                rd.start = a0 % B.P; rd.len = N_FFT;
+                // absolute first sample 160 g - 256 (unmasked frame of the stream grid)
+                int pos = hs_pos + 160 * (gfrom_rel + job) - N_FFT / 2;
+                pos %= B.P; if (pos < 0) pos += B.P;
+                rd.start = pos; rd.len = N_FFT;
                 f0 = 0;
-                row = G + (size_t)(g % A.DG) * ROW;
+                int r = gfrom_row + job; if (r >= A.DG) r -= A.DG;
+                row = G + r * ROW;
             } else {
-                const int e = (job - n_g) & 3, kh = (job - n_g) >> 2;
-                const int k = kh / nh, hl = kh % nh;
+                int rem = job - n_g, k = 0;
+                while (rem >= nh * (2 + A.t[k].r)) { rem -= nh * (2 + A.t[k].r); k++; }
                 const DenseTmplDev& tp = A.t[k];
-                const long long j = hs + hl - tp.n;
-                if (j < 0 || (e >= 2 && e - 2 >= tp.r)) continue;  // window not available / no such right-edge frame
+                const int per = 2 + tp.r;
+                const int hl = rem / per, e = rem - hl * per;
+                if (hs + hl - tp.n < 0) continue;                   // window starts before the stream
                 const int t = e < 2 ? e : tp.t_hi + 1 + (e - 2);
-                rd.start = (160 * j) % B.P; rd.len = tp.L;          // zeros outside the window
+                int pos = hs_pos + 160 * (hl - tp.n);
+                pos %= B.P; if (pos < 0) pos += B.P;
+                rd.start = pos; rd.len = tp.L;                      // zeros outside the window
                 f0 = t * HOP - N_FFT / 2;
-                row = edge + ((size_t)(k * DH + hl) * 4 + e) * ROW;
+                row = edge + ((k * DH + hl) * 4 + e) * ROW;
             }
             float2 x[8];
             load_frame_pairs_at(rd, f0, lane, x);
@@ -134,12 +145,13 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
 
         // ---- windows of this sub-chunk, one warp per (template, hop)
         for (int w = warp; w < A.T * nh; w += DENSE_WARPS) {
-            const int k = w / nh, hl = w % nh;
+            const int k = w / nh, hl = w - k * nh;
             const DenseTmplDev tp = A.t[k];
-            const long long j = hs + hl - tp.n;
+            const long long jl = hs + hl - tp.n;
             float* outp = A.out + ((size_t)s * A.n_hops + (size_t)(hs - A.hop0 + hl)) * A.T + k;
-            if (j < 0) { if (lane == 0) *outp = __int_as_float(0x7fc00000); continue; }
-            const float* ekh = edge + (size_t)(k * DH + hl) * 4 * ROW;
+            if (jl < 0) { if (lane == 0) *outp = __int_as_float(0x7fc00000); continue; }
+            const int j = (int)(jl % A.DG);                            // ring row base of this window
+            const float* ekh = edge + (k * DH + hl) * 4 * ROW;
             // window max of the frames' log-mel max -> floor (librosa.power_to_db(top_db=80) on this window)
             float wmax = -INFINITY;
             for (int t = lane; t < tp.F; t += 32) wmax = fmaxf(wmax, dense_row(G, ekh, tp, A.DG, j, t)[N_MFCC + 1]);
@@ -158,7 +170,8 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
             __syncwarp();
             if (n_aff) {
                 // recompute the floored frames (window-local PCM view), keep the first PATCH_CAP of them
-                rd.start = (160 * j) % B.P; rd.len = tp.L;
+                { int pos = hs_pos + 160 * (hl - tp.n); pos %= B.P; if (pos < 0) pos += B.P; rd.start = pos; }
+                rd.len = tp.L;
                 int slot = 0;
                 for (int c = 0; c * 32 < tp.F && slot < PATCH_CAP; c++) {
                     unsigned m = masks[c];

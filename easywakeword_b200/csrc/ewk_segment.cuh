@@ -137,12 +137,39 @@ __device__ __forceinline__ void load_frame_pairs_at(const PcmReader& rd, int f0,
 #pragma unroll
             for (int a = 0; a < 8; a++) x[a] = __ldg(w + lane + 32 * a);
         }
-    } else {
+        return;
+    }
+    // masked frame (window edges, ring wrap).  When the frame starts on an even buffer position every pair
+    // is one aligned 4- / 8-byte load (a pair never straddles the ring end: ring length is even); the mask
+    // is applied per sample.
+    const long long p00 = rd.start + f0;                        // may be negative by up to N_FFT/2
+    const bool even = ((p00 & 1) == 0) && (rd.ring == 0 || (rd.ring & 1) == 0) &&
+                      !(rd.q ? ((size_t)rd.q & 3) : ((size_t)rd.f & 7));
+    if (even) {
+        int p0 = (int)p00;                                       // |p00| < 2^31 for rings; linear buffers < 2^30 samples
+        if (rd.ring) { if (p0 < 0) p0 += rd.ring; else if (p0 >= rd.ring) p0 -= rd.ring; }
 #pragma unroll
         for (int a = 0; a < 8; a++) {
-            const int i = f0 + 2 * lane + 64 * a;
-            x[a] = make_float2(rd.at(i), rd.at(i + 1));
+            const int off = 2 * lane + 64 * a;
+            const int i = f0 + off;
+            float2 v = make_float2(0.f, 0.f);
+            if (i >= 0 && i < rd.len) {
+                int p = p0 + off;
+                if (rd.ring && p >= rd.ring) p -= rd.ring;
+                if (rd.q) {
+                    const unsigned u = __ldg(reinterpret_cast<const unsigned*>(rd.q + p));
+                    v = make_float2((float)(short)(u & 0xffff) * (1.0f / 32768.0f), (float)((int)u >> 16) * (1.0f / 32768.0f));
+                } else v = __ldg(reinterpret_cast<const float2*>(rd.f + p));
+                if (i + 1 >= rd.len) v.y = 0.f;
+            }
+            x[a] = v;
         }
+        return;
+    }
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        const int i = f0 + 2 * lane + 64 * a;
+        x[a] = make_float2(rd.at(i), rd.at(i + 1));
     }
 }
 
