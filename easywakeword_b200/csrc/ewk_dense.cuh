@@ -73,11 +73,10 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.x;
     load_frame_tables(*ft, T, tid, DENSE_THREADS);
-    LaneMel lmel;
-    init_lane_mel(lmel, T, lane);
+    float* scr = scratch + warp * SCR_WARP;
+    init_warp_scratch(scr, lane);
     __syncthreads();
 
-    float* scr = scratch + warp * SCR_WARP;
     float* patch = wbuf + (size_t)warp * (PATCH_CAP * N_MFCC + 2 * N_MFCC + 16);
     float* feat = patch + PATCH_CAP * N_MFCC;
     unsigned* masks = reinterpret_cast<unsigned*>(feat + 2 * N_MFCC);   // [8] floored-frame bit masks, [8] prefix counts
@@ -137,7 +136,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
             float2 x[8];
             load_frame_pairs_at(rd, f0, lane, x);
             float mn, mx;
-            warp_frame_mfcc(x, *ft, lmel, scr, lane, -INFINITY, row, mn, mx);
+            warp_frame_mfcc(x, *ft, scr, lane, -INFINITY, row, mn, mx);
             if (lane == 0) { row[N_MFCC] = mn; row[N_MFCC + 1] = mx; }
         }
         g_done = g_hi + 1;
@@ -181,7 +180,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                         float2 x[8];
                         load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
                         float mn, mx;
-                        warp_frame_mfcc(x, *ft, lmel, scr, lane, floor_db, patch + slot * N_MFCC, mn, mx);
+                        warp_frame_mfcc(x, *ft, scr, lane, floor_db, patch + slot * N_MFCC, mn, mx);
                         slot++;
                     }
                 }
@@ -229,7 +228,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                             float2 x[8];
                             load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
                             float mn, mx;
-                            warp_frame_mfcc(x, *ft, lmel, scr, lane, floor_db, patch, mn, mx);
+                            warp_frame_mfcc(x, *ft, scr, lane, floor_db, patch, mn, mx);
                             __syncwarp();
                             src = patch;
                         } else src = dense_row(G, ekh, tp, A.DG, j, t);

@@ -24,6 +24,11 @@ constexpr int N_BINS = 257;
 constexpr int N_MELS = 128;
 constexpr int N_MFCC = 20;
 constexpr int MEL_NNZ_CAP = 512;          // 504 used for sr=16000, n_fft=512, 128 bands
+// Lane l owns mel bands l + 32 j (j = 0..3).  The Slaney bank's non-zero counts grow with the band index:
+// the widest band of each group of 32 has 2 / 3 / 6 / 12 taps, so padding every band of a group with zero
+// weights to that length gives branch-free, fully unrolled loops of 23 taps per lane (checked on the host).
+constexpr int MEL_TAPS0 = 2, MEL_TAPS1 = 3, MEL_TAPS2 = 6, MEL_TAPS3 = 12;
+constexpr int MEL_TAPS = MEL_TAPS0 + MEL_TAPS1 + MEL_TAPS2 + MEL_TAPS3;
 constexpr int SCR_PLANE = 320;            // floats per re / im transpose plane (8 rows x 40)
 constexpr int SCR_P = 264;                // power spectrum, 257 bins padded
 constexpr int SCR_WARP = 2 * SCR_PLANE + SCR_P;   // floats of scratch per warp (3616 B)
@@ -40,6 +45,8 @@ struct DeviceTables {
     int mel_off[N_MELS];          // offset into mel_w
     float mel_w[MEL_NNZ_CAP];     // librosa.filters.mel(htk=False, norm='slaney'), row-compressed
     float dct_t[N_MELS * N_MFCC]; // ortho DCT-II, transposed: dct_t[b*20 + k]
+    float mel_pad[MEL_TAPS * 32]; // zero-padded taps: mel_pad[tap * 32 + lane], taps grouped by j
+    int mel_first[4 * 32];        // mel_first[j * 32 + lane] = first FFT bin of band lane + 32 j
 };
 
 // Per-CTA shared copy, laid out for conflict-free lane-indexed access.
@@ -48,7 +55,8 @@ struct FrameTables {
     float2 tw1[8 * 32];           // tw1[k*32 + lane]  = W256^(lane k)
     float2 tw3[8 * 32];           // tw3[m*32 + lane]  = W512^(lane + 32 m)
     float2 tw2[8 * 4];            // tw2[k*4 + c]      = W32^(c k)
-    float melw[MEL_NNZ_CAP];
+    float melp[MEL_TAPS * 32];    // zero-padded mel taps, [tap][lane]
+    int mfirst[4 * 32];           // first FFT bin of band lane + 32 j, [j][lane]
     float4 dct[N_MELS * N_MFCC / 4];   // dct_t rows of 20 floats, read as 5 float4
 };
 
@@ -60,22 +68,10 @@ __device__ __forceinline__ void load_frame_tables(FrameTables& ft, const DeviceT
         ft.tw3[i] = T->w512[lane + 32 * a];
     }
     for (int i = tid; i < 32; i += nthr) ft.tw2[i] = T->w256[(8 * (i & 3) * (i >> 2)) & 255];
-    for (int i = tid; i < MEL_NNZ_CAP; i += nthr) ft.melw[i] = T->mel_w[i];
+    for (int i = tid; i < MEL_TAPS * 32; i += nthr) ft.melp[i] = T->mel_pad[i];
+    for (int i = tid; i < 4 * 32; i += nthr) ft.mfirst[i] = T->mel_first[i];
     const float4* d = reinterpret_cast<const float4*>(T->dct_t);
     for (int i = tid; i < N_MELS * N_MFCC / 4; i += nthr) ft.dct[i] = d[i];
-}
-
-struct LaneMel {                  // the lane's four mel bands: lane + 32 j
-    int start[4], len[4], off[4];
-};
-
-__device__ __forceinline__ void init_lane_mel(LaneMel& lm, const DeviceTables* __restrict__ T, int lane) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        lm.start[j] = T->mel_start[lane + 32 * j];
-        lm.len[j] = T->mel_len[lane + 32 * j];
-        lm.off[j] = T->mel_off[lane + 32 * j];
-    }
 }
 
 __device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -167,18 +163,22 @@ __device__ __forceinline__ void warp_power_spectrum(const float2 (&x)[8], const 
     __syncwarp();
 }
 
-// One warp: P[0..256] -> the lane's four log-mel values (bands lane + 32 j), 10*log10(max(1e-10, S)).
-__device__ __forceinline__ void warp_log_mel(const float* __restrict__ P, const FrameTables& ft,
-                                             const LaneMel& lm, float (&out)[4]) {
+// One warp: P[0..263] (bins 257..263 hold zeros) -> the lane's four log-mel values (bands lane + 32 j),
+// 10*log10(max(1e-10, S)).  Branch-free: zero-padded taps, compile-time trip counts.
+template <int NT>
+__device__ __forceinline__ float mel_band(const float* __restrict__ p, const float* __restrict__ w) {
+    float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const float* p = P + lm.start[j];
-        const float* w = ft.melw + lm.off[j];
-        float acc = 0.f;
-        const int n = lm.len[j];
-        for (int i = 0; i < n; i++) acc = fmaf(w[i], p[i], acc);
-        out[j] = TEN_LOG10_2 * __log2f(fmaxf(acc, 1e-10f));
-    }
+    for (int i = 0; i < NT; i++) acc = fmaf(w[i * 32], p[i], acc);
+    return TEN_LOG10_2 * __log2f(fmaxf(acc, 1e-10f));
+}
+
+__device__ __forceinline__ void warp_log_mel(const float* __restrict__ P, const FrameTables& ft, int lane, float (&out)[4]) {
+    const float* w = ft.melp + lane;
+    out[0] = mel_band<MEL_TAPS0>(P + ft.mfirst[lane], w);
+    out[1] = mel_band<MEL_TAPS1>(P + ft.mfirst[32 + lane], w + 32 * MEL_TAPS0);
+    out[2] = mel_band<MEL_TAPS2>(P + ft.mfirst[64 + lane], w + 32 * (MEL_TAPS0 + MEL_TAPS1));
+    out[3] = mel_band<MEL_TAPS3>(P + ft.mfirst[96 + lane], w + 32 * (MEL_TAPS0 + MEL_TAPS1 + MEL_TAPS2));
 }
 
 // Which coefficient the lane holds after warp_dct20 (or -1).
@@ -235,14 +235,19 @@ __device__ __forceinline__ float warp_dct20(const float (&x)[4], const FrameTabl
     return keep + __shfl_xor_sync(FULL, send, 1);
 }
 
-// One warp, one frame: PCM -> 20 MFCCs written to out[0..19]; returns the frame's log-mel min / max
-// (before flooring) in every lane.  floor_db = -INFINITY disables the power_to_db floor.
-__device__ __forceinline__ void warp_frame_mfcc(const float2 (&x)[8], const FrameTables& ft, const LaneMel& lm, float* scr,
-                                                int lane, float floor_db, float* __restrict__ out, float& fmin_o,
-                                                float& fmax_o) {
+// One warp, one frame: PCM -> 20 MFCCs written to out[0..19]; the frame's log-mel min / max (before
+// flooring) are returned in every lane.  floor_db = -INFINITY disables the power_to_db floor.
+// Deliberately NOT inlined: every kernel shares one copy of the ~1.5k-instruction pipeline, which keeps the
+// kernels inside the instruction cache.  scr[2*SCR_PLANE + 257 .. +263] must be zero (mel tap padding).
+__device__ __noinline__ float2 warp_frame_mfcc(float2 x0, float2 x1, float2 x2, float2 x3, float2 x4, float2 x5, float2 x6,
+                                               float2 x7, const FrameTables* __restrict__ ftp, float* scr,
+                                               float floor_db, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const FrameTables& ft = *ftp;
+    const float2 x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
     warp_power_spectrum(x, ft, scr, lane);
     float v[4];
-    warp_log_mel(scr + 2 * SCR_PLANE, ft, lm, v);
+    warp_log_mel(scr + 2 * SCR_PLANE, ft, lane, v);
     float mn = fminf(fminf(v[0], v[1]), fminf(v[2], v[3]));
     float mx = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
 #pragma unroll
@@ -255,8 +260,20 @@ __device__ __forceinline__ void warp_frame_mfcc(const float2 (&x)[8], const Fram
     const float cft = warp_dct20(v, ft, lane);
     const int k = dct_lane_coef(lane);
     if (k >= 0) out[k] = cft;
-    fmin_o = mn;
-    fmax_o = mx;
+    return make_float2(mn, mx);
+}
+
+__device__ __forceinline__ void warp_frame_mfcc(const float2 (&x)[8], const FrameTables& ft, float* scr, int lane,
+                                                float floor_db, float* __restrict__ out, float& fmin_o, float& fmax_o) {
+    const float2 r = warp_frame_mfcc(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], &ft, scr, floor_db, out);
+    fmin_o = r.x;
+    fmax_o = r.y;
+}
+
+// zero the mel tap padding of a warp's scratch once per kernel
+__device__ __forceinline__ void init_warp_scratch(float* scr, int lane) {
+    if (lane < SCR_P - N_BINS) scr[2 * SCR_PLANE + N_BINS + lane] = 0.f;
+    __syncwarp();
 }
 
 }  // namespace ewk

@@ -114,9 +114,9 @@ __device__ __forceinline__ SegSmem seg_carve(float* smem, int cap_frames) {
 }
 
 // once per CTA: tables into shared memory, the lane's mel band descriptors into registers
-__device__ __forceinline__ void seg_prologue(const DeviceTables* __restrict__ T, const SegSmem& m, LaneMel& lmel) {
+__device__ __forceinline__ void seg_prologue(const DeviceTables* __restrict__ T, const SegSmem& m) {
     load_frame_tables(*m.ft, T, threadIdx.x, SEG_THREADS);
-    init_lane_mel(lmel, T, threadIdx.x & 31);
+    init_warp_scratch(m.scratch + (threadIdx.x >> 5) * SCR_WARP, threadIdx.x & 31);
     __syncthreads();
 }
 
@@ -183,7 +183,7 @@ __device__ __forceinline__ void load_frame_pairs(const PcmReader& rd, int t, int
 //   B  block max -> floor = max - 80 (librosa.power_to_db(top_db=80) couples all frames of a segment)
 //   C  only frames whose min lies below the floor are recomputed with it (none in the common case)
 //   D  mean / std over frames (two-pass, ddof 0)
-__device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegSmem& m, const LaneMel& lmel,
+__device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegSmem& m,
                                                    int cap_frames, float* __restrict__ ws,
                                                    float* __restrict__ frames_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -211,7 +211,7 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
             float2 x[8];
             load_frame_pairs(rd, t, lane, x);
             float mn, mx;
-            warp_frame_mfcc(x, *m.ft, lmel, scr, lane, floor_db, mf + (size_t)t * N_MFCC, mn, mx);
+            warp_frame_mfcc(x, *m.ft, scr, lane, floor_db, mf + (size_t)t * N_MFCC, mn, mx);
             if (!pass && lane == 0) { fmn[t] = mn; fmx[t] = mx; }
             vmax = fmaxf(vmax, mx);
         }
@@ -276,11 +276,10 @@ segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __r
 {
     extern __shared__ __align__(16) float smem[];
     const SegSmem m = seg_carve(smem, cap_frames);
-    LaneMel lmel;
-    seg_prologue(T, m, lmel);
+    seg_prologue(T, m);
     const int tid = threadIdx.x;
     const SegDesc sd = segs[blockIdx.x];
-    const float* feat = segment_features(sd, m, lmel, cap_frames, ws, frames_out);
+    const float* feat = segment_features(sd, m, cap_frames, ws, frames_out);
     if (feat_out && tid < FEAT) feat_out[(size_t)blockIdx.x * FEAT + tid] = feat[tid];
     if (scores && tid < n_tmpl) {
         const TemplateFeat& tf = tmpl[tmpl_first + tid];

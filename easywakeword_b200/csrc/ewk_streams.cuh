@@ -555,8 +555,7 @@ __global__ void __launch_bounds__(SEG_THREADS, 3)
 segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, int n_tmpl_slots) {
     extern __shared__ __align__(16) float smem[];
     const SegSmem m = seg_carve(smem, SEG_SMEM_FRAMES);
-    LaneMel lc;
-    seg_prologue(T, m, lc);
+    seg_prologue(T, m);
     __shared__ float sc_s[EWK_MAX_TEMPLATES];
     const int tid = threadIdx.x;
     const int n = min(B.ev_count[0], B.max_events);
@@ -568,7 +567,7 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
         sd.base = (const char*)B.ring + (size_t)e.stream * B.P * esz;
         sd.start = e.seg_start % B.P; sd.ring = B.P; sd.len = e.seg_len; sd.fmt = B.fmt;
         sd.ws_frame_off = 0; sd.frames_off = 0;
-        const float* feat = segment_features(sd, m, lc, SEG_SMEM_FRAMES, nullptr, nullptr);
+        const float* feat = segment_features(sd, m, SEG_SMEM_FRAMES, nullptr, nullptr);
         const StreamParams& prm = B.prm[e.stream];
         const int t0 = max(0, prm.template_first);
         const int nt = max(0, min(prm.template_count, n_tmpl_slots - t0));

@@ -81,6 +81,19 @@ inline int build_tables(DeviceTables& T) {
         for (int k = 0; k < len; k++) T.mel_w[off + k] = mel[(size_t)i * N_BINS + first + k];
         off += len;
     }
+    // zero-padded taps for the branch-free mel loops (lane l owns bands l + 32 j)
+    const int taps[4] = {MEL_TAPS0, MEL_TAPS1, MEL_TAPS2, MEL_TAPS3};
+    int tap0 = 0;
+    for (int j = 0; j < 4; j++) {
+        for (int lane = 0; lane < 32; lane++) {
+            const int b = lane + 32 * j;
+            if (T.mel_len[b] > taps[j] || T.mel_start[b] + taps[j] > SCR_P) return -1;
+            T.mel_first[j * 32 + lane] = T.mel_start[b];
+            for (int i = 0; i < taps[j]; i++)
+                T.mel_pad[(tap0 + i) * 32 + lane] = i < T.mel_len[b] ? T.mel_w[T.mel_off[b] + i] : 0.f;
+        }
+        tap0 += taps[j];
+    }
     build_dct_t(T.dct_t);
     return off;
 }
