@@ -703,7 +703,7 @@ extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl
         t.slot = tmpl_first + k;
         max_n = std::max(max_n, t.n);
     }
-    A.DG = DH + max_n + 8;
+    A.DG = DH + max_n + 2;
     // the audio of every requested window must be resident
     const long long need_hi = 160LL * (hop0 + n_hops - 1);
     const long long need_lo = std::max<long long>(0, 160LL * (hop0 - max_n) - N_FFT / 2);

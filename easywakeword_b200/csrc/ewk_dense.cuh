@@ -31,7 +31,7 @@ constexpr int DENSE_MAX_T = 4;         // templates per launch
 constexpr int DENSE_MAX_F = 224;       // frames per window (templates up to ~2.2 s)
 constexpr int DENSE_MIN_L = 640;       // shorter templates would make a frame both left- and right-masked
 constexpr int ROW = N_MFCC + 2;        // mfcc[20], log-mel min, log-mel max
-constexpr int PATCH_CAP = 12;          // floored frames kept per warp before falling back to recomputation
+constexpr int PATCH_CAP = 8;           // floored frames kept per warp before falling back to recomputation
 
 struct DenseTmplDev {
     int L, n, F, t_hi, r, slot;        // r = F - 1 - t_hi right-edge frames
@@ -61,7 +61,7 @@ __device__ __forceinline__ const float* dense_row(const float* G, const float* e
     return edge_kh + (2 + t - tp.t_hi - 1) * ROW;
 }
 
-__global__ void __launch_bounds__(DENSE_THREADS, 2)
+__global__ void __launch_bounds__(DENSE_THREADS, 3)
 dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, DenseArgs A) {
     extern __shared__ __align__(16) float smem[];
     FrameTables* ft = reinterpret_cast<FrameTables*>(smem);
@@ -151,18 +151,28 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
             if (jl < 0) { if (lane == 0) *outp = __int_as_float(0x7fc00000); continue; }
             const int j = (int)(jl % A.DG);                            // ring row base of this window
             const float* ekh = edge + (k * DH + hl) * 4 * ROW;
-            // window max of the frames' log-mel max -> floor (librosa.power_to_db(top_db=80) on this window)
+            // window max of the frames' log-mel max -> floor (librosa.power_to_db(top_db=80) on this window);
+            // lanes walk the frames 32 at a time and keep their rows' min for the floored-frame test
             float wmax = -INFINITY;
-            for (int t = lane; t < tp.F; t += 32) wmax = fmaxf(wmax, dense_row(G, ekh, tp, A.DG, j, t)[N_MFCC + 1]);
+            float fmin_c[DENSE_MAX_F / 32];
+#pragma unroll
+            for (int c = 0; c < DENSE_MAX_F / 32; c++) {
+                const int t = c * 32 + lane;
+                fmin_c[c] = INFINITY;
+                if (t < tp.F) {
+                    const float* row = dense_row(G, ekh, tp, A.DG, j, t);
+                    fmin_c[c] = row[N_MFCC];
+                    wmax = fmaxf(wmax, row[N_MFCC + 1]);
+                }
+            }
 #pragma unroll
             for (int o = 16; o; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(FULL, wmax, o));
             const float floor_db = wmax - 80.0f;
             // frames that the floor changes
             int n_aff = 0;
-            for (int c = 0; c * 32 < tp.F; c++) {
-                const int t = c * 32 + lane;
-                const bool a = t < tp.F && dense_row(G, ekh, tp, A.DG, j, t)[N_MFCC] < floor_db;
-                const unsigned m = __ballot_sync(FULL, a);
+#pragma unroll
+            for (int c = 0; c < DENSE_MAX_F / 32; c++) {
+                const unsigned m = __ballot_sync(FULL, fmin_c[c] < floor_db);
                 if (lane == 0) { masks[c] = m; masks[8 + c] = (unsigned)n_aff; }
                 n_aff += __popc(m);
             }
@@ -187,26 +197,40 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                 __syncwarp();
             }
             // mean / std over the F frames: lane = (group g3 of 3, coefficient pair c2 of 10); three frames per step
-            const int g3 = lane / 10, c2 = lane % 10;
+            const int g3 = lane / 10, c2 = lane - 10 * g3;
             const bool act = lane < 30;
             float2 mean = make_float2(0.f, 0.f), var = make_float2(0.f, 0.f);
             for (int pass = 0; pass < 2; pass++) {
                 float2 acc = make_float2(0.f, 0.f);
-                for (int t0 = 0; t0 < tp.F; t0 += 3) {
-                    const int t = t0 + g3;
-                    if (!act || t >= tp.F) continue;
-                    float2 v;
-                    bool patched = false;
-                    if (n_aff) {
-                        const unsigned m = masks[t >> 5];
-                        if ((m >> (t & 31)) & 1u) {
-                            const int sl = (int)masks[8 + (t >> 5)] + __popc(m & ((1u << (t & 31)) - 1u));
-                            if (sl < PATCH_CAP) { v = *reinterpret_cast<const float2*>(patch + sl * N_MFCC + 2 * c2); patched = true; }
+                if (act) {
+                    if (!n_aff) {
+                        // fast path: two left-edge rows, a run of ring rows, the right-edge rows
+                        auto add = [&](const float* row) {
+                            const float2 v = *reinterpret_cast<const float2*>(row + 2 * c2);
+                            if (pass == 0) { acc.x += v.x; acc.y += v.y; }
+                            else { const float dx = v.x - mean.x, dy = v.y - mean.y; acc.x = fmaf(dx, dx, acc.x); acc.y = fmaf(dy, dy, acc.y); }
+                        };
+                        if (g3 < 2) add(ekh + g3 * ROW);                               // t = 0, 1
+                        if (g3 < tp.r) add(ekh + (2 + g3) * ROW);                      // t = t_hi+1 ..
+                        int r = j + 2 + g3; if (r >= A.DG) r -= A.DG;
+                        for (int t = 2 + g3; t <= tp.t_hi; t += 3) {
+                            add(G + r * ROW);
+                            r += 3; if (r >= A.DG) r -= A.DG;
+                        }
+                    } else {
+                        for (int t = g3; t < tp.F; t += 3) {
+                            float2 v;
+                            bool patched = false;
+                            const unsigned m = masks[t >> 5];
+                            if ((m >> (t & 31)) & 1u) {
+                                const int sl = (int)masks[8 + (t >> 5)] + __popc(m & ((1u << (t & 31)) - 1u));
+                                if (sl < PATCH_CAP) { v = *reinterpret_cast<const float2*>(patch + sl * N_MFCC + 2 * c2); patched = true; }
+                            }
+                            if (!patched) v = *reinterpret_cast<const float2*>(dense_row(G, ekh, tp, A.DG, j, t) + 2 * c2);
+                            if (pass == 0) { acc.x += v.x; acc.y += v.y; }
+                            else { const float dx = v.x - mean.x, dy = v.y - mean.y; acc.x = fmaf(dx, dx, acc.x); acc.y = fmaf(dy, dy, acc.y); }
                         }
                     }
-                    if (!patched) v = *reinterpret_cast<const float2*>(dense_row(G, ekh, tp, A.DG, j, t) + 2 * c2);
-                    if (pass == 0) { acc.x += v.x; acc.y += v.y; }
-                    else { const float dx = v.x - mean.x, dy = v.y - mean.y; acc.x = fmaf(dx, dx, acc.x); acc.y = fmaf(dy, dy, acc.y); }
                 }
                 // combine the three frame groups (lanes c2, c2+10, c2+20)
                 const float ax = __shfl_sync(FULL, acc.x, c2) + __shfl_sync(FULL, acc.x, c2 + 10) + __shfl_sync(FULL, acc.x, c2 + 20);

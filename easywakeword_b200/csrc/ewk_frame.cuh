@@ -30,8 +30,8 @@ constexpr int MEL_NNZ_CAP = 512;          // 504 used for sr=16000, n_fft=512, 1
 constexpr int MEL_TAPS0 = 2, MEL_TAPS1 = 3, MEL_TAPS2 = 6, MEL_TAPS3 = 12;
 constexpr int MEL_TAPS = MEL_TAPS0 + MEL_TAPS1 + MEL_TAPS2 + MEL_TAPS3;
 constexpr int SCR_PLANE = 320;            // floats per re / im transpose plane (8 rows x 40)
-constexpr int SCR_P = 264;                // power spectrum, 257 bins padded
-constexpr int SCR_WARP = 2 * SCR_PLANE + SCR_P;   // floats of scratch per warp (3616 B)
+constexpr int SCR_P = 264;                // power spectrum, 257 bins padded; aliases the re plane (dead by then)
+constexpr int SCR_WARP = 2 * SCR_PLANE;   // floats of scratch per warp (2560 B)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float TEN_LOG10_2 = 3.01029995663981195f;   // 10 * log10(2)
 
@@ -107,7 +107,7 @@ __device__ __forceinline__ void fft8(float2 (&v)[8]) {
 __device__ __forceinline__ void warp_power_spectrum(const float2 (&x)[8], const FrameTables& ft, float* scr, int lane) {
     float* sre = scr;
     float* sim = scr + SCR_PLANE;
-    float* P = scr + 2 * SCR_PLANE;
+    float* P = scr;                           // written only after the last read of the transpose planes
     float2 v[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) {
@@ -145,6 +145,7 @@ __device__ __forceinline__ void warp_power_spectrum(const float2 (&x)[8], const 
         const float2 w3 = make_float2(sre[base + 24], sim[base + 24]);
         dft4(w0, w1, w2, w3, o[e], o[e + 2], o[e + 4], o[e + 6]);
     }
+    __syncwarp();                             // every lane holds its Z values: the planes may be overwritten by P
     // real-FFT untangle: X[k] = E[k] + W512^k O[k],  E = (Z[k] + conj Z[256-k])/2,  O = (Z[k] - conj Z[256-k])/(2i)
     const int pl = (32 - lane) & 31;
 #pragma unroll
@@ -160,6 +161,7 @@ __device__ __forceinline__ void warp_power_spectrum(const float2 (&x)[8], const 
         P[lane + 32 * m] = 0.25f * (xr * xr + xi * xi);
     }
     if (lane == 0) { const float d = o[0].x - o[0].y; P[256] = d * d; }
+    if (lane >= 1 && lane < SCR_P - 256) P[256 + lane] = 0.f;      // zero padding read by the padded mel taps
     __syncwarp();
 }
 
@@ -238,7 +240,7 @@ __device__ __forceinline__ float warp_dct20(const float (&x)[4], const FrameTabl
 // One warp, one frame: PCM -> 20 MFCCs written to out[0..19]; the frame's log-mel min / max (before
 // flooring) are returned in every lane.  floor_db = -INFINITY disables the power_to_db floor.
 // Deliberately NOT inlined: every kernel shares one copy of the ~1.5k-instruction pipeline, which keeps the
-// kernels inside the instruction cache.  scr[2*SCR_PLANE + 257 .. +263] must be zero (mel tap padding).
+// kernels inside the instruction cache.
 __device__ __noinline__ float2 warp_frame_mfcc(float2 x0, float2 x1, float2 x2, float2 x3, float2 x4, float2 x5, float2 x6,
                                                float2 x7, const FrameTables* __restrict__ ftp, float* scr,
                                                float floor_db, float* __restrict__ out) {
@@ -247,7 +249,7 @@ __device__ __noinline__ float2 warp_frame_mfcc(float2 x0, float2 x1, float2 x2, 
     const float2 x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
     warp_power_spectrum(x, ft, scr, lane);
     float v[4];
-    warp_log_mel(scr + 2 * SCR_PLANE, ft, lane, v);
+    warp_log_mel(scr, ft, lane, v);
     float mn = fminf(fminf(v[0], v[1]), fminf(v[2], v[3]));
     float mx = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
 #pragma unroll
@@ -270,10 +272,6 @@ __device__ __forceinline__ void warp_frame_mfcc(const float2 (&x)[8], const Fram
     fmax_o = r.y;
 }
 
-// zero the mel tap padding of a warp's scratch once per kernel
-__device__ __forceinline__ void init_warp_scratch(float* scr, int lane) {
-    if (lane < SCR_P - N_BINS) scr[2 * SCR_PLANE + N_BINS + lane] = 0.f;
-    __syncwarp();
-}
+__device__ __forceinline__ void init_warp_scratch(float*, int) {}
 
 }  // namespace ewk
