@@ -385,7 +385,7 @@ int ewk_ctx::init_streams() {
     CK(cudaFuncSetAttribute(segment_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
     CK(cudaFuncSetAttribute(tick_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(sizeof(double) * 3 * (size_t)chunk_cap * GATE_WARPS)));
+                            (int)(sizeof(double) * 3 * (size_t)(chunk_cap + 1) * GATE_WARPS + 2 * TICK * 4 * GATE_WARPS)));
     return EWK_OK;
 }
 
@@ -530,12 +530,16 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         tr.silent = (unsigned char*)(base + cells * 16);
         tr.state = (unsigned char*)(base + cells * 17);
     }
-    const int smem_chunks = ctx->gate_chunks();
+    int smem_chunks = ctx->gate_chunks();
+    if (smem_chunks & 1) smem_chunks++;                   // keeps the staging area 16-byte aligned
+    // bulk staging of whole ticks pays when chunk arrays are small (frame_size 1600: 100 chunks)
+    const int stage_bytes = smem_chunks <= 128 ? TICK * (B.fmt == 1 ? 2 : 4) : 0;
     cudaEvent_t pe = ctx->prof_begin(1);
     for (int done = 0; done < n_ticks; done += GATE_MAX_TICKS) {
         const int nt = std::min(GATE_MAX_TICKS, n_ticks - done);
         tick_gate_kernel<<<(B.n_streams + GATE_WARPS - 1) / GATE_WARPS, GATE_THREADS,
-                           sizeof(double) * 3 * (size_t)smem_chunks * GATE_WARPS, ctx->stream>>>(B, nt, tr, n_ticks, done, smem_chunks);
+                           sizeof(double) * 3 * (size_t)smem_chunks * GATE_WARPS + (size_t)2 * stage_bytes * GATE_WARPS,
+                           ctx->stream>>>(B, nt, tr, n_ticks, done, smem_chunks, stage_bytes);
         ctx->launches++;
     }
     ctx->prof_end(pe, 1);

@@ -290,6 +290,55 @@ __device__ __forceinline__ double percentile25_rms_sorted(const double* S, int n
     return r;
 }
 
+// ---- TMA-style bulk staging (cp.async.bulk + mbarrier): one lane moves a whole 0.1 s tick of PCM from the
+// ring into shared memory with a single instruction; the warp overlaps the copy of tick j+2 with the
+// arithmetic of tick j.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+// sum of squares of one staged tick (TICK samples in shared memory), whole warp, result in every lane
+__device__ __forceinline__ double warp_sumsq_smem(const void* buf, int fmt, int lane) {
+    double acc;
+    if (fmt == 1) {
+        const int4* v = reinterpret_cast<const int4*>(buf);
+        long long iacc = 0;
+#pragma unroll
+        for (int u = 0; u < 7; u++) {
+            const int k = lane + 32 * u;
+            if (k < TICK / 8) iacc += sq8(v[k]);
+        }
+        acc = (double)iacc;
+    } else {
+        const float4* v = reinterpret_cast<const float4*>(buf);
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int u = 0; u < 13; u++) {
+            const int k = lane + 32 * u;
+            if (k < TICK / 4) { if (u & 1) a1 = sq4(v[k], a1); else a0 = sq4(v[k], a0); }
+        }
+        acc = a0 + a1;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    return acc;
+}
+
 struct GatePlan {                                   // one per warp (= per stream)
     long long V[GATE_MAX_TICKS];                    // samples visible at each tick
     double pv[GATE_MAX_TICKS][GATE_MAXP + 1];       // piece values; [GATE_MAXP] = recent-window sum of squares
@@ -382,9 +431,11 @@ __device__ __forceinline__ unsigned gate_state_step(const BankView& B, int s, St
 // 16-byte loads, eight in flight per lane); phase 2: the ticks are replayed in order — chunk updates
 // into an incrementally maintained sorted array, percentile, threshold, is_silent, state machine.
 __global__ void __launch_bounds__(GATE_THREADS, 8)
-tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int trace_off, int smem_chunks) {
-    extern __shared__ double sm_d[];
+tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int trace_off, int smem_chunks, int stage_bytes) {
+    extern __shared__ __align__(16) double sm_d[];
     __shared__ GatePlan plans[GATE_WARPS];
+    __shared__ __align__(8) unsigned long long mbar[GATE_WARPS][2];
+    char* stage = reinterpret_cast<char*>(sm_d + (size_t)GATE_WARPS * 3 * smem_chunks);   // [warp][2][stage_bytes], 16-byte aligned
     __shared__ StreamState st_s[GATE_WARPS];
     __shared__ StreamParams prm_s[GATE_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -458,29 +509,12 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
     }
     __syncwarp();
 
-    // ---- phase 1: every planned range
     const int nrec = min(TICK, B.R);
-    for (int j = 0; j < n_ticks; j++) {
-        const long long V = plan.V[j];
-        const int np = plan.np[j] == 255 ? 0 : plan.np[j];
-        for (int i = 0; i < np; i++) {
-            const double v = warp_chunk_ms(B, s, V, fs, plan.pc[j][i], lane);
-            if (lane == 0) plan.pv[j][i] = v;
-        }
-        if (fs > 0 && !plan.alias[j]) {
-            // RMS window of is_silent: the last min(1600, R) samples; zeros before the stream began
-            const long long a0 = V - nrec;
-            const double ss = warp_sumsq((const char*)B.ring + (size_t)s * B.P * (B.fmt == 1 ? 2 : 4), B.P, B.fmt,
-                                         a0 < 0 ? 0 : a0, (int)(a0 < 0 ? V : nrec), lane);
-            if (lane == 0) plan.pv[j][GATE_MAXP] = ss;
-        }
-    }
-    __syncwarp();
-
-    // ---- phase 2: replay the ticks in order
     unsigned evflag = 0;
     int valid = valid0;
-    for (int j = 0; j < n_ticks; j++) {
+
+    // ---- one tick of phase 2: chunk updates into the sorted array, percentile, threshold, is_silent, state machine
+    auto replay_tick = [&](int j) {
         const long long k = tick0 + j + 1;
         const long long V = plan.V[j];
         const bool full = plan.full[j];
@@ -531,8 +565,67 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
                 tr.thr[o] = st.thr;
                 tr.rms[o] = rms;
             }
+            st.tick = k; st.visible = V;
         }
-        if (lane == 0) { st.tick = k; st.visible = V; }
+    };
+
+    // Is every tick the aligned case (frame_size 1600: the tick's new block is one storage chunk and also the
+    // RMS window) with its 1600 samples contiguous in the physical ring?  Then stage ticks through shared
+    // memory with bulk copies, two ticks ahead, and replay tick j while ticks j+1, j+2 are in flight.
+    const size_t esz = B.fmt == 1 ? 2 : 4;
+    const bool mine_ok = lane >= n_ticks || (plan.alias[lane] && plan.np[lane] == 1);
+    const bool pipelined = stage_bytes > 0 && (B.P % TICK) == 0 && __all_sync(FULL, mine_ok);
+    if (pipelined) {
+        unsigned long long* bar = mbar[warp];
+        char* buf = stage + (size_t)warp * 2 * stage_bytes;
+        const char* ring_s = (const char*)B.ring + (size_t)s * B.P * esz;
+        if (lane == 0) {
+            mbar_init(bar, 1); mbar_init(bar + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        auto issue = [&](int j) {
+            if (lane == 0) {
+                const long long a0 = plan.V[j] - TICK;
+                mbar_expect_tx(bar + (j & 1), (unsigned)(TICK * esz));
+                bulk_g2s(buf + (size_t)(j & 1) * stage_bytes, ring_s + (size_t)(a0 % B.P) * esz, (unsigned)(TICK * esz), bar + (j & 1));
+            }
+        };
+        issue(0);
+        if (n_ticks > 1) issue(1);
+        for (int j = 0; j < n_ticks; j++) {
+            mbar_wait(bar + (j & 1), (unsigned)((j >> 1) & 1));
+            double ss = warp_sumsq_smem(buf + (size_t)(j & 1) * stage_bytes, B.fmt, lane);
+            __syncwarp();
+            if (j + 2 < n_ticks) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(j + 2);
+            }
+            if (B.fmt == 1) ss *= (1.0 / 1073741824.0);
+            if (lane == 0) plan.pv[j][0] = ss / (double)fs;              // np.mean(frame**2)   wakeword.py:481
+            __syncwarp();
+            replay_tick(j);
+        }
+    } else {
+        // ---- phase 1: every planned range (generic: any frame size, wrap, first-full and live streams)
+        for (int j = 0; j < n_ticks; j++) {
+            const long long V = plan.V[j];
+            const int np = plan.np[j] == 255 ? 0 : plan.np[j];
+            for (int i = 0; i < np; i++) {
+                const double v = warp_chunk_ms(B, s, V, fs, plan.pc[j][i], lane);
+                if (lane == 0) plan.pv[j][i] = v;
+            }
+            if (fs > 0 && !plan.alias[j]) {
+                // RMS window of is_silent: the last min(1600, R) samples; zeros before the stream began
+                const long long a0 = V - nrec;
+                const double ss = warp_sumsq((const char*)B.ring + (size_t)s * B.P * esz, B.P, B.fmt,
+                                             a0 < 0 ? 0 : a0, (int)(a0 < 0 ? V : nrec), lane);
+                if (lane == 0) plan.pv[j][GATE_MAXP] = ss;
+            }
+        }
+        __syncwarp();
+        // ---- phase 2: replay the ticks in order
+        for (int j = 0; j < n_ticks; j++) replay_tick(j);
     }
     __syncwarp();
 
