@@ -137,15 +137,17 @@ constexpr int GATE_WARPS = GATE_THREADS / 32;
 constexpr int GATE_MAX_TICKS = 16;     // ticks per launch (the host splits longer requests)
 constexpr int GATE_MAXP = 12;          // chunk pieces planned per tick; more -> the tick is "heavy"
 
+// sum of the squares of the eight int16 samples of a 16-byte word, exact (64-bit integer): per 32-bit
+// word one sign-extracting BFE, one arithmetic shift and two signed 32x32+64 multiply-adds.
 __device__ __forceinline__ long long sq8(const int4 q) {
-    const int w[4] = {q.x, q.y, q.z, q.w};
-    long long out = 0;
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-        const int lo = (short)(w[u] & 0xffff), hi = w[u] >> 16;
-        out += (long long)(unsigned)(lo * lo) + (long long)(unsigned)(hi * hi);
-    }
-    return out;
+    long long acc = 0;
+    asm("{\n\t.reg .s32 lo, hi;\n\t"
+        "bfe.s32 lo, %1, 0, 16;\n\tshr.s32 hi, %1, 16;\n\tmad.wide.s32 %0, lo, lo, %0;\n\tmad.wide.s32 %0, hi, hi, %0;\n\t"
+        "bfe.s32 lo, %2, 0, 16;\n\tshr.s32 hi, %2, 16;\n\tmad.wide.s32 %0, lo, lo, %0;\n\tmad.wide.s32 %0, hi, hi, %0;\n\t"
+        "bfe.s32 lo, %3, 0, 16;\n\tshr.s32 hi, %3, 16;\n\tmad.wide.s32 %0, lo, lo, %0;\n\tmad.wide.s32 %0, hi, hi, %0;\n\t"
+        "bfe.s32 lo, %4, 0, 16;\n\tshr.s32 hi, %4, 16;\n\tmad.wide.s32 %0, lo, lo, %0;\n\tmad.wide.s32 %0, hi, hi, %0;\n\t}"
+        : "+l"(acc) : "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w));
+    return acc;
 }
 
 __device__ __forceinline__ double sq4(const float4 q, double acc) {
@@ -512,6 +514,7 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
     const int nrec = min(TICK, B.R);
     unsigned evflag = 0;
     int valid = valid0;
+    long long key_lo = -1, key_hi = -1;            // bit patterns of the order statistics behind st.thr (lane 0)
 
     // ---- one tick of phase 2: chunk updates into the sorted array, percentile, threshold, is_silent, state machine
     auto replay_tick = [&](int j) {
@@ -541,9 +544,15 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
         }
         if (lane == 0) {
             if (np != 0) {
-                const double p25 = percentile25_rms_sorted(SA, n_chunks);
-                const double nt = __dmul_rn(p25, 1.5);                  // wakeword.py:485
-                st.thr = nt > prm.min_threshold ? nt : prm.min_threshold;   // max(new, MIN_THRESHOLD)  :486
+                // the threshold only moves when one of the two order statistics np.percentile reads moved
+                const int k_lo = (int)floor((double)n_chunks * 0.25 - 0.25), k_hi = min(k_lo + 1, n_chunks - 1);
+                const long long b_lo = __double_as_longlong(SA[k_lo]), b_hi = __double_as_longlong(SA[k_hi]);
+                if (b_lo != key_lo || b_hi != key_hi) {
+                    key_lo = b_lo; key_hi = b_hi;
+                    const double p25 = percentile25_rms_sorted(SA, n_chunks);
+                    const double nt = __dmul_rn(p25, 1.5);                  // wakeword.py:485
+                    st.thr = nt > prm.min_threshold ? nt : prm.min_threshold;   // max(new, MIN_THRESHOLD)  :486
+                }
             }
             // ---- is_silent (wakeword.py:488-496)
             int silent = 1;
@@ -584,11 +593,13 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
+        const int pos0 = (int)((plan.V[0] - TICK) % B.P);      // every tick advances by exactly TICK samples
         auto issue = [&](int j) {
             if (lane == 0) {
-                const long long a0 = plan.V[j] - TICK;
+                int pos = pos0 + j * TICK;
+                while (pos >= B.P) pos -= B.P;
                 mbar_expect_tx(bar + (j & 1), (unsigned)(TICK * esz));
-                bulk_g2s(buf + (size_t)(j & 1) * stage_bytes, ring_s + (size_t)(a0 % B.P) * esz, (unsigned)(TICK * esz), bar + (j & 1));
+                bulk_g2s(buf + (size_t)(j & 1) * stage_bytes, ring_s + (size_t)pos * esz, (unsigned)(TICK * esz), bar + (j & 1));
             }
         };
         issue(0);
