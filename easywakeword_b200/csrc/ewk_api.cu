@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -533,7 +534,8 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     int smem_chunks = ctx->gate_chunks();
     if (smem_chunks & 1) smem_chunks++;                   // keeps the staging area 16-byte aligned
     // bulk staging of whole ticks pays when chunk arrays are small (frame_size 1600: 100 chunks)
-    const int stage_bytes = smem_chunks <= 128 ? TICK * (B.fmt == 1 ? 2 : 4) : 0;
+    static const int stage_env = [] { const char* e = getenv("EWK_GATE_STAGE"); return e ? atoi(e) : 1; }();
+    const int stage_bytes = (stage_env && smem_chunks <= 128) ? TICK * (B.fmt == 1 ? 2 : 4) : 0;
     cudaEvent_t pe = ctx->prof_begin(1);
     for (int done = 0; done < n_ticks; done += GATE_MAX_TICKS) {
         const int nt = std::min(GATE_MAX_TICKS, n_ticks - done);
