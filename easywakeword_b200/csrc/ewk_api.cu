@@ -363,6 +363,8 @@ int ewk_ctx::init_streams() {
     CK(cudaMalloc(&bank.events, sizeof(EventRec) * (size_t)bank.max_events));
     CK(cudaMalloc(&bank.ev_count, sizeof(int) * 4));
     CK(cudaMemsetAsync(bank.ev_count, 0, sizeof(int) * 4, stream));
+    bank.NB = bank.P / TICK;
+    CK(cudaMalloc(&bank.block_ss, sizeof(double) * (size_t)n * std::max(1, bank.NB)));
     CK(cudaMalloc(&own_results, sizeof(StreamResult) * (size_t)n));
     bank.results = (StreamResult*)own_results;
     std::vector<StreamState> st(n);
@@ -392,7 +394,7 @@ int ewk_ctx::init_streams() {
 
 void ewk_ctx::release_streams() {
     for (void* p : {bank.ring, (void*)bank.st, (void*)bank.prm, (void*)bank.chunk_ms, (void*)bank.events,
-                    (void*)bank.ev_count, own_results})
+                    (void*)bank.ev_count, (void*)bank.block_ss, own_results})
         if (p) cudaFree(p);
     bank = BankView{};
     own_results = nullptr;
@@ -474,6 +476,7 @@ extern "C" int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pc
     bool uniform = true;
     for (int s = stream0 + 1; s < stream0 + n_streams; s++) uniform &= ctx->h_written[s] == ctx->h_written[stream0];
     const int p0 = (int)(ctx->h_written[stream0] % B.P);
+    int with_sums = 0;
     if (where == EWK_HOST && uniform) {
         // host PCM lands straight in the rings: one (or, at the wrap, two) pitched H2D copies, no staging pass
         const int first = (int)std::min<int64_t>(n, B.P - p0);
@@ -495,16 +498,26 @@ extern "C" int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pc
             d_src = ctx->b_stage.p;
             d_stride = n;
         }
-        const int per = esz == 2 ? 8 : 4;
-        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (n / per + 255) / 256)), (unsigned)n_streams);
+        // fused copy + per-block sums when every stream of the push sits on a 0.1 s block boundary
+        bool aligned = (n % TICK) == 0 && (B.P % TICK) == 0 && B.NB > 0 && ((size_t)d_src & 15) == 0 && ((d_stride * esz) & 15) == 0;
+        for (int s = stream0; aligned && s < stream0 + n_streams; s++) aligned = (ctx->h_written[s] % TICK) == 0;
         cudaEvent_t pe = ctx->prof_begin(0);
-        if (B.fmt == 1) ring_push_kernel<short><<<grid, 256, 0, ctx->stream>>>(B, stream0, (const short*)d_src, d_stride, (int)n);
-        else ring_push_kernel<float><<<grid, 256, 0, ctx->stream>>>(B, stream0, (const float*)d_src, d_stride, (int)n);
+        if (aligned) {
+            dim3 grid((unsigned)((n / TICK + 3) / 4), (unsigned)n_streams);
+            if (B.fmt == 1) ring_push_sums_kernel<short><<<grid, 128, 0, ctx->stream>>>(B, stream0, (const short*)d_src, d_stride, (int)n);
+            else ring_push_sums_kernel<float><<<grid, 128, 0, ctx->stream>>>(B, stream0, (const float*)d_src, d_stride, (int)n);
+            with_sums = 1;
+        } else {
+            const int per = esz == 2 ? 8 : 4;
+            dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (n / per + 255) / 256)), (unsigned)n_streams);
+            if (B.fmt == 1) ring_push_kernel<short><<<grid, 256, 0, ctx->stream>>>(B, stream0, (const short*)d_src, d_stride, (int)n);
+            else ring_push_kernel<float><<<grid, 256, 0, ctx->stream>>>(B, stream0, (const float*)d_src, d_stride, (int)n);
+        }
         ctx->prof_end(pe, 0);
         CK(cudaGetLastError());
         ctx->launches++;
     }
-    ring_commit_kernel<<<(n_streams + 255) / 256, 256, 0, ctx->stream>>>(B, stream0, n_streams, (int)n);
+    ring_commit_kernel<<<(n_streams + 255) / 256, 256, 0, ctx->stream>>>(B, stream0, n_streams, (int)n, with_sums);
     CK(cudaGetLastError());
     ctx->launches++;
     for (int s = stream0; s < stream0 + n_streams; s++) {

@@ -56,6 +56,7 @@ struct StreamState {
     int n_timeouts;
     int n_events;
     int pad;
+    long long ss_from;      // block_ss holds the sum of squares of every aligned 1600-sample block in [ss_from, written)
 };
 
 struct EventRec {           // mirrors ewk_event
@@ -82,7 +83,8 @@ struct BankView {
     EventRec* events;
     int* ev_count;          // [0] count, [1] dropped
     StreamResult* results;
-    int n_streams, R, P, fmt, chunk_cap, max_events;
+    double* block_ss;       // [n_streams][NB]: sum of squares of absolute block b = a / 1600 at b % NB (written by K1)
+    int n_streams, R, P, fmt, chunk_cap, max_events, NB;
 };
 
 struct TraceView {          // optional per-tick trace for parity tests: [n_streams][n_ticks]
@@ -120,8 +122,69 @@ __global__ void ring_push_kernel(BankView B, int stream0, const T* __restrict__ 
     }
 }
 
-// bookkeeping after the payload of a push landed (kernel or 2-D copy): written += n, frame_size latch
-__global__ void ring_commit_kernel(BankView B, int stream0, int n_streams, int n) {
+// K1, fused form: the copy of a device-resident push also produces the sum of squares of every 0.1 s block
+// it writes (what K2 needs for the adaptive threshold and is_silent), so the samples are read once for both.
+// One warp per (stream, 1600-sample block).  Preconditions (checked per stream, identical in the commit
+// kernel): the stream's `written` and `n` are multiples of 1600, 16-byte aligned source rows.
+__device__ __forceinline__ long long sq8(const int4 q);
+__device__ __forceinline__ double sq4(const float4 q, double acc);
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+ring_push_sums_kernel(BankView B, int stream0, const T* __restrict__ src, long long stride, int n) {
+    constexpr int V = 16 / sizeof(T);                 // samples per 16-byte word
+    constexpr int NV = TICK / V;                      // words per block: 200 (int16) / 400 (f32)
+    constexpr int PER = (NV + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const int blk = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int s = stream0 + blockIdx.y;
+    if (blk * TICK >= n) return;
+    const long long w = B.st[s].written;
+    const T* in = src + (size_t)blockIdx.y * stride + (size_t)blk * TICK;
+    T* ring = (T*)B.ring + (size_t)s * B.P;
+    const long long a0 = w + (long long)blk * TICK;
+    const int p0 = (int)(a0 % B.P);
+    const int4* vin = reinterpret_cast<const int4*>(in);
+    int4 q[PER];
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+        const int k = lane + 32 * u;
+        q[u] = k < NV ? __ldg(vin + k) : make_int4(0, 0, 0, 0);
+    }
+    if (p0 + TICK <= B.P) {
+        int4* vout = reinterpret_cast<int4*>(ring + p0);
+#pragma unroll
+        for (int u = 0; u < PER; u++) { const int k = lane + 32 * u; if (k < NV) vout[k] = q[u]; }
+    } else {
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int k = lane + 32 * u;
+            if (k < NV) { int p = p0 + k * V; if (p >= B.P) p -= B.P; *reinterpret_cast<int4*>(ring + p) = q[u]; }
+        }
+    }
+    double acc;
+    if (sizeof(T) == 2) {
+        long long iacc = 0;
+#pragma unroll
+        for (int u = 0; u < PER; u++) iacc += sq8(q[u]);
+        acc = (double)iacc;
+    } else {
+        double a0d = 0.0, a1d = 0.0;
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const float4 f = make_float4(__int_as_float(q[u].x), __int_as_float(q[u].y), __int_as_float(q[u].z), __int_as_float(q[u].w));
+            if (u & 1) a1d = sq4(f, a1d); else a0d = sq4(f, a0d);
+        }
+        acc = a0d + a1d;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if (lane == 0) B.block_ss[(size_t)s * B.NB + (size_t)((a0 / TICK) % B.NB)] = acc;
+}
+
+// bookkeeping after the payload of a push landed (kernel or 2-D copy): written += n, frame_size latch,
+// validity range of the per-block sums (with_sums: the fused kernel produced them for this push)
+__global__ void ring_commit_kernel(BankView B, int stream0, int n_streams, int n, int with_sums) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_streams) return;
     StreamState& st = B.st[stream0 + s];
@@ -129,6 +192,8 @@ __global__ void ring_commit_kernel(BankView B, int stream0, int n_streams, int n
         const int fs = B.prm[stream0 + s].frame_size;
         st.frame_size = fs > 0 ? fs : n;                               // wakeword.py:457-458
     }
+    if (!with_sums) st.ss_from = st.written + n;                        // nothing known about these samples
+    else if (st.ss_from > st.written) st.ss_from = st.written;          // sums restart at this push
     st.written += n;
 }
 
@@ -583,41 +648,38 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
     // memory with bulk copies, two ticks ahead, and replay tick j while ticks j+1, j+2 are in flight.
     const size_t esz = B.fmt == 1 ? 2 : 4;
     const bool mine_ok = lane >= n_ticks || (plan.alias[lane] && plan.np[lane] == 1);
-    const bool pipelined = stage_bytes > 0 && (B.P % TICK) == 0 && __all_sync(FULL, mine_ok);
+    const bool all_alias = (B.P % TICK) == 0 && __all_sync(FULL, mine_ok);
+    // block sums from the fused push kernel cover these ticks? then no PCM is read here at all
+    const bool presummed = all_alias && B.NB > 0 && n_ticks > 0 && plan.V[0] - TICK >= st.ss_from;
+    if (presummed) {
+        if (lane < n_ticks) {
+            double ss = B.block_ss[(size_t)s * B.NB + (size_t)(((plan.V[lane] - TICK) / TICK) % B.NB)];
+            if (B.fmt == 1) ss *= (1.0 / 1073741824.0);
+            plan.pv[lane][0] = ss / (double)fs;                          // np.mean(frame**2)   wakeword.py:481
+        }
+        __syncwarp();
+    }
+    const bool pipelined = !presummed && stage_bytes > 0 && all_alias;
+    unsigned long long* bar = mbar[warp];
+    char* buf = stage + (size_t)warp * 2 * stage_bytes;
+    const char* ring_s = (const char*)B.ring + (size_t)s * B.P * esz;
+    int pos0 = 0;
+    auto issue = [&](int j) {                                      // lane 0: bulk-copy tick j into stage j & 1
+        int pos = pos0 + j * TICK;
+        while (pos >= B.P) pos -= B.P;
+        mbar_expect_tx(bar + (j & 1), (unsigned)(TICK * esz));
+        bulk_g2s(buf + (size_t)(j & 1) * stage_bytes, ring_s + (size_t)pos * esz, (unsigned)(TICK * esz), bar + (j & 1));
+    };
     if (pipelined) {
-        unsigned long long* bar = mbar[warp];
-        char* buf = stage + (size_t)warp * 2 * stage_bytes;
-        const char* ring_s = (const char*)B.ring + (size_t)s * B.P * esz;
+        pos0 = (int)((plan.V[0] - TICK) % B.P);                    // every tick advances by exactly TICK samples
         if (lane == 0) {
             mbar_init(bar, 1); mbar_init(bar + 1, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            issue(0);
+            if (n_ticks > 1) issue(1);
         }
         __syncwarp();
-        const int pos0 = (int)((plan.V[0] - TICK) % B.P);      // every tick advances by exactly TICK samples
-        auto issue = [&](int j) {
-            if (lane == 0) {
-                int pos = pos0 + j * TICK;
-                while (pos >= B.P) pos -= B.P;
-                mbar_expect_tx(bar + (j & 1), (unsigned)(TICK * esz));
-                bulk_g2s(buf + (size_t)(j & 1) * stage_bytes, ring_s + (size_t)pos * esz, (unsigned)(TICK * esz), bar + (j & 1));
-            }
-        };
-        issue(0);
-        if (n_ticks > 1) issue(1);
-        for (int j = 0; j < n_ticks; j++) {
-            mbar_wait(bar + (j & 1), (unsigned)((j >> 1) & 1));
-            double ss = warp_sumsq_smem(buf + (size_t)(j & 1) * stage_bytes, B.fmt, lane);
-            __syncwarp();
-            if (j + 2 < n_ticks) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(j + 2);
-            }
-            if (B.fmt == 1) ss *= (1.0 / 1073741824.0);
-            if (lane == 0) plan.pv[j][0] = ss / (double)fs;              // np.mean(frame**2)   wakeword.py:481
-            __syncwarp();
-            replay_tick(j);
-        }
-    } else {
+    } else if (!presummed) {
         // ---- phase 1: every planned range (generic: any frame size, wrap, first-full and live streams)
         for (int j = 0; j < n_ticks; j++) {
             const long long V = plan.V[j];
@@ -629,14 +691,29 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
             if (fs > 0 && !plan.alias[j]) {
                 // RMS window of is_silent: the last min(1600, R) samples; zeros before the stream began
                 const long long a0 = V - nrec;
-                const double ss = warp_sumsq((const char*)B.ring + (size_t)s * B.P * esz, B.P, B.fmt,
-                                             a0 < 0 ? 0 : a0, (int)(a0 < 0 ? V : nrec), lane);
+                const double ss = warp_sumsq(ring_s, B.P, B.fmt, a0 < 0 ? 0 : a0, (int)(a0 < 0 ? V : nrec), lane);
                 if (lane == 0) plan.pv[j][GATE_MAXP] = ss;
             }
         }
         __syncwarp();
-        // ---- phase 2: replay the ticks in order
-        for (int j = 0; j < n_ticks; j++) replay_tick(j);
+    }
+    // ---- phase 2: replay the ticks in order (pipelined: tick j's sum first, copies of j+1, j+2 in flight)
+    for (int j = 0; j < n_ticks; j++) {
+        if (pipelined) {
+            mbar_wait(bar + (j & 1), (unsigned)((j >> 1) & 1));
+            double ss = warp_sumsq_smem(buf + (size_t)(j & 1) * stage_bytes, B.fmt, lane);
+            __syncwarp();
+            if (lane == 0) {
+                if (j + 2 < n_ticks) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(j + 2);
+                }
+                if (B.fmt == 1) ss *= (1.0 / 1073741824.0);
+                plan.pv[j][0] = ss / (double)fs;                     // np.mean(frame**2)   wakeword.py:481
+            }
+            __syncwarp();
+        }
+        replay_tick(j);
     }
     __syncwarp();
 
