@@ -520,6 +520,10 @@ extern "C" int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pc
     ring_commit_kernel<<<(n_streams + 255) / 256, 256, 0, ctx->stream>>>(B, stream0, n_streams, (int)n, with_sums);
     CK(cudaGetLastError());
     ctx->launches++;
+    // do the per-block sums of K1 cover everything pushed since the last tick, for every stream?
+    if (!with_sums) ctx->all_presummed = false;
+    else if (stream0 == 0 && n_streams == B.n_streams && ctx->pushes_since_tick == 0) ctx->all_presummed = true;
+    ctx->pushes_since_tick++;
     for (int s = stream0; s < stream0 + n_streams; s++) {
         ctx->h_written[s] += n;
         if (ctx->h_frame_size[s] == 0) ctx->h_frame_size[s] = ctx->h_prm[s].frame_size > 0 ? ctx->h_prm[s].frame_size : (int)n;
@@ -548,7 +552,7 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     if (smem_chunks & 1) smem_chunks++;                   // keeps the staging area 16-byte aligned
     // bulk staging of whole ticks pays when chunk arrays are small (frame_size 1600: 100 chunks)
     static const int stage_env = [] { const char* e = getenv("EWK_GATE_STAGE"); return e ? atoi(e) : 1; }();
-    const int stage_bytes = (stage_env && smem_chunks <= 128) ? TICK * (B.fmt == 1 ? 2 : 4) : 0;
+    const int stage_bytes = (stage_env && smem_chunks <= 128 && !ctx->all_presummed) ? TICK * (B.fmt == 1 ? 2 : 4) : 0;
     cudaEvent_t pe = ctx->prof_begin(1);
     for (int done = 0; done < n_ticks; done += GATE_MAX_TICKS) {
         const int nt = std::min(GATE_MAX_TICKS, n_ticks - done);
@@ -566,6 +570,7 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     ctx->prof_end(pe, 2);
     CK(cudaGetLastError());
     ctx->launches += 1;
+    ctx->pushes_since_tick = 0;
     // host mirrors (audio clock): V after these ticks, given what has been pushed
     for (int s = 0; s < B.n_streams; s++) {
         ctx->h_tick[s] += n_ticks;

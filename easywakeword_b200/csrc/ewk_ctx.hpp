@@ -51,6 +51,8 @@ struct ewk_ctx {
     void* own_results = nullptr;
     ewk::DevBuf b_stage, b_trace, b_read, b_dense;
     int chunk_cap = 0;
+    bool all_presummed = false;            // K1's block sums cover every sample pushed since the last tick
+    int pushes_since_tick = 0;
     long long launches = 0;
     std::vector<ewk::StreamParams> h_prm;
     std::vector<long long> h_written;      // host mirror of StreamState.written

@@ -516,17 +516,26 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
     // per-stream state and parameters live in shared memory (only lane 0 mutates them)
     StreamState& st = st_s[warp];
     const StreamParams& prm = prm_s[warp];
-    if (lane == 0) { st_s[warp] = B.st[s]; prm_s[warp] = B.prm[s]; }
+    double* g_ms = B.chunk_ms + (size_t)s * 2 * B.chunk_cap;
+    double* g_sorted = g_ms + B.chunk_cap;
+    {
+        // one round trip: state, parameters and (speculatively, up to the shared-memory capacity) the chunk arrays
+        static_assert(sizeof(StreamState) % 8 == 0 && sizeof(StreamParams) % 8 == 0, "8-byte words");
+        const unsigned long long* gs = reinterpret_cast<const unsigned long long*>(B.st + s);
+        const unsigned long long* gp = reinterpret_cast<const unsigned long long*>(B.prm + s);
+        unsigned long long* ds = reinterpret_cast<unsigned long long*>(&st_s[warp]);
+        unsigned long long* dp = reinterpret_cast<unsigned long long*>(&prm_s[warp]);
+        if (lane < (int)(sizeof(StreamState) / 8)) ds[lane] = gs[lane];
+        if (lane < (int)(sizeof(StreamParams) / 8)) dp[lane] = gp[lane];
+        const int spec = min(smem_chunks, B.chunk_cap);
+        for (int i = lane; i < spec; i += 32) { ms[i] = g_ms[i]; SA[i] = g_sorted[i]; }
+    }
     __syncwarp();
     const int fs = st.frame_size;
     const long long tick0 = st.tick, visible0 = st.visible, written0 = st.written;
     const int valid0 = st.chunks_valid;
     const int n_chunks = fs > 0 ? B.R / fs : 0;
-    double* g_ms = B.chunk_ms + (size_t)s * 2 * B.chunk_cap;
-    double* g_sorted = g_ms + B.chunk_cap;
     const bool use_chunks = n_chunks > 0 && n_chunks <= B.chunk_cap && n_chunks <= smem_chunks;
-    if (use_chunks && valid0)
-        for (int i = lane; i < n_chunks; i += 32) { ms[i] = g_ms[i]; SA[i] = g_sorted[i]; }
 
     // ---- phase 0: lane j plans tick j
     {
