@@ -139,7 +139,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     K, W = args.steps, args.warmup
     # a step = every core runs the reference algorithm over `sample_s` seconds of one stream
-    sample_s = 4.0
+    sample_s = 8.0
     if W > 0:
         cpu_throughput(1.0, cores, fast=False, rounds=1)
     t0 = time.perf_counter()
@@ -302,23 +302,43 @@ def run_ours(args):
         kern = {k: v for k, v in prof.items() if v["launches"]}
         tot_ms = sum(v["ms"] for v in kern.values()) or 1.0
         dom = max(kern, key=lambda k: kern[k]["ms"])
-        # algorithmic bytes per launch: PCM of the step read once from the ring + per-tick gate
-        # state (8 B) per stream; + 8 B per event.  One launch of the dominant kernel covers one step.
         ev_per_step = n_events / max(1, K) / world
-        alg_bytes = {"tick_gate": n * (STEP_SAMPLES * 2 + TICKS_PER_STEP * 8) + ev_per_step * 8,
-                     "ring_push": n * STEP_SAMPLES * 2 * 2,
+        # ALGORITHMIC bytes per launch, one launch = one step of one rank:
+        #  ring_push   (K1 fused): step PCM read once + written once into the rings + one 8-byte block sum per tick
+        #  tick_gate   (K2): with K1's block sums it reads no PCM: 10 block sums + state in/out per stream;
+        #              (host pushes: it reads the step's PCM once itself)
+        #  segment_queue (K3): the PCM of every candidate segment once (mean 17.6 k samples) + its 40-byte event
+        alg_bytes = {"ring_push": n * (STEP_SAMPLES * 2 * 2 + TICKS_PER_STEP * 8),
+                     "tick_gate": n * (TICKS_PER_STEP * 8 + 2 * 104 + 72 + 2 * 1600),
                      "segment_queue": ev_per_step * (17600 * 2 + 40)}
         share = {k: v["ms"] / tot_ms for k, v in kern.items()}
+
+        def kroof(name):
+            if name not in kern:
+                return None
+            ms = kern[name]["ms"] / kern[name]["launches"]
+            gbs = alg_bytes.get(name, 0.0) / (ms * 1e-3) / 1e9
+            return {"avg_launch_ms": ms, "algorithmic_bytes": alg_bytes.get(name), "achieved_gbs": gbs, "frac": gbs / hbm_peak,
+                    "traffic": traffic.get(name)}
+
+        traffic = {}
+        tp = os.path.join(REPO, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp))      # dram read+write bytes per launch from the committed ncu --set full captures
         avg_ms = kern[dom]["ms"] / kern[dom]["launches"]
         achieved = alg_bytes.get(dom, 0.0) / (avg_ms * 1e-3) / 1e9
-        gate_avg = kern.get("tick_gate", {"ms": 0, "launches": 1})
-        gate_ms = gate_avg["ms"] / max(1, gate_avg["launches"])
+        frames_per_step = ev_per_step * 111.0          # 1 + 17600 // 160 frames per candidate
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / hbm_peak, "traffic": traffic.get(dom), "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "share_of_kernel_time": share,
-                    "tick_gate": {"avg_launch_ms": gate_ms,
-                                  "achieved_gbs": alg_bytes["tick_gate"] / (gate_ms * 1e-3) / 1e9 if gate_ms else None,
-                                  "frac": alg_bytes["tick_gate"] / (gate_ms * 1e-3) / 1e9 / hbm_peak if gate_ms else None},
+                    "note": "the dominant kernel (fused MFCC+match on candidate segments) is FP32-issue bound, ~55 flop per "
+                            "PCM byte (DESIGN.md §4): its HBM fraction is small by construction; `compute` gives its FP32 "
+                            "rate and `hbm_bound_kernel` the roofline of the HBM-bound kernel of the step (K1 fused push+sums)",
+                    "compute": {"frames_per_launch": frames_per_step, "flop_per_frame": 17700,
+                                "achieved_tflops": frames_per_step * 17700 / (avg_ms * 1e-3) / 1e12 if dom == "segment_queue" else None,
+                                "fp32_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12},
+                    "hbm_bound_kernel": dict(kernel="ring_push", **(kroof("ring_push") or {})),
+                    "tick_gate": kroof("tick_gate"),
                     "whole_step_frac": (n * STEP_SAMPLES * 2) * K / (ms_dev * 1e-3) / 1e9 / hbm_peak}
         cpu = None
         if world == 1 and not args.no_cpu:

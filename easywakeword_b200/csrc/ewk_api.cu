@@ -563,7 +563,7 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     }
     ctx->prof_end(pe, 1);
     CK(cudaGetLastError());
-    const int grid = std::max(1, 3 * ctx->sm_count);
+    const int grid = std::max(1, 2 * ctx->sm_count);
     pe = ctx->prof_begin(2);
     segment_queue_kernel<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ctx->stream>>>(
         ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);

@@ -24,7 +24,7 @@
 
 namespace ewk {
 
-constexpr int DENSE_THREADS = 256;
+constexpr int DENSE_THREADS = 512;
 constexpr int DENSE_WARPS = DENSE_THREADS / 32;
 constexpr int DH = 32;                 // hops per sub-chunk
 constexpr int DENSE_MAX_T = 4;         // templates per launch
@@ -61,7 +61,7 @@ __device__ __forceinline__ const float* dense_row(const float* G, const float* e
     return edge_kh + (2 + t - tp.t_hi - 1) * ROW;
 }
 
-__global__ void __launch_bounds__(DENSE_THREADS, 3)
+__global__ void __launch_bounds__(DENSE_THREADS, 2)
 dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, DenseArgs A) {
     extern __shared__ __align__(16) float smem[];
     FrameTables* ft = reinterpret_cast<FrameTables*>(smem);

@@ -15,7 +15,7 @@
 
 namespace ewk {
 
-constexpr int SEG_THREADS = 256;
+constexpr int SEG_THREADS = 512;
 constexpr int SEG_WARPS = SEG_THREADS / 32;
 constexpr int SEG_SMEM_FRAMES = 301;           // 1 + 48000/160
 constexpr int FEAT = 2 * N_MFCC;               // mean[20] ++ std[20]
@@ -264,7 +264,7 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
 }
 
 // K3, batch form: one CTA per caller-described segment (extract_mfcc / calculate_similarity / matches).
-__global__ void __launch_bounds__(SEG_THREADS, 3)
+__global__ void __launch_bounds__(SEG_THREADS, 2)
 segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __restrict__ segs,
                           int cap_frames, float* __restrict__ ws,           // global spill [frames][22]
                           const TemplateFeat* __restrict__ tmpl, int n_tmpl, int tmpl_first,

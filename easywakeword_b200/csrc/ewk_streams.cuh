@@ -741,7 +741,7 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
 // ------------------------------------------------------------------------------------ K3 (queue form)
 // Persistent CTAs drain the segments K2 queued: PCM straight from the stream's device ring ->
 // fused MFCC + template match -> score written back into the event record and the per-stream result.
-__global__ void __launch_bounds__(SEG_THREADS, 3)
+__global__ void __launch_bounds__(SEG_THREADS, 2)
 segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, int n_tmpl_slots) {
     extern __shared__ __align__(16) float smem[];
     const SegSmem m = seg_carve(smem, SEG_SMEM_FRAMES);
