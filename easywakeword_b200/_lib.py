@@ -227,6 +227,7 @@ def _declare_stream_protos(lib):
         "ewk_read_segment": (C.c_int, [vp, i32, i64, i64, f32p]),
         "ewk_stream_results": (C.c_int, [vp, vp]),
         "ewk_dense_scores": (C.c_int, [vp, i64, i32, i32, i32, vp, i32]),
+        "ewk_prepare_segments": (C.c_int, [vp, i32, _p(C.c_int32), _p(i64), _p(i64), _p(i64), f32p, i64, i32]),
         "ewk_results_device_ptr": (C.c_int, [vp, _p(vp)]),
         "ewk_set_results_buffer": (C.c_int, [vp, vp]),
         "ewk_host_alloc": (C.c_int, [_p(vp), i64]),
@@ -363,6 +364,19 @@ def _bank_methods():
                                            out.ctypes.data, HOST))
         return out
 
+    def prepare_segments(self, streams, starts, lens):
+        """Level-3 pre-processing (wakeword.py:1020-1025) of many ring segments at once -> list of float32 arrays."""
+        st = np.ascontiguousarray(streams, dtype=np.int32)
+        a = np.ascontiguousarray(starts, dtype=np.int64)
+        ln = np.ascontiguousarray(lens, dtype=np.int64)
+        if len(st) == 0:
+            return []
+        off = np.concatenate([[0], np.cumsum(ln)[:-1]]).astype(np.int64)
+        out = np.empty(int(ln.sum()), np.float32)
+        self._ck(self.lib.ewk_prepare_segments(self.h, len(st), st.ctypes.data_as(_p(C.c_int32)), i64ptr(a), i64ptr(ln),
+                                               i64ptr(off), f32ptr(out), len(out), HOST))
+        return [out[o:o + n] for o, n in zip(off, ln)]
+
     def results(self):
         out = np.empty(self.cfg.n_streams, dtype=RESULT_DTYPE)
         self._ck(self.lib.ewk_stream_results(self.h, out.ctypes.data))
@@ -389,10 +403,10 @@ def _bank_methods():
         ms = (C.c_double * 8)()
         n = (C.c_int64 * 8)()
         self._ck(self.lib.ewk_profile_read(self.h, ms, n))
-        names = ["ring_push", "tick_gate", "segment_queue", "segment_batch", "dense_score"]
+        names = ["ring_push", "tick_gate", "segment_queue", "segment_batch", "dense_score", "segment_prepare"]
         return {names[i]: {"ms": ms[i], "launches": int(n[i])} for i in range(len(names))}
 
-    for f in (dense_scores, profile, profile_read, set_stream_params, push, tick, poll, status, read_last, read_segment, results, results_device_ptr,
+    for f in (prepare_segments, dense_scores, profile, profile_read, set_stream_params, push, tick, poll, status, read_last, read_segment, results, results_device_ptr,
               set_results_buffer, set_cuda_stream, launch_count):
         setattr(Context, f.__name__, f)
 

@@ -117,6 +117,13 @@ class WakeWordBank:
         """word_audio of a level-2 event as float32 (what level 3 transcribes)."""
         return self.ctx.read_segment(int(event["stream"]), int(event["seg_start"]), int(event["seg_len"]))
 
+    def prepare_for_transcription(self, events) -> list:
+        """Batched level-3 pre-processing on the device (wakeword.py:1020-1025) of the word_audio of `events`
+        (any structured rows with stream / seg_start / seg_len): list of float32 arrays ready for the STT backend."""
+        ev = [e for e in events]
+        return self.ctx.prepare_segments([int(e["stream"]) for e in ev], [int(e["seg_start"]) for e in ev],
+                                         [int(e["seg_len"]) for e in ev])
+
     def status(self, stream: int):
         return self.ctx.status(stream)
 
@@ -130,14 +137,13 @@ class WakeWordBank:
         for blk in blocks:
             self.step(blk)
             ev = self.poll()
-            for e in ev:
-                log.append(e.copy())
-                if e["kind"] != EV_SCORED or not e["matched"] or on_match is None:
-                    continue
-                text = None
-                if transcriber is not None:
-                    audio = WakeWord.prepare_for_transcription(self.read_segment(e).astype(np.float64))
-                    text = transcriber.transcribe(audio)
+            log.extend(e.copy() for e in ev)
+            hits = [e for e in ev if e["kind"] == EV_SCORED and e["matched"]]
+            if not hits or on_match is None:
+                continue
+            audio = self.prepare_for_transcription(hits) if transcriber is not None else [None] * len(hits)
+            for e, a in zip(hits, audio):
+                text = transcriber.transcribe(a) if transcriber is not None else None
                 on_match(int(e["stream"]), int(e["tick"]), float(e["score"]), text)
         return log
 

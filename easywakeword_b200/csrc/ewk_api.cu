@@ -699,6 +699,45 @@ extern "C" int ewk_read_segment(ewk_ctx* ctx, int stream, int64_t seg_start, int
     return read_abs(ctx, stream, seg_start, seg_len, out);
 }
 
+extern "C" int ewk_prepare_segments(ewk_ctx* ctx, int n_seg, const int32_t* streams, const int64_t* starts, const int64_t* lens,
+                                    const int64_t* out_offsets, float* out, int64_t out_len, int where) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_prepare_segments");
+    if (rc) return rc;
+    if (n_seg == 0) return EWK_OK;
+    BankView& B = ctx->bank;
+    if (n_seg < 0 || !streams || !starts || !lens || !out_offsets || !out || out_len < 1) {
+        ctx->fail("ewk_prepare_segments: bad arguments");
+        return EWK_ERR_ARG;
+    }
+    std::vector<PrepDesc> d(n_seg);
+    for (int i = 0; i < n_seg; i++) {
+        if (streams[i] < 0 || streams[i] >= B.n_streams || lens[i] < 1 || lens[i] > B.P || starts[i] < 0 ||
+            out_offsets[i] < 0 || out_offsets[i] + lens[i] > out_len) {
+            ctx->fail("ewk_prepare_segments: segment %d is out of range", i);
+            return EWK_ERR_ARG;
+        }
+        if (starts[i] + lens[i] > ctx->h_written[streams[i]]) { ctx->fail("ewk_prepare_segments: segment %d not pushed yet", i); return EWK_ERR_STATE; }
+        if (ctx->h_written[streams[i]] - starts[i] > B.P) { ctx->fail("ewk_prepare_segments: segment %d already overwritten in the ring", i); return EWK_ERR_STATE; }
+        d[i] = PrepDesc{streams[i], (int)lens[i], starts[i], out_offsets[i]};
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->b_desc.ensure(sizeof(PrepDesc) * (size_t)n_seg));
+    CK(cudaMemcpyAsync(ctx->b_desc.p, d.data(), sizeof(PrepDesc) * (size_t)n_seg, cudaMemcpyHostToDevice, ctx->stream));
+    float* d_out = out;
+    if (where == EWK_HOST) { CK(ctx->b_read.ensure(sizeof(float) * (size_t)out_len)); d_out = (float*)ctx->b_read.p; }
+    cudaEvent_t pe = ctx->prof_begin(5);
+    segment_prepare_kernel<<<n_seg, 256, 0, ctx->stream>>>(B, (const PrepDesc*)ctx->b_desc.p, d_out);
+    ctx->prof_end(pe, 5);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (where == EWK_HOST) {
+        CK(cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)out_len, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EWK_OK;
+}
+
 extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl_first, int tmpl_count, float* out, int where) {
     if (!ctx) return EWK_ERR_ARG;
     int rc = need_streams(ctx, "ewk_dense_scores");

@@ -738,6 +738,53 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
     }
 }
 
+// ------------------------------------------------------------------------------------ K5 (level-3 hand-off)
+struct PrepDesc { int stream; int len; long long start; long long out_off; };
+
+// One CTA per segment: mean (double), max |x - mean|, then (x - mean) / max * 1.5 clipped to [-1, 1]
+// (wakeword.py:1020-1025; the reference works in float64 on the float64 ring, the result here is its float32).
+__global__ void __launch_bounds__(256)
+segment_prepare_kernel(BankView B, const PrepDesc* __restrict__ d, float* __restrict__ out) {
+    __shared__ double red[8];
+    __shared__ double bc[2];
+    const PrepDesc pd = d[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const short* q = B.fmt == 1 ? (const short*)B.ring + (size_t)pd.stream * B.P : nullptr;
+    const float* f = B.fmt == 0 ? (const float*)B.ring + (size_t)pd.stream * B.P : nullptr;
+    const int p0 = (int)(pd.start % B.P);
+    auto at = [&](int i) -> double {
+        int p = p0 + i;
+        if (p >= B.P) p -= B.P;
+        return q ? (double)q[p] * (1.0 / 32768.0) : (double)f[p];
+    };
+    double s = 0.0;
+    for (int i = tid; i < pd.len; i += 256) s += at(i);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t += red[w]; bc[0] = t / (double)pd.len; }
+    __syncthreads();
+    const double mean = bc[0];
+    double m = 0.0;
+    for (int i = tid; i < pd.len; i += 256) m = fmax(m, fabs(at(i) - mean));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
+    __syncthreads();
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t = fmax(t, red[w]); bc[1] = t; }
+    __syncthreads();
+    const double mx = bc[1];
+    for (int i = tid; i < pd.len; i += 256) {
+        double v = at(i) - mean;
+        if (mx > 0.0) v = v / mx;
+        v = v * 1.5;
+        v = v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v);
+        out[pd.out_off + i] = (float)v;
+    }
+}
+
 // ------------------------------------------------------------------------------------ K3 (queue form)
 // Persistent CTAs drain the segments K2 queued: PCM straight from the stream's device ring ->
 // fused MFCC + template match -> score written back into the event record and the per-stream result.

@@ -159,6 +159,14 @@ int ewk_stream_status_get(ewk_ctx* ctx, int stream, ewk_stream_status* out);
 int ewk_read_last(ewk_ctx* ctx, int stream, int64_t n_samples, float* out);
 /* word_audio of an event (wakeword.py:1105-1111) for the level-3 hand-off; EWK_ERR_STATE if overwritten. */
 int ewk_read_segment(ewk_ctx* ctx, int stream, int64_t seg_start, int64_t seg_len, float* out);
+/* Level-3 hand-off, batched: what WakeWord._transcribe_audio does to word_audio before the
+ * speech-to-text call (wakeword.py:1020-1025): x - mean(x), / max|.| when > 0, * 1.5, clip to [-1, 1] — for
+ * n_seg segments of the rings at once (typically the matched events of one ewk_poll).  Segment i is
+ * streams[i], absolute samples [starts[i], starts[i] + lens[i]); its float32 result is written at
+ * out + out_offsets[i].  `where` tells whether `out` is host or device memory.  EWK_ERR_STATE if a segment was
+ * already overwritten in its ring. */
+int ewk_prepare_segments(ewk_ctx* ctx, int n_seg, const int32_t* streams, const int64_t* starts, const int64_t* lens,
+                         const int64_t* out_offsets, float* out, int64_t out_len, int where);
 /* Dense per-hop scoring (usage shape of examples/tune_threshold.py:86-116 at hop
  * granularity): for every stream, every hop h in [hop0, hop0 + n_hops) (hop h <-> 160*h samples pushed)
  * and every template slot k in [template_first, template_first + template_count), the value

@@ -155,3 +155,47 @@ def test_bank_run_reports_matches(word):
         want += [(i, e["tick"]) for e in o["events"] if e["matched"]]
     assert sorted((s, t) for s, t, _ in hits) == sorted(want) and len(want) >= 4
     assert all(sc >= 75.0 for _, _, sc in hits)
+
+
+# ---- N1: batched level-3 pre-processing on the device; N4: several reference templates, best one wins
+def test_bank_level3_handoff_and_multi_template(word):
+    from easywakeword_b200.bank import WakeWordBank
+    from oracle import ewk_oracle as O
+    other = synth.synthetic_word(seed=3, duration=0.8)
+    n = 4
+    xs = []
+    for i in range(n):
+        x, _ = synth.stream(6000 + i, 20.0, word if i % 2 == 0 else other, gain=(2.0, 4.0), inserts_per_10s=(2, 3))
+        xs.append(x)
+    q = np.stack([synth.to_int16(x) for x in xs])
+    bank = WakeWordBank(n, [word, other], frame_size=1600, similarity_threshold=75.0,
+                        speech_duration_min=0.5, speech_duration_max=1.6)
+    heard = []
+
+    class Stt:
+        def transcribe(self, audio):
+            assert audio.dtype == np.float32 and np.max(np.abs(audio)) <= 1.0
+            heard.append(audio)
+            return "computer"
+
+    log = bank.run((np.ascontiguousarray(q[:, p:p + 16000]) for p in range(0, q.shape[1], 16000)),
+                   on_match=lambda s, t, sc, txt: None, transcriber=Stt())
+    ev = [e for e in log if e["kind"] == 2]
+    assert len(ev) >= 6 and len(heard) == sum(bool(e["matched"]) for e in ev)
+    # N4: the event's template is the best-scoring slot, equal to the oracle's argmax over both templates
+    mats = [O.WordMatcherOracle(), O.WordMatcherOracle()]
+    mats[0].set_reference(word); mats[1].set_reference(other)
+    # ring content is gone for old events; recompute from the source streams
+    for e in ev:
+        seg = synth.from_int16(q[e["stream"], e["seg_start"]:e["seg_start"] + e["seg_len"]])
+        sc = [float(m.calculate_similarity(seg)) for m in mats]
+        assert abs(float(e["score"]) - max(sc)) <= 0.01
+        if abs(sc[0] - sc[1]) > 0.02:
+            assert int(e["template_slot"]) == int(np.argmax(sc))
+    # N1: device pre-processing == the reference formula (float64) rounded to float32
+    last = [e for e in ev if e["matched"]][-2:]
+    got = bank.prepare_for_transcription(last)
+    for e, g in zip(last, got):
+        seg = synth.from_int16(q[e["stream"], e["seg_start"]:e["seg_start"] + e["seg_len"]]).astype(np.float64)
+        np.testing.assert_allclose(g, O.prepare_for_level3(seg).astype(np.float32), atol=2e-7, rtol=0)
+    bank.close()
