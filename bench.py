@@ -55,13 +55,15 @@ def load_word():
 
 
 def make_pool(stream0, n_streams, word, out):
-    """out[n_streams, POOL_SECONDS*16000] int16 <- synthetic streams (seed = SEED0 + global stream id)."""
+    """out[POOL_SECONDS, n_streams, 16000] int16 <- synthetic streams (seed = SEED0 + global stream id), laid out
+    so that one step (1.0 s of every stream) is one contiguous block, the layout a caller pushing [streams, n]
+    arrays has."""
     from concurrent.futures import ThreadPoolExecutor
     from easywakeword_b200 import synth
 
     def one(s):
         x, _ = synth.stream(SEED0 + stream0 + s, POOL_SECONDS, word, noise_sigma=0.002, gain=(1.0, 4.0))
-        out[s] = synth.to_int16(x)
+        out[:, s, :] = synth.to_int16(x).reshape(POOL_SECONDS, STEP_SAMPLES)
 
     with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 8)) as ex:
         list(ex.map(one, range(n_streams)))
@@ -182,7 +184,7 @@ def run_ours(args):
     word, word_name = load_word()
 
     n = N_STREAMS
-    pool_pin = _lib.PinnedArray((n, POOL_SECONDS * 16000), np.int16)
+    pool_pin = _lib.PinnedArray((POOL_SECONDS, n, STEP_SAMPLES), np.int16)
     make_pool(rank * n, n, word, pool_pin.array)
     pool_host = torch.from_numpy(pool_pin.array)
     pool_dev = pool_host.to(dev, non_blocking=False)
@@ -191,21 +193,33 @@ def run_ours(args):
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     bank = WakeWordBank(n, [word], device=local_rank, buffer_seconds=RING_SECONDS, pcm_dtype=np.int16,
-                        max_push_seconds=STEP_SECONDS, cuda_stream=stream.cuda_stream, max_events=1 << 17, **PARAMS)
+                        max_push_seconds=2 * STEP_SECONDS, cuda_stream=stream.cuda_stream, max_events=1 << 17, **PARAMS)
     ctx = bank.ctx
     results = torch.zeros(n, 2, dtype=torch.int32, device=dev)          # ewk_stream_result[n]: NCCL send buffer
     ctx.set_results_buffer(results.data_ptr())
     gathered = torch.zeros(world * n, 2, dtype=torch.int32, device=dev) if world > 1 else None
 
     def slice_ptr(t, j, esz=2):
-        return (t.data_ptr() + j * STEP_SAMPLES * esz, n, STEP_SAMPLES, POOL_SECONDS * 16000)
+        return (t.data_ptr() + j * n * STEP_SAMPLES * esz, n, STEP_SAMPLES, STEP_SAMPLES)
 
     step_no = [0]
+    pushed = [0]
+
+    def push_next(where):
+        j = pushed[0] % POOL_SECONDS
+        pushed[0] += 1
+        bank.push(slice_ptr(pool_dev if where == _lib.DEVICE else pool_host, j), where=where)
 
     def step(where, read_back):
-        j = step_no[0] % POOL_SECONDS
+        """One step = push of 1.0 s for every stream + its 10 ticks (+ gather, + event read-back).
+        The push of the NEXT step is issued before this step's ticks so that, for host PCM, its H2D copy
+        (copy stream, double-buffered staging) overlaps this step's kernels; every step still pays its own copy."""
+        if pushed[0] == step_no[0]:
+            push_next(where)
         step_no[0] += 1
-        bank.step(slice_ptr(pool_dev if where == _lib.DEVICE else pool_host, j), where=where)
+        if read_back and where == _lib.HOST:
+            push_next(where)
+        bank.tick(TICKS_PER_STEP)
         if gathered is not None:
             dist.all_gather_into_tensor(gathered, results)
         return bank.poll() if read_back else None
@@ -260,9 +274,8 @@ def run_ours(args):
     # dense mode (A9): per-hop scoring of every stream, same push, K4 instead of K2/K3
     dense_out = torch.empty(n * 100, dtype=torch.float32, device=dev)
     def dense_step():
-        j = step_no[0] % POOL_SECONDS
-        step_no[0] += 1
-        bank.push(slice_ptr(pool_dev, j), where=_lib.DEVICE)
+        push_next(_lib.DEVICE)
+        step_no[0] = pushed[0]
         hop_end = bank.samples_pushed // 160
         ctx.dense_scores(hop_end - 100, 100, 0, 1, out_device_ptr=dense_out.data_ptr())
     # no ticks in this arm: let pushes run free of the gate's "un-gated audio" guard

@@ -37,7 +37,11 @@ struct ewk_ctx {
     int sm_count = 0;
     ewk_config cfg{};
     std::string err;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    bool ev_free_valid[2] = {false, false};
+    int stage_idx = 0;
+    ewk::DevBuf b_stage2[2];
     ewk::DeviceTables* d_tables = nullptr;
     ewk::TemplateFeat* d_tmpl = nullptr;
     std::vector<ewk::TemplateFeat> h_tmpl;
