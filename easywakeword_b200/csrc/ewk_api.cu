@@ -109,6 +109,7 @@ extern "C" int ewk_set_cuda_stream(ewk_ctx* ctx, void* s) {
 extern "C" int ewk_synchronize(ewk_ctx* ctx) {
     if (!ctx) return EWK_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->bank.n_streams) { int rc = ctx->flush_pending(); if (rc) return rc; }
     CK(cudaStreamSynchronize(ctx->stream));
     return EWK_OK;
 }
@@ -463,6 +464,58 @@ extern "C" int ewk_set_stream_params(ewk_ctx* ctx, int stream, const ewk_stream_
     return EWK_OK;
 }
 
+// K1 on device-resident PCM (caller's buffer or a staging slot): rings <- src, per-block sums, bookkeeping.
+int ewk_ctx::land(int stream0, int n_streams, const void* d_src, long long d_stride, long long n, int stage_slot) {
+    ewk_ctx* ctx = this;
+    BankView& B = bank;
+    const size_t esz = B.fmt == 1 ? 2 : 4;
+    int with_sums = 0;
+    // fused copy + per-block sums when every stream of the push sits on a 0.1 s block boundary
+    bool aligned = (n % TICK) == 0 && (B.P % TICK) == 0 && B.NB > 0 && ((size_t)d_src & 15) == 0 && ((d_stride * esz) & 15) == 0;
+    for (int s = stream0; aligned && s < stream0 + n_streams; s++) aligned = (h_written[s] % TICK) == 0;
+    if (stage_slot >= 0) CK(cudaStreamWaitEvent(stream, ev_ready[stage_slot], 0));
+    cudaEvent_t pe = prof_begin(0);
+    if (aligned) {
+        dim3 grid((unsigned)((n / TICK + 3) / 4), (unsigned)n_streams);
+        if (B.fmt == 1) ring_push_sums_kernel<short><<<grid, 128, 0, stream>>>(B, stream0, (const short*)d_src, d_stride, (int)n);
+        else ring_push_sums_kernel<float><<<grid, 128, 0, stream>>>(B, stream0, (const float*)d_src, d_stride, (int)n);
+        with_sums = 1;
+    } else {
+        const int per = esz == 2 ? 8 : 4;
+        dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(64, (n / per + 255) / 256)), (unsigned)n_streams);
+        if (B.fmt == 1) ring_push_kernel<short><<<grid, 256, 0, stream>>>(B, stream0, (const short*)d_src, d_stride, (int)n);
+        else ring_push_kernel<float><<<grid, 256, 0, stream>>>(B, stream0, (const float*)d_src, d_stride, (int)n);
+    }
+    prof_end(pe, 0);
+    CK(cudaGetLastError());
+    launches++;
+    if (stage_slot >= 0) {
+        CK(cudaEventRecord(ev_free[stage_slot], stream));
+        ev_free_valid[stage_slot] = true;
+    }
+    ring_commit_kernel<<<(n_streams + 255) / 256, 256, 0, stream>>>(B, stream0, n_streams, (int)n, with_sums);
+    CK(cudaGetLastError());
+    launches++;
+    // do the per-block sums of K1 cover everything pushed since the last tick, for every stream?
+    if (!with_sums) all_presummed = false;
+    else if (stream0 == 0 && n_streams == B.n_streams && pushes_since_tick == 0) all_presummed = true;
+    pushes_since_tick++;
+    for (int s = stream0; s < stream0 + n_streams; s++) {
+        h_written[s] += n;
+        if (h_frame_size[s] == 0) h_frame_size[s] = h_prm[s].frame_size > 0 ? h_prm[s].frame_size : (int)n;
+    }
+    return EWK_OK;
+}
+
+// A host push whose H2D copy is in flight on the copy stream lands (K1) only when something needs its samples:
+// the next push, a tick that reaches into it, or any read of stream state.  That keeps K1(i+1) — which must wait
+// for its copy — out of the way of the kernels of step i on the compute stream, so copy and compute overlap.
+int ewk_ctx::flush_pending() {
+    if (!pending.valid) return EWK_OK;
+    pending.valid = false;
+    return land(pending.stream0, pending.n_streams, b_stage2[pending.slot].p, pending.n, pending.n, pending.slot);
+}
+
 extern "C" int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pcm, int64_t n, int64_t stride, int where) {
     if (!ctx) return EWK_ERR_ARG;
     int rc = need_streams(ctx, "ewk_push");
@@ -473,6 +526,9 @@ extern "C" int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pc
         return EWK_ERR_ARG;
     }
     if (n > B.P - B.R && n > B.R) { ctx->fail("ewk_push: %lld samples exceed the ring (%d)", (long long)n, B.R); return EWK_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    rc = ctx->flush_pending();
+    if (rc) return rc;
     // audio-clock streams: the push may not overwrite samples a pending tick still has to see
     for (int s = stream0; s < stream0 + n_streams; s++) {
         if (ctx->h_prm[s].live) continue;
@@ -483,70 +539,22 @@ extern "C" int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pc
             return EWK_ERR_STATE;
         }
     }
-    CK(cudaSetDevice(ctx->device));
     const size_t esz = B.fmt == 1 ? 2 : 4;
-    bool uniform = true;
-    for (int s = stream0 + 1; s < stream0 + n_streams; s++) uniform &= ctx->h_written[s] == ctx->h_written[stream0];
-    const int p0 = (int)(ctx->h_written[stream0] % B.P);
-    int with_sums = 0;
-    (void)uniform; (void)p0;
-    {
-        const void* d_src = pcm;
-        long long d_stride = stride;
-        int stage_slot = -1;
-        if (where == EWK_HOST) {
-            // Host PCM: H2D on a dedicated copy stream into one of two staging buffers, then the fused K1 moves it
-            // into the rings.  Contiguous sources ([n_streams][n]) go as ONE linear copy (55 GB/s over PCIe 5 vs
-            // 47 GB/s pitched); with the double buffer the copy of push i+1 overlaps the kernels of push i.
-            const int b = ctx->stage_idx;
-            ctx->stage_idx ^= 1;
-            stage_slot = b;
-            CK(ctx->b_stage2[b].ensure(esz * (size_t)n * n_streams));
-            if (ctx->ev_free_valid[b]) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));
-            if (stride == n)
-                CK(cudaMemcpyAsync(ctx->b_stage2[b].p, pcm, esz * (size_t)n * n_streams, cudaMemcpyHostToDevice, ctx->copy_stream));
-            else
-                CK(cudaMemcpy2DAsync(ctx->b_stage2[b].p, (size_t)n * esz, pcm, (size_t)stride * esz, (size_t)n * esz, n_streams,
-                                     cudaMemcpyHostToDevice, ctx->copy_stream));
-            CK(cudaEventRecord(ctx->ev_ready[b], ctx->copy_stream));
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[b], 0));
-            d_src = ctx->b_stage2[b].p;
-            d_stride = n;
-        }
-        // fused copy + per-block sums when every stream of the push sits on a 0.1 s block boundary
-        bool aligned = (n % TICK) == 0 && (B.P % TICK) == 0 && B.NB > 0 && ((size_t)d_src & 15) == 0 && ((d_stride * esz) & 15) == 0;
-        for (int s = stream0; aligned && s < stream0 + n_streams; s++) aligned = (ctx->h_written[s] % TICK) == 0;
-        cudaEvent_t pe = ctx->prof_begin(0);
-        if (aligned) {
-            dim3 grid((unsigned)((n / TICK + 3) / 4), (unsigned)n_streams);
-            if (B.fmt == 1) ring_push_sums_kernel<short><<<grid, 128, 0, ctx->stream>>>(B, stream0, (const short*)d_src, d_stride, (int)n);
-            else ring_push_sums_kernel<float><<<grid, 128, 0, ctx->stream>>>(B, stream0, (const float*)d_src, d_stride, (int)n);
-            with_sums = 1;
-        } else {
-            const int per = esz == 2 ? 8 : 4;
-            dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (n / per + 255) / 256)), (unsigned)n_streams);
-            if (B.fmt == 1) ring_push_kernel<short><<<grid, 256, 0, ctx->stream>>>(B, stream0, (const short*)d_src, d_stride, (int)n);
-            else ring_push_kernel<float><<<grid, 256, 0, ctx->stream>>>(B, stream0, (const float*)d_src, d_stride, (int)n);
-        }
-        ctx->prof_end(pe, 0);
-        CK(cudaGetLastError());
-        ctx->launches++;
-        if (stage_slot >= 0) {
-            CK(cudaEventRecord(ctx->ev_free[stage_slot], ctx->stream));
-            ctx->ev_free_valid[stage_slot] = true;
-        }
-    }
-    ring_commit_kernel<<<(n_streams + 255) / 256, 256, 0, ctx->stream>>>(B, stream0, n_streams, (int)n, with_sums);
-    CK(cudaGetLastError());
-    ctx->launches++;
-    // do the per-block sums of K1 cover everything pushed since the last tick, for every stream?
-    if (!with_sums) ctx->all_presummed = false;
-    else if (stream0 == 0 && n_streams == B.n_streams && ctx->pushes_since_tick == 0) ctx->all_presummed = true;
-    ctx->pushes_since_tick++;
-    for (int s = stream0; s < stream0 + n_streams; s++) {
-        ctx->h_written[s] += n;
-        if (ctx->h_frame_size[s] == 0) ctx->h_frame_size[s] = ctx->h_prm[s].frame_size > 0 ? ctx->h_prm[s].frame_size : (int)n;
-    }
+    if (where != EWK_HOST) return ctx->land(stream0, n_streams, pcm, stride, n, -1);
+    // Host PCM: H2D on a dedicated copy stream into one of two staging buffers.  Contiguous sources
+    // ([n_streams][n]) go as ONE linear copy (55 GB/s over PCIe 5 vs 47 GB/s pitched).
+    const int b = ctx->stage_idx;
+    ctx->stage_idx ^= 1;
+    CK(ctx->b_stage2[b].ensure(esz * (size_t)n * n_streams));
+    if (ctx->ev_free_valid[b]) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));
+    if (stride == n)
+        CK(cudaMemcpyAsync(ctx->b_stage2[b].p, pcm, esz * (size_t)n * n_streams, cudaMemcpyHostToDevice, ctx->copy_stream));
+    else
+        CK(cudaMemcpy2DAsync(ctx->b_stage2[b].p, (size_t)n * esz, pcm, (size_t)stride * esz, (size_t)n * esz, n_streams,
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_ready[b], ctx->copy_stream));
+    ctx->pending.valid = true; ctx->pending.slot = b; ctx->pending.stream0 = stream0; ctx->pending.n_streams = n_streams;
+    ctx->pending.n = n;
     return EWK_OK;
 }
 
@@ -556,6 +564,16 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     if (n_ticks < 1 || n_ticks > 4096) { ctx->fail("ewk_tick: n_ticks must be in [1, 4096]"); return EWK_ERR_ARG; }
     BankView& B = ctx->bank;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->pending.valid) {
+        // land the in-flight host push only if these ticks reach into its samples
+        bool need = false;
+        for (int s = ctx->pending.stream0; !need && s < ctx->pending.stream0 + ctx->pending.n_streams; s++) {
+            const int fs = ctx->h_frame_size[s] > 0 ? ctx->h_frame_size[s] : ctx->h_prm[s].frame_size;
+            if (ctx->h_prm[s].live || fs <= 0) need = true;
+            else need = ((ctx->h_tick[s] + n_ticks) * TICK / fs) * fs > ctx->h_written[s];
+        }
+        if (need) { rc = ctx->flush_pending(); if (rc) return rc; }
+    }
     TraceView tr{};
     const bool want = silent || state || thr || rms;
     const size_t cells = (size_t)B.n_streams * n_ticks;
@@ -651,6 +669,9 @@ extern "C" int ewk_stream_status_get(ewk_ctx* ctx, int stream, ewk_stream_status
     if (!ctx) return EWK_ERR_ARG;
     int rc = need_streams(ctx, "ewk_stream_status_get");
     if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    rc = ctx->flush_pending();
+    if (rc) return rc;
     if (!out || stream < 0 || stream >= ctx->bank.n_streams) { ctx->fail("ewk_stream_status_get: bad stream %d", stream); return EWK_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     StreamState st;
@@ -686,6 +707,9 @@ extern "C" int ewk_read_last(ewk_ctx* ctx, int stream, int64_t n_samples, float*
     if (!ctx) return EWK_ERR_ARG;
     int rc = need_streams(ctx, "ewk_read_last");
     if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    rc = ctx->flush_pending();
+    if (rc) return rc;
     BankView& B = ctx->bank;
     if (!out || stream < 0 || stream >= B.n_streams || n_samples < 0 || n_samples > B.R) {
         ctx->fail("ewk_read_last: bad arguments"); return EWK_ERR_ARG;
@@ -708,6 +732,9 @@ extern "C" int ewk_read_segment(ewk_ctx* ctx, int stream, int64_t seg_start, int
     if (!ctx) return EWK_ERR_ARG;
     int rc = need_streams(ctx, "ewk_read_segment");
     if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    rc = ctx->flush_pending();
+    if (rc) return rc;
     BankView& B = ctx->bank;
     if (!out || stream < 0 || stream >= B.n_streams || seg_len < 1 || seg_len > B.P || seg_start < 0) {
         ctx->fail("ewk_read_segment: bad arguments"); return EWK_ERR_ARG;
@@ -722,6 +749,9 @@ extern "C" int ewk_prepare_segments(ewk_ctx* ctx, int n_seg, const int32_t* stre
                                     const int64_t* out_offsets, float* out, int64_t out_len, int where) {
     if (!ctx) return EWK_ERR_ARG;
     int rc = need_streams(ctx, "ewk_prepare_segments");
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    rc = ctx->flush_pending();
     if (rc) return rc;
     if (n_seg == 0) return EWK_OK;
     BankView& B = ctx->bank;
@@ -760,6 +790,9 @@ extern "C" int ewk_prepare_segments(ewk_ctx* ctx, int n_seg, const int32_t* stre
 extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl_first, int tmpl_count, float* out, int where) {
     if (!ctx) return EWK_ERR_ARG;
     int rc = need_streams(ctx, "ewk_dense_scores");
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    rc = ctx->flush_pending();
     if (rc) return rc;
     BankView& B = ctx->bank;
     if (!out || hop0 < 0 || n_hops < 1 || tmpl_count < 1 || tmpl_count > DENSE_MAX_T || tmpl_first < 0 ||

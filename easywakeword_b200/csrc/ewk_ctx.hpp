@@ -41,6 +41,9 @@ struct ewk_ctx {
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool ev_free_valid[2] = {false, false};
     int stage_idx = 0;
+    struct Pending { bool valid = false; int slot = 0, stream0 = 0, n_streams = 0; long long n = 0; } pending;
+    int land(int stream0, int n_streams, const void* d_src, long long d_stride, long long n, int stage_slot);
+    int flush_pending();
     ewk::DevBuf b_stage2[2];
     ewk::DeviceTables* d_tables = nullptr;
     ewk::TemplateFeat* d_tmpl = nullptr;
