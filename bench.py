@@ -69,34 +69,48 @@ def make_pool(stream0, n_streams, word, out):
         list(ex.map(one, range(n_streams)))
 
 
-class ClockSampler(threading.Thread):
+class ClockSampler:
+    """nvidia-smi in loop mode (100 ms) for the whole measured part of the run (B200_PROFILING.md clocks line)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_ev = index, [], threading.Event()
+        self.rows, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+        except Exception:
+            self.proc = None
 
-    def run(self):
-        while not self._stop_ev.is_set():
-            try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                    str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([c.strip() for c in o.split(",")])
-            except Exception:
-                pass
-            self._stop_ev.wait(0.1)
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def start(self):
+        if self.thread:
+            self.thread.start()
 
     def finish(self):
-        self._stop_ev.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
+        def num(x):
+            try:
+                return float(x)
+            except Exception:
+                return None
+        sm = [num(r[0]) for r in self.rows if r and num(r[0]) is not None]
+        mx = [num(r[1]) for r in self.rows if len(r) > 1 and num(r[1]) is not None]
+        pw = [num(r[6]) for r in self.rows if len(r) > 6 and num(r[6]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -261,7 +275,6 @@ def run_ours(args):
     ms_dev, launches, _ = timed(_lib.DEVICE, False, K)          # inputs resident in HBM
     bank.poll()
     ms_e2e, _, n_events = timed(_lib.HOST, True, K)             # host PCM -> rings -> events on host
-    clocks = sampler.finish() if sampler else None
 
     # per-kernel device time (CUDA events on the launching stream), same workload, separate loop
     ctx.profile(True)
@@ -301,6 +314,7 @@ def run_ours(args):
     prof_dense = ctx.profile_read()
     ctx.profile(False)
 
+    clocks = sampler.finish() if sampler else None
     audio_per_step = n * STEP_SECONDS * world
     value = audio_per_step * K / (ms_dev * 1e-3)
     e2e_val = audio_per_step * K / (ms_e2e * 1e-3)
