@@ -32,6 +32,7 @@ constexpr int MEL_TAPS = MEL_TAPS0 + MEL_TAPS1 + MEL_TAPS2 + MEL_TAPS3;
 constexpr int SCR_PLANE = 320;            // floats per re / im transpose plane (8 rows x 40)
 constexpr int SCR_P = 264;                // power spectrum, 257 bins padded; aliases the re plane (dead by then)
 constexpr int SCR_WARP = 2 * SCR_PLANE;   // floats of scratch per warp (2560 B)
+constexpr int DCT_ROW4 = 7;                // float4 per band row of the shared DCT table (odd: conflict-free)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float TEN_LOG10_2 = 3.01029995663981195f;   // 10 * log10(2)
 
@@ -53,11 +54,12 @@ struct DeviceTables {
 struct FrameTables {
     float2 hw[8 * 32];            // hw[a*32 + lane]   = hann[2 lane + 64 a], hann[2 lane + 64 a + 1]
     float2 tw1[8 * 32];           // tw1[k*32 + lane]  = W256^(lane k)
-    float2 tw3[8 * 32];           // tw3[m*32 + lane]  = W512^(lane + 32 m)
+    float2 tw3[4 * 32];           // tw3[m*32 + lane]  = W512^(lane + 32 m), m < 4 (bin pairs k, 256-k share it)
     float2 tw2[8 * 4];            // tw2[k*4 + c]      = W32^(c k)
     float melp[MEL_TAPS * 32];    // zero-padded mel taps, [tap][lane]
     int mfirst[4 * 32];           // first FFT bin of band lane + 32 j, [j][lane]
-    float4 dct[N_MELS * N_MFCC / 4];   // dct_t rows of 20 floats, read as 5 float4
+    int coef_of_lane[32];         // which MFCC coefficient the lane holds after warp_dct20 (-1: none)
+    float4 dct[N_MELS * DCT_ROW4];     // per band: coefficients 0-9 (+2 pad) | 10-19 (+2 pad) | pad: 7 float4
 };
 
 __device__ __forceinline__ void load_frame_tables(FrameTables& ft, const DeviceTables* __restrict__ T, int tid, int nthr) {
@@ -65,13 +67,22 @@ __device__ __forceinline__ void load_frame_tables(FrameTables& ft, const DeviceT
         const int a = i >> 5, lane = i & 31;
         ft.hw[i] = make_float2(T->hann[2 * lane + 64 * a], T->hann[2 * lane + 64 * a + 1]);
         ft.tw1[i] = T->w256[(lane * a) & 255];
-        ft.tw3[i] = T->w512[lane + 32 * a];
+        if (a < 4) ft.tw3[i] = T->w512[lane + 32 * a];
     }
     for (int i = tid; i < 32; i += nthr) ft.tw2[i] = T->w256[(8 * (i & 3) * (i >> 2)) & 255];
     for (int i = tid; i < MEL_TAPS * 32; i += nthr) ft.melp[i] = T->mel_pad[i];
     for (int i = tid; i < 4 * 32; i += nthr) ft.mfirst[i] = T->mel_first[i];
-    const float4* d = reinterpret_cast<const float4*>(T->dct_t);
-    for (int i = tid; i < N_MELS * N_MFCC / 4; i += nthr) ft.dct[i] = d[i];
+    float* dd = reinterpret_cast<float*>(ft.dct);
+    for (int i = tid; i < N_MELS * DCT_ROW4 * 4; i += nthr) {
+        const int b = i / (DCT_ROW4 * 4), r = i - b * (DCT_ROW4 * 4);      // r < 28: [half 0: 12][half 1: 12][pad 4]
+        const int half = r / 12, c = r - half * 12;
+        dd[i] = (half < 2 && c < 10) ? T->dct_t[b * N_MFCC + 10 * half + c] : 0.f;
+    }
+    for (int i = tid; i < 32; i += nthr) {
+        const int w = i & 7;
+        const int within = w == 0 ? 0 : w == 1 ? 1 : w == 2 ? 2 : w == 4 ? 3 : w == 5 ? 4 : -1;
+        ft.coef_of_lane[i] = within < 0 ? -1 : 10 * ((i >> 4) & 1) + 5 * ((i >> 3) & 1) + within;
+    }
 }
 
 __device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -146,21 +157,24 @@ __device__ __forceinline__ void warp_power_spectrum(const float2 (&x)[8], const 
         dft4(w0, w1, w2, w3, o[e], o[e + 2], o[e + 4], o[e + 6]);
     }
     __syncwarp();                             // every lane holds its Z values: the planes may be overwritten by P
-    // real-FFT untangle: X[k] = E[k] + W512^k O[k],  E = (Z[k] + conj Z[256-k])/2,  O = (Z[k] - conj Z[256-k])/(2i)
+    // real-FFT untangle, two bins per step: with E = (Z[k] + conj Z[256-k])/2, O = (Z[k] - conj Z[256-k])/(2i) and
+    // T = W512^k O,  X[k] = E + T  and  X[256-k] = conj(E - T).  The lane owning k = lane + 32 m (m < 4) fetches
+    // Z[256-k] from lane 32 - lane (register 7 - m) and writes both powers; lane 0 pairs with itself.
     const int pl = (32 - lane) & 31;
 #pragma unroll
-    for (int m = 0; m < 8; m++) {
+    for (int m = 0; m < 4; m++) {
         float pr = __shfl_sync(FULL, o[7 - m].x, pl);
         float pi = __shfl_sync(FULL, o[7 - m].y, pl);
         if (lane == 0) { pr = o[(8 - m) & 7].x; pi = o[(8 - m) & 7].y; }
         const float er = o[m].x + pr, ei = o[m].y - pi;     // 2E
         const float qr = o[m].y + pi, qi = pr - o[m].x;     // 2O
         const float2 w = ft.tw3[m * 32 + lane];
-        const float xr = er + (w.x * qr - w.y * qi);
-        const float xi = ei + (w.x * qi + w.y * qr);
-        P[lane + 32 * m] = 0.25f * (xr * xr + xi * xi);
+        const float tr = w.x * qr - w.y * qi, ti = w.x * qi + w.y * qr;
+        const float ar = er + tr, ai = ei + ti, br = er - tr, bi = ei - ti;
+        P[lane + 32 * m] = 0.25f * (ar * ar + ai * ai);
+        P[(32 - lane) + 32 * (7 - m)] = 0.25f * (br * br + bi * bi);
     }
-    if (lane == 0) { const float d = o[0].x - o[0].y; P[256] = d * d; }
+    if (lane == 0) P[128] = o[4].x * o[4].x + o[4].y * o[4].y;
     if (lane >= 1 && lane < SCR_P - 256) P[256 + lane] = 0.f;      // zero padding read by the padded mel taps
     __syncwarp();
 }
@@ -183,42 +197,39 @@ __device__ __forceinline__ void warp_log_mel(const float* __restrict__ P, const 
     out[3] = mel_band<MEL_TAPS3>(P + ft.mfirst[96 + lane], w + 32 * (MEL_TAPS0 + MEL_TAPS1 + MEL_TAPS2));
 }
 
-// Which coefficient the lane holds after warp_dct20 (or -1).
-__device__ __forceinline__ int dct_lane_coef(int lane) {
-    const int w = lane & 7;                       // (b2 b1 b0)
-    const int within = w == 0 ? 0 : w == 1 ? 1 : w == 2 ? 2 : w == 4 ? 3 : w == 5 ? 4 : -1;
-    return within < 0 ? -1 : 10 * ((lane >> 4) & 1) + 5 * ((lane >> 3) & 1) + within;
-}
-
-// One warp: log-mel x[4] per lane (bands lane + 32 j, already floored) -> ortho DCT-II coefficient
-// dct_lane_coef(lane) returned in the lanes that own one.
+// One warp: log-mel x[4] per lane (bands lane + 32 j, already floored) -> ortho DCT-II.  Lanes 0-15 form
+// coefficients 0-9, lanes 16-31 coefficients 10-19, each over its own four bands and the four of lane ^ 16
+// (80 FMAs, 24 16-byte shared loads); a halving shuffle butterfly over the 16 lanes of a half
+// (10 -> 5 -> 3 -> 2 -> 1 values, 11 exchanges) leaves coefficient ft.coef_of_lane[lane] in the lane.
 __device__ __forceinline__ float warp_dct20(const float (&x)[4], const FrameTables& ft, int lane) {
-    float acc[N_MFCC];
+    float xp[4];
 #pragma unroll
-    for (int k = 0; k < N_MFCC; k++) acc[k] = 0.f;
+    for (int j = 0; j < 4; j++) xp[j] = __shfl_xor_sync(FULL, x[j], 16);
+    const int half = lane >> 4;
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) acc[k] = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const float4* row = ft.dct + (lane + 32 * j) * (N_MFCC / 4);
+        const float4* r0 = ft.dct + (lane + 32 * j) * DCT_ROW4 + 3 * half;
+        const float4* r1 = ft.dct + ((lane ^ 16) + 32 * j) * DCT_ROW4 + 3 * half;
 #pragma unroll
-        for (int q = 0; q < N_MFCC / 4; q++) {
-            const float4 w = row[q];
-            acc[4 * q + 0] = fmaf(w.x, x[j], acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(w.y, x[j], acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(w.z, x[j], acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(w.w, x[j], acc[4 * q + 3]);
+        for (int q = 0; q < 3; q++) {
+            const float4 w0 = r0[q], w1 = r1[q];
+            acc[4 * q + 0] = fmaf(w0.x, x[j], fmaf(w1.x, xp[j], acc[4 * q + 0]));
+            acc[4 * q + 1] = fmaf(w0.y, x[j], fmaf(w1.y, xp[j], acc[4 * q + 1]));
+            if (q < 2) {
+                acc[4 * q + 2] = fmaf(w0.z, x[j], fmaf(w1.z, xp[j], acc[4 * q + 2]));
+                acc[4 * q + 3] = fmaf(w0.w, x[j], fmaf(w1.w, xp[j], acc[4 * q + 3]));
+            }
         }
     }
-    // halving butterfly: 20 -> 10 -> 5 -> (6) 3 -> (4) 2 -> 1 values per lane
-    float a10[10], a5[6], a3[4], a2[2];
-    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
-#pragma unroll
-    for (int i = 0; i < 10; i++) {
-        const float send = u16 ? acc[i] : acc[i + 10], keep = u16 ? acc[i + 10] : acc[i];
-        a10[i] = keep + __shfl_xor_sync(FULL, send, 16);
-    }
+    // halving butterfly over lane bits 3..0: 10 -> 5 -> (6) 3 -> (4) 2 -> 1 values per lane
+    float a5[6], a3[4], a2[2];
+    const bool u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
 #pragma unroll
     for (int i = 0; i < 5; i++) {
-        const float send = u8 ? a10[i] : a10[i + 5], keep = u8 ? a10[i + 5] : a10[i];
+        const float send = u8 ? acc[i] : acc[i + 5], keep = u8 ? acc[i + 5] : acc[i];
         a5[i] = keep + __shfl_xor_sync(FULL, send, 8);
     }
     a5[5] = 0.f;
@@ -260,7 +271,7 @@ __device__ __noinline__ float2 warp_frame_mfcc(float2 x0, float2 x1, float2 x2, 
 #pragma unroll
     for (int j = 0; j < 4; j++) v[j] = fmaxf(v[j], floor_db);
     const float cft = warp_dct20(v, ft, lane);
-    const int k = dct_lane_coef(lane);
+    const int k = ft.coef_of_lane[lane];
     if (k >= 0) out[k] = cft;
     return make_float2(mn, mx);
 }
