@@ -177,56 +177,36 @@ __device__ __forceinline__ void load_frame_pairs(const PcmReader& rd, int t, int
     load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
 }
 
-// Phases A-D for one segment by the whole CTA.  Returns a shared-memory pointer to mean[20] ++ std[20]
-// (valid until the next call).  All threads must call it.
-//   A  every frame -> MFCC without the power_to_db floor, plus the frame's log-mel min / max
-//   B  block max -> floor = max - 80 (librosa.power_to_db(top_db=80) couples all frames of a segment)
-//   C  only frames whose min lies below the floor are recomputed with it (none in the common case)
-//   D  mean / std over frames (two-pass, ddof 0)
-__device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegSmem& m,
-                                                   int cap_frames, float* __restrict__ ws,
-                                                   float* __restrict__ frames_out) {
+// Phases B-D for one segment whose un-floored MFCC rows (mf[F][20]) and per-frame log-mel min / max are in
+// place: block max -> floor = max - 80 (librosa.power_to_db(top_db=80) couples all frames of a segment); only
+// frames whose min lies below the floor are recomputed with it (none in the common case); mean / std over
+// frames (two-pass, ddof 0).  Returns a shared-memory pointer to mean[20] ++ std[20] (valid until the next call).
+__device__ __forceinline__ float* segment_finish(const PcmReader& rd, int F, const SegSmem& m, float* mf, float* fmn,
+                                                 const float* fmx, float* __restrict__ frames_out, long long frames_off) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int F = 1 + sd.len / HOP;
-    float* mf = m.mf;
-    float* fmn = m.fmin;
-    float* fmx = m.fmax;
-    if (F > cap_frames) {
-        mf = ws + (size_t)sd.ws_frame_off * FR_STRIDE;
-        fmn = mf + (size_t)F * N_MFCC;
-        fmx = fmn + F;
-    }
-    PcmReader rd;
-    rd.f = sd.fmt == 0 ? (const float*)sd.base : nullptr;
-    rd.q = sd.fmt == 1 ? (const short*)sd.base : nullptr;
-    rd.ring = sd.ring; rd.len = sd.len; rd.start = sd.start;
-
-    // ---- phases A, B, C: one frame loop (a single instance of the frame pipeline in the code)
     float* scr = m.scratch + warp * SCR_WARP;
-    float floor_db = -INFINITY;
-    for (int pass = 0; pass < 2; pass++) {
-        float vmax = -INFINITY;
-        for (int t = warp; t < F; t += SEG_WARPS) {
-            if (pass && !(fmn[t] < floor_db)) continue;      // warp-uniform: only floored frames are redone
-            float2 x[8];
-            load_frame_pairs(rd, t, lane, x);
-            float mn, mx;
-            warp_frame_mfcc(x, *m.ft, scr, lane, floor_db, mf + (size_t)t * N_MFCC, mn, mx);
-            if (!pass && lane == 0) { fmn[t] = mn; fmx[t] = mx; }
-            vmax = fmaxf(vmax, mx);
-        }
-        if (!pass) {
-            if (lane == 0) m.red[warp] = vmax;
-            __syncthreads();
-            float gmax = m.red[0];
+    // ---- phase B
+    float vmax = -INFINITY;
+    for (int t = tid; t < F; t += SEG_THREADS) vmax = fmaxf(vmax, fmx[t]);
 #pragma unroll
-            for (int w = 1; w < SEG_WARPS; w++) gmax = fmaxf(gmax, m.red[w]);
-            floor_db = gmax - 80.0f;                          // librosa.power_to_db(top_db=80)
-        }
+    for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
+    if (lane == 0) m.red[warp] = vmax;
+    __syncthreads();
+    float gmax = m.red[0];
+#pragma unroll
+    for (int w = 1; w < SEG_WARPS; w++) gmax = fmaxf(gmax, m.red[w]);
+    const float floor_db = gmax - 80.0f;                      // librosa.power_to_db(top_db=80)
+    // ---- phase C
+    for (int t = warp; t < F; t += SEG_WARPS) {
+        if (!(fmn[t] < floor_db)) continue;                   // warp-uniform: only floored frames are redone
+        float2 x[8];
+        load_frame_pairs(rd, t, lane, x);
+        float mn, mx;
+        warp_frame_mfcc(x, *m.ft, scr, lane, floor_db, mf + (size_t)t * N_MFCC, mn, mx);
     }
     __syncthreads();
     if (frames_out)
-        for (int i = tid; i < F * N_MFCC; i += SEG_THREADS) frames_out[sd.frames_off * N_MFCC + i] = mf[i];
+        for (int i = tid; i < F * N_MFCC; i += SEG_THREADS) frames_out[frames_off * N_MFCC + i] = mf[i];
 
     // ---- phase D: mean / std over frames; thread = (slice of frames, coefficient)
     constexpr int SL = 12;                       // 12 * 20 = 240 active threads
@@ -261,6 +241,37 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
     }
     __syncthreads();
     return feat;
+}
+
+// Phases A-D for one segment by the whole CTA.  All threads must call it.
+//   A  every frame -> MFCC without the power_to_db floor, plus the frame's log-mel min / max; B-D: segment_finish
+__device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegSmem& m,
+                                                   int cap_frames, float* __restrict__ ws,
+                                                   float* __restrict__ frames_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int F = 1 + sd.len / HOP;
+    float* mf = m.mf;
+    float* fmn = m.fmin;
+    float* fmx = m.fmax;
+    if (F > cap_frames) {
+        mf = ws + (size_t)sd.ws_frame_off * FR_STRIDE;
+        fmn = mf + (size_t)F * N_MFCC;
+        fmx = fmn + F;
+    }
+    PcmReader rd;
+    rd.f = sd.fmt == 0 ? (const float*)sd.base : nullptr;
+    rd.q = sd.fmt == 1 ? (const short*)sd.base : nullptr;
+    rd.ring = sd.ring; rd.len = sd.len; rd.start = sd.start;
+    float* scr = m.scratch + warp * SCR_WARP;
+    for (int t = warp; t < F; t += SEG_WARPS) {
+        float2 x[8];
+        load_frame_pairs(rd, t, lane, x);
+        float mn, mx;
+        warp_frame_mfcc(x, *m.ft, scr, lane, -INFINITY, mf + (size_t)t * N_MFCC, mn, mx);
+        if (lane == 0) { fmn[t] = mn; fmx[t] = mx; }
+    }
+    __syncthreads();
+    return segment_finish(rd, F, m, mf, fmn, fmx, frames_out, sd.frames_off);
 }
 
 // K3, batch form: one CTA per caller-described segment (extract_mfcc / calculate_similarity / matches).

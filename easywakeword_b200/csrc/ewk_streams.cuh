@@ -84,7 +84,10 @@ struct BankView {
     int* ev_count;          // [0] count, [1] dropped
     StreamResult* results;
     double* block_ss;       // [n_streams][NB]: sum of squares of absolute block b = a / 1600 at b % NB (written by K1)
-    int n_streams, R, P, fmt, chunk_cap, max_events, NB;
+    int2* jobs;             // K3 job table: (event index, first frame) per group of SEG_WARPS frames
+    float* jrows;           // [JCAP][SEG_WARPS][22]: MFCC[20], log-mel min, max of every frame of every job
+    int* seg_done;          // [max_events]: finished jobs per event
+    int n_streams, R, P, fmt, chunk_cap, max_events, NB, JCAP;
 };
 
 struct TraceView {          // optional per-tick trace for parity tests: [n_streams][n_ticks]
@@ -786,25 +789,102 @@ segment_prepare_kernel(BankView B, const PrepDesc* __restrict__ d, float* __rest
 }
 
 // ------------------------------------------------------------------------------------ K3 (queue form)
-// Persistent CTAs drain the segments K2 queued: PCM straight from the stream's device ring ->
-// fused MFCC + template match -> score written back into the event record and the per-stream result.
+// The candidates K2 queued are split into jobs of SEG_WARPS (16) frames so that the whole GPU works on every
+// step's candidates at frame granularity (segments differ in length and a step holds ~2 per CTA slot: whole
+// segments per CTA would leave most SMs idle during the last round).
+//   plan kernel (1 CTA): prefix-sum of the pending events' job counts -> job table; events that do not fit the
+//                        job capacity stay pending for the next launch (delayed, never lost).
+//   job kernel:          CTA = one job: 16 warps x 1 frame -> rows in an L2-resident scratch; the CTA that finishes
+//                        a segment's last job gathers its rows into shared memory and runs phases B-D + the match.
+constexpr int EVC_COUNT = 0, EVC_DROPPED = 1, EVC_JOBS = 4;
+
+__global__ void __launch_bounds__(1024)
+segment_plan_kernel(BankView B) {
+    __shared__ int wsum[32];
+    __shared__ int running, sched_end;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = min(B.ev_count[EVC_COUNT], B.max_events);
+    if (tid == 0) { running = 0; sched_end = 0; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int e = base + tid;
+        int ng = 0, F = 0;
+        if (e < n && B.events[e].kind == EV_PENDING) { F = 1 + B.events[e].seg_len / HOP; ng = (F + SEG_WARPS - 1) / SEG_WARPS; }
+        int incl = ng;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int v = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, v, o); if (lane >= o) v += u; }
+            wsum[lane] = v;
+        }
+        __syncthreads();
+        const int first = running + (warp ? wsum[warp - 1] : 0) + incl - ng;
+        if (ng && first + ng <= B.JCAP) {
+            for (int g = 0; g < ng; g++) B.jobs[first + g] = make_int2(e, g * SEG_WARPS);
+            B.events[e].tmpl = first;                       // first job of the event (until the score overwrites it)
+            B.seg_done[e] = 0;
+            atomicMax(&sched_end, first + ng);              // scheduled events form a prefix: jobs [0, sched_end)
+        }
+        __syncthreads();
+        if (tid == 0) running += wsum[31];
+        __syncthreads();
+    }
+    if (tid == 0) B.ev_count[EVC_JOBS] = sched_end;
+}
+
 __global__ void __launch_bounds__(SEG_THREADS, 2)
 segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, int n_tmpl_slots) {
     extern __shared__ __align__(16) float smem[];
     const SegSmem m = seg_carve(smem, SEG_SMEM_FRAMES);
     seg_prologue(T, m);
     __shared__ float sc_s[EWK_MAX_TEMPLATES];
-    const int tid = threadIdx.x;
-    const int n = min(B.ev_count[0], B.max_events);
+    __shared__ int last_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_jobs = B.ev_count[EVC_JOBS];
     const size_t esz = B.fmt == 1 ? 2 : 4;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        const EventRec e = B.events[i];
+    float* scr = m.scratch + warp * SCR_WARP;
+    for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const int2 jb = B.jobs[job];
+        const int ei = jb.x;
+        const EventRec e = B.events[ei];
         if (e.kind != EV_PENDING) continue;                             // uniform across the CTA
-        SegDesc sd;
-        sd.base = (const char*)B.ring + (size_t)e.stream * B.P * esz;
-        sd.start = e.seg_start % B.P; sd.ring = B.P; sd.len = e.seg_len; sd.fmt = B.fmt;
-        sd.ws_frame_off = 0; sd.frames_off = 0;
-        const float* feat = segment_features(sd, m, SEG_SMEM_FRAMES, nullptr, nullptr);
+        const int F = 1 + e.seg_len / HOP;
+        const int ng = (F + SEG_WARPS - 1) / SEG_WARPS;
+        PcmReader rd;
+        rd.q = B.fmt == 1 ? (const short*)((const char*)B.ring + (size_t)e.stream * B.P * esz) : nullptr;
+        rd.f = B.fmt == 0 ? (const float*)((const char*)B.ring + (size_t)e.stream * B.P * esz) : nullptr;
+        rd.ring = B.P; rd.len = e.seg_len; rd.start = e.seg_start % B.P;
+        // ---- phase A of this job: one frame per warp, rows straight to the scratch (stays in L2)
+        const int t = jb.y + warp;
+        if (t < F) {
+            float2 x[8];
+            load_frame_pairs(rd, t, lane, x);
+            float mn, mx;
+            float* row = B.jrows + ((size_t)job * SEG_WARPS + warp) * FR_STRIDE;
+            warp_frame_mfcc(x, *m.ft, scr, lane, -INFINITY, row, mn, mx);
+            if (lane == 0) { row[N_MFCC] = mn; row[N_MFCC + 1] = mx; }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last_s = (atomicAdd(B.seg_done + ei, 1) == ng - 1);
+        __syncthreads();
+        if (!last_s) continue;                                          // uniform across the CTA
+        // ---- this CTA finished the segment: gather its rows (its jobs are consecutive) and finish it
+        __threadfence();
+        const float* rows = B.jrows + (size_t)e.tmpl * SEG_WARPS * FR_STRIDE;
+        for (int i = tid; i < F * FR_STRIDE; i += SEG_THREADS) {
+            const int fr = i / FR_STRIDE, c = i - fr * FR_STRIDE;
+            const float v = __ldcg(rows + i);
+            if (c < N_MFCC) m.mf[fr * N_MFCC + c] = v;
+            else if (c == N_MFCC) m.fmin[fr] = v;
+            else m.fmax[fr] = v;
+        }
+        __syncthreads();
+        const float* feat = segment_finish(rd, F, m, m.mf, m.fmin, m.fmax, nullptr, 0);
         const StreamParams& prm = B.prm[e.stream];
         const int t0 = max(0, prm.template_first);
         const int nt = max(0, min(prm.template_count, n_tmpl_slots - t0));
@@ -820,7 +900,7 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
             for (int k = 0; k < nt; k++)
                 if (!(sc_s[k] != sc_s[k]) && (best != best || sc_s[k] > best)) { best = sc_s[k]; arg = t0 + k; }
             const int ok = best >= prm.similarity_threshold ? 1 : 0;
-            EventRec* o = B.events + i;
+            EventRec* o = B.events + ei;
             o->score = best; o->tmpl = arg; o->matched = ok; o->kind = EV_SCORED;
             StreamResult r = B.results[e.stream];
             r.score = best;
