@@ -404,7 +404,7 @@ int ewk_ctx::init_streams() {
     h_tick.assign(n, 0);
     h_frame_size.assign(n, 0);
     CK(cudaFuncSetAttribute(segment_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
+                            (int)seg_queue_smem_bytes()));
     CK(cudaFuncSetAttribute(tick_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(sizeof(double) * 3 * (size_t)(chunk_cap + 1) * GATE_WARPS + 2 * TICK * 4 * GATE_WARPS)));
     return EWK_OK;
@@ -609,7 +609,7 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     const int grid = std::max(1, 2 * ctx->sm_count);
     pe = ctx->prof_begin(2);
     segment_plan_kernel<<<1, 1024, 0, ctx->stream>>>(B);
-    segment_queue_kernel<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ctx->stream>>>(
+    segment_queue_kernel<<<grid, SEG_THREADS, seg_queue_smem_bytes(), ctx->stream>>>(
         ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
     ctx->prof_end(pe, 2);
     CK(cudaGetLastError());
