@@ -376,11 +376,7 @@ int ewk_ctx::init_streams() {
     CK(cudaMalloc(&bank.events, sizeof(EventRec) * (size_t)bank.max_events));
     CK(cudaMalloc(&bank.ev_count, sizeof(int) * 8));
     CK(cudaMemsetAsync(bank.ev_count, 0, sizeof(int) * 8, stream));
-    bank.JCAP = std::max(4096, 8 * n);
-    CK(cudaMalloc(&bank.jobs, sizeof(int2) * (size_t)bank.JCAP));
-    CK(cudaMalloc(&bank.jrows, sizeof(float) * (size_t)bank.JCAP * SEG_WARPS * FR_STRIDE));
-    CK(cudaMalloc(&bank.seg_done, sizeof(int) * (size_t)bank.max_events));
-    CK(cudaMemsetAsync(bank.seg_done, 0, sizeof(int) * (size_t)bank.max_events, stream));
+
     bank.NB = bank.P / TICK;
     CK(cudaMalloc(&bank.block_ss, sizeof(double) * (size_t)n * std::max(1, bank.NB)));
     CK(cudaMalloc(&own_results, sizeof(StreamResult) * (size_t)n));
@@ -404,7 +400,7 @@ int ewk_ctx::init_streams() {
     h_tick.assign(n, 0);
     h_frame_size.assign(n, 0);
     CK(cudaFuncSetAttribute(segment_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)seg_queue_smem_bytes()));
+                            (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
     CK(cudaFuncSetAttribute(tick_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(sizeof(double) * 3 * (size_t)(chunk_cap + 1) * GATE_WARPS + 2 * TICK * 4 * GATE_WARPS)));
     return EWK_OK;
@@ -412,8 +408,7 @@ int ewk_ctx::init_streams() {
 
 void ewk_ctx::release_streams() {
     for (void* p : {bank.ring, (void*)bank.st, (void*)bank.prm, (void*)bank.chunk_ms, (void*)bank.events,
-                    (void*)bank.ev_count, (void*)bank.block_ss, (void*)bank.jobs, (void*)bank.jrows, (void*)bank.seg_done,
-                    own_results})
+                    (void*)bank.ev_count, (void*)bank.block_ss, own_results})
         if (p) cudaFree(p);
     bank = BankView{};
     own_results = nullptr;
@@ -608,12 +603,11 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     CK(cudaGetLastError());
     const int grid = std::max(1, 2 * ctx->sm_count);
     pe = ctx->prof_begin(2);
-    segment_plan_kernel<<<1, 1024, 0, ctx->stream>>>(B);
-    segment_queue_kernel<<<grid, SEG_THREADS, seg_queue_smem_bytes(), ctx->stream>>>(
+    segment_queue_kernel<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ctx->stream>>>(
         ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
     ctx->prof_end(pe, 2);
     CK(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 1;
     ctx->pushes_since_tick = 0;
     // host mirrors (audio clock): V after these ticks, given what has been pushed
     for (int s = 0; s < B.n_streams; s++) {

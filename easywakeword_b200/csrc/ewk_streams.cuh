@@ -84,10 +84,7 @@ struct BankView {
     int* ev_count;          // [0] count, [1] dropped
     StreamResult* results;
     double* block_ss;       // [n_streams][NB]: sum of squares of absolute block b = a / 1600 at b % NB (written by K1)
-    int2* jobs;             // K3 job table: (event index, first frame) per group of SEG_WARPS frames
-    float* jrows;           // [JCAP][SEG_WARPS][22]: MFCC[20], log-mel min, max of every frame of every job
-    int* seg_done;          // [max_events]: finished jobs per event
-    int n_streams, R, P, fmt, chunk_cap, max_events, NB, JCAP;
+    int n_streams, R, P, fmt, chunk_cap, max_events, NB;
 };
 
 struct TraceView {          // optional per-tick trace for parity tests: [n_streams][n_ticks]
@@ -789,170 +786,49 @@ segment_prepare_kernel(BankView B, const PrepDesc* __restrict__ d, float* __rest
 }
 
 // ------------------------------------------------------------------------------------ K3 (queue form)
-// The candidates K2 queued are split into jobs of SEG_WARPS (16) frames so that the whole GPU works on every
-// step's candidates at frame granularity (segments differ in length and a step holds ~2 per CTA slot: whole
-// segments per CTA would leave most SMs idle during the last round).
-//   plan kernel (1 CTA): prefix-sum of the pending events' job counts -> job table; events that do not fit the
-//                        job capacity stay pending for the next launch (delayed, never lost).
-//   job kernel:          CTA = one job: 16 warps x 1 frame -> rows in an L2-resident scratch; the CTA that finishes
-//                        a segment's last job gathers its rows into shared memory and runs phases B-D + the match.
-constexpr int EVC_COUNT = 0, EVC_DROPPED = 1, EVC_JOBS = 4;
-
-__global__ void __launch_bounds__(1024)
-segment_plan_kernel(BankView B) {
-    __shared__ int wsum[32];
-    __shared__ int running, sched_end;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = min(B.ev_count[EVC_COUNT], B.max_events);
-    if (tid == 0) { running = 0; sched_end = 0; }
-    __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int e = base + tid;
-        int ng = 0, F = 0;
-        if (e < n && B.events[e].kind == EV_PENDING) { F = 1 + B.events[e].seg_len / HOP; ng = (F + SEG_WARPS - 1) / SEG_WARPS; }
-        int incl = ng;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int v = wsum[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, v, o); if (lane >= o) v += u; }
-            wsum[lane] = v;
-        }
-        __syncthreads();
-        const int first = running + (warp ? wsum[warp - 1] : 0) + incl - ng;
-        if (ng && first + ng <= B.JCAP) {
-            for (int g = 0; g < ng; g++) B.jobs[first + g] = make_int2(e, g * SEG_WARPS);
-            B.events[e].tmpl = first;                       // first job of the event (until the score overwrites it)
-            B.seg_done[e] = 0;
-            atomicMax(&sched_end, first + ng);              // scheduled events form a prefix: jobs [0, sched_end)
-        }
-        __syncthreads();
-        if (tid == 0) running += wsum[31];
-        __syncthreads();
-    }
-    if (tid == 0) B.ev_count[EVC_JOBS] = sched_end;
-}
-
-// Warp-granular: every warp of the grid strides over the global frame slots (16 per job) of all pending
-// candidates; no block barrier anywhere.  The warp that completes a segment's last frame finishes it alone:
-// floor check, recomputation of floored frames, mean / std (three frames per step, float2), cosine, score.
+// Persistent CTAs drain the segments K2 queued: PCM straight from the stream's device ring ->
+// fused MFCC + template match -> score written back into the event record and the per-stream result.
 __global__ void __launch_bounds__(SEG_THREADS, 2)
 segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, int n_tmpl_slots) {
     extern __shared__ __align__(16) float smem[];
-    FrameTables* ft = reinterpret_cast<FrameTables*>(smem);
-    float* scratch = smem + sizeof(FrameTables) / sizeof(float);
-    float* featbuf = scratch + SEG_WARPS * SCR_WARP;               // per warp: mean[20] ++ std[20]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    load_frame_tables(*ft, T, tid, SEG_THREADS);
-    __syncthreads();
-    float* scr = scratch + warp * SCR_WARP;
-    float* feat = featbuf + warp * FEAT;
-    const int n_slots = B.ev_count[EVC_JOBS] * SEG_WARPS;
+    const SegSmem m = seg_carve(smem, SEG_SMEM_FRAMES);
+    seg_prologue(T, m);
+    __shared__ float sc_s[EWK_MAX_TEMPLATES];
+    const int tid = threadIdx.x;
+    const int n = min(B.ev_count[0], B.max_events);
     const size_t esz = B.fmt == 1 ? 2 : 4;
-    const int total_warps = gridDim.x * SEG_WARPS;
-    for (int f = blockIdx.x * SEG_WARPS + warp; f < n_slots; f += total_warps) {
-        const int2 jb = B.jobs[f / SEG_WARPS];
-        const int ei = jb.x;
-        const EventRec e = B.events[ei];
-        const int F = 1 + e.seg_len / HOP;
-        const int t = jb.y + (f % SEG_WARPS);
-        if (e.kind != EV_PENDING || t >= F) continue;                   // warp-uniform
-        PcmReader rd;
-        rd.q = B.fmt == 1 ? (const short*)((const char*)B.ring + (size_t)e.stream * B.P * esz) : nullptr;
-        rd.f = B.fmt == 0 ? (const float*)((const char*)B.ring + (size_t)e.stream * B.P * esz) : nullptr;
-        rd.ring = B.P; rd.len = e.seg_len; rd.start = e.seg_start % B.P;
-        {
-            float2 x[8];
-            load_frame_pairs(rd, t, lane, x);
-            float mn, mx;
-            float* row = B.jrows + (size_t)f * FR_STRIDE;
-            warp_frame_mfcc(x, *ft, scr, lane, -INFINITY, row, mn, mx);
-            if (lane == 0) { row[N_MFCC] = mn; row[N_MFCC + 1] = mx; }
-        }
-        __threadfence();
-        __syncwarp();
-        int done = 0;
-        if (lane == 0) done = atomicAdd(B.seg_done + ei, 1);
-        done = __shfl_sync(FULL, done, 0);
-        if (done != F - 1) continue;
-        // ---- this warp completed the segment: finish it from the rows in the (L2-resident) scratch
-        __threadfence();
-        float* rows = B.jrows + (size_t)e.tmpl * SEG_WARPS * FR_STRIDE;
-        float wmax = -INFINITY;
-        for (int u = lane; u < F; u += 32) wmax = fmaxf(wmax, __ldcg(rows + (size_t)u * FR_STRIDE + N_MFCC + 1));
-#pragma unroll
-        for (int o = 16; o; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(FULL, wmax, o));
-        const float floor_db = wmax - 80.0f;                            // librosa.power_to_db(top_db=80)
-        for (int u0 = 0; u0 < F; u0 += 32) {
-            const int u = u0 + lane;
-            const bool hit = u < F && __ldcg(rows + (size_t)u * FR_STRIDE + N_MFCC) < floor_db;
-            unsigned mask = __ballot_sync(FULL, hit);
-            while (mask) {                                              // frames the floor changes: redo them with it
-                const int tt = u0 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                float2 x[8];
-                load_frame_pairs(rd, tt, lane, x);
-                float mn, mx;
-                warp_frame_mfcc(x, *ft, scr, lane, floor_db, rows + (size_t)tt * FR_STRIDE, mn, mx);
-            }
-        }
-        __threadfence();
-        __syncwarp();
-        // mean / std over frames: lane = (group g3 of 3 frames, coefficient pair c2 of 10)
-        const int g3 = lane / 10, c2 = lane - 10 * g3;
-        float2 mean = make_float2(0.f, 0.f), var = make_float2(0.f, 0.f);
-        for (int pass = 0; pass < 2; pass++) {
-            float2 acc = make_float2(0.f, 0.f);
-            if (lane < 30)
-                for (int u = g3; u < F; u += 3) {
-                    const float2 v = __ldcg(reinterpret_cast<const float2*>(rows + (size_t)u * FR_STRIDE + 2 * c2));
-                    if (pass == 0) { acc.x += v.x; acc.y += v.y; }
-                    else { const float dx = v.x - mean.x, dy = v.y - mean.y; acc.x = fmaf(dx, dx, acc.x); acc.y = fmaf(dy, dy, acc.y); }
-                }
-            const float ax = __shfl_sync(FULL, acc.x, c2) + __shfl_sync(FULL, acc.x, c2 + 10) + __shfl_sync(FULL, acc.x, c2 + 20);
-            const float ay = __shfl_sync(FULL, acc.y, c2) + __shfl_sync(FULL, acc.y, c2 + 10) + __shfl_sync(FULL, acc.y, c2 + 20);
-            if (pass == 0) mean = make_float2(ax / (float)F, ay / (float)F);
-            else var = make_float2(ax / (float)F, ay / (float)F);
-        }
-        if (lane < 10) {
-            feat[2 * lane] = mean.x; feat[2 * lane + 1] = mean.y;
-            feat[N_MFCC + 2 * lane] = sqrtf(var.x); feat[N_MFCC + 2 * lane + 1] = sqrtf(var.y);
-        }
-        __syncwarp();
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const EventRec e = B.events[i];
+        if (e.kind != EV_PENDING) continue;                             // uniform across the CTA
+        SegDesc sd;
+        sd.base = (const char*)B.ring + (size_t)e.stream * B.P * esz;
+        sd.start = e.seg_start % B.P; sd.ring = B.P; sd.len = e.seg_len; sd.fmt = B.fmt;
+        sd.ws_frame_off = 0; sd.frames_off = 0;
+        const float* feat = segment_features(sd, m, SEG_SMEM_FRAMES, nullptr, nullptr);
         const StreamParams& prm = B.prm[e.stream];
         const int t0 = max(0, prm.template_first);
         const int nt = max(0, min(prm.template_count, n_tmpl_slots - t0));
-        // best score over the stream's template set (NaN never wins: NaN >= x is false, as in wakeword.py:638-639)
-        float best = __int_as_float(0x7fc00000);
-        int arg = nt > 0 ? t0 : -1;
-        for (int k0 = 0; k0 < nt; k0 += 32) {
-            const int k = k0 + lane;
-            float sc = __int_as_float(0x7fc00000);
-            if (k < nt && tmpl[t0 + k].valid) sc = similarity_score(tmpl[t0 + k].mean, tmpl[t0 + k].std, feat, feat + N_MFCC);
-            for (int l = 0; l < 32 && k0 + l < nt; l++) {               // slot order: the first best wins
-                const float v = __shfl_sync(FULL, sc, l);
-                if (!(v != v) && (best != best || v > best)) { best = v; arg = t0 + k0 + l; }
-            }
+        if (tid < nt) {
+            const TemplateFeat& tf = tmpl[t0 + tid];
+            sc_s[tid] = tf.valid ? similarity_score(tf.mean, tf.std, feat, feat + N_MFCC) : __int_as_float(0x7fc00000);
         }
-        if (lane == 0) {
+        __syncthreads();
+        if (tid == 0) {
+            // best score over the stream's template set (NaN never wins: NaN >= x is false, as in wakeword.py:638-639)
+            float best = __int_as_float(0x7fc00000);
+            int arg = nt > 0 ? t0 : -1;
+            for (int k = 0; k < nt; k++)
+                if (!(sc_s[k] != sc_s[k]) && (best != best || sc_s[k] > best)) { best = sc_s[k]; arg = t0 + k; }
             const int ok = best >= prm.similarity_threshold ? 1 : 0;
-            EventRec* o = B.events + ei;
+            EventRec* o = B.events + i;
             o->score = best; o->tmpl = arg; o->matched = ok; o->kind = EV_SCORED;
             StreamResult r = B.results[e.stream];
             r.score = best;
             r.flags = (r.flags & ~1u) | (unsigned)ok;
             B.results[e.stream] = r;
         }
-        __syncwarp();
+        __syncthreads();
     }
-}
-
-// shared memory of the queue kernel: tables + FFT scratch + one feature buffer per warp
-__host__ __device__ inline size_t seg_queue_smem_bytes() {
-    return sizeof(FrameTables) + sizeof(float) * ((size_t)SEG_WARPS * SCR_WARP + SEG_WARPS * FEAT);
 }
 
 }  // namespace ewk
