@@ -143,7 +143,10 @@ int ewk_default_stream_params(ewk_stream_params* out);
 int ewk_set_stream_params(ewk_ctx* ctx, int stream, const ewk_stream_params* p);
 /* SoundBuffer._add_sound_to_buffer (wakeword.py:454-465) for n_streams streams at once: n samples per
  * stream, stream s reads pcm + s*stride (in samples, format = the ring's).  `where` tells whether pcm is
- * a host pointer (pinned memory makes the copy asynchronous) or a device pointer. */
+ * a host pointer (pinned memory makes the copy asynchronous) or a device pointer.  Host PCM is copied on a
+ * dedicated copy stream into one of two staging buffers and lands in the rings (K1) when something needs it:
+ * the next push, a tick that reaches into it, or a read of stream state; a PINNED host buffer must therefore
+ * stay unchanged until one of those calls (or ewk_synchronize) returns.  Pageable buffers are safe on return. */
 int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pcm, int64_t n, int64_t stride, int where);
 /* n_ticks polls of WakeWord._detect_word (wakeword.py:1064-1157) for every stream: adaptive threshold,
  * is_silent, timing state machine, segment cut, then the fused MFCC+match kernel on every candidate.
