@@ -36,7 +36,7 @@ def test_full_size_gated_path(big, word):
     ev = np.concatenate(events)
     res = bank.results()
     bank.close()
-    assert len(ev) > 2 * N                                   # timeouts (4 s) and level-2 evaluations everywhere
+    assert len(ev) > N                                       # timeouts (4 s) and level-2 evaluations everywhere
     # replication invariance: every replica of a distinct stream reports exactly the same event list
     by_stream = {}
     order = np.lexsort((ev["kind"], ev["tick"], ev["stream"]))
@@ -66,7 +66,7 @@ def test_full_size_gated_path(big, word):
             assert np.isnan(res["score"][s])
     # oracle spot check on a sample of the distinct streams: identical decisions, scores within 0.01
     n_dec = n_no = 0
-    for u in range(0, UNIQUE, 9):
+    for u in range(0, UNIQUE, 3):
         s = canon[u][1]
         mine = ev[starts[s]:starts[s + 1]]
         o = O.detect_stream(synth.from_int16(uniq[u]), word, block=1600, fast=True, similarity_threshold=95.0,
