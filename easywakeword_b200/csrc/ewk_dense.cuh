@@ -31,7 +31,7 @@ constexpr int DENSE_MAX_T = 4;         // templates per launch
 constexpr int DENSE_MAX_F = 224;       // frames per window (templates up to ~2.2 s)
 constexpr int DENSE_MIN_L = 640;       // shorter templates would make a frame both left- and right-masked
 constexpr int ROW = N_MFCC + 2;        // mfcc[20], log-mel min, log-mel max
-constexpr int PATCH_CAP = 8;           // floored frames kept per warp before falling back to recomputation
+constexpr int PATCH_CAP = 6;           // floored frames kept per warp before falling back to recomputation
 
 struct DenseTmplDev {
     int L, n, F, t_hi, r, slot;        // r = F - 1 - t_hi right-edge frames
@@ -49,7 +49,8 @@ struct DenseArgs {
 __host__ __device__ inline size_t dense_smem_bytes(int DG, int T) {
     return sizeof(FrameTables) +
            sizeof(float) * ((size_t)DENSE_WARPS * SCR_WARP + (size_t)DG * ROW + (size_t)T * DH * 4 * ROW +
-                            (size_t)DENSE_WARPS * (PATCH_CAP * N_MFCC + 2 * N_MFCC + 16));
+                            (size_t)DENSE_WARPS * (PATCH_CAP * N_MFCC + 2 * N_MFCC + 16) +
+                            (size_t)DG * (N_MFCC + 1) + 4);
 }
 
 // frame `t` of the window of template `tp` starting at grid index j: pointer to its ROW
@@ -69,12 +70,18 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
     float* G = scratch + DENSE_WARPS * SCR_WARP;                 // [DG][ROW]
     float* edge = G + (size_t)A.DG * ROW;                        // [T][DH][4][ROW]
     float* wbuf = edge + (size_t)A.T * DH * 4 * ROW;             // per warp: patch[PATCH_CAP][20], feat[40], masks[16]
+    // alternate ring: rows of G recomputed with ONE floor value (the current one of the stream), tagged per row, so
+    // that a floored stream-grid frame is recomputed once per floor value and not once per window that contains it
+    float* G2 = wbuf + (size_t)DENSE_WARPS * (PATCH_CAP * N_MFCC + 2 * N_MFCC + 16);   // [DG][20]
+    int* g2tag = reinterpret_cast<int*>(G2 + (size_t)A.DG * N_MFCC);                    // [DG] floor bits of the row
+    int* fstar_s = g2tag + A.DG;                                                        // [1] floor bits served by G2
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.x;
     load_frame_tables(*ft, T, tid, DENSE_THREADS);
     float* scr = scratch + warp * SCR_WARP;
     init_warp_scratch(scr, lane);
+    for (int i = tid; i < A.DG; i += DENSE_THREADS) g2tag[i] = 0x7fc00001;     // matches no floor
     __syncthreads();
 
     float* patch = wbuf + (size_t)warp * (PATCH_CAP * N_MFCC + 2 * N_MFCC + 16);
@@ -119,6 +126,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                 f0 = 0;
                 int r = gfrom_row + job; if (r >= A.DG) r -= A.DG;
                 row = G + r * ROW;
+                if (lane == 0) g2tag[r] = 0x7fc00001;
             } else {
                 int rem = job - n_g, k = 0;
                 while (rem >= nh * (2 + A.t[k].r)) { rem -= nh * (2 + A.t[k].r); k++; }
@@ -141,6 +149,44 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
         }
         g_done = g_hi + 1;
         __syncthreads();
+
+        // ---- the floor of the newest window of template 0 is the stream's current floor f*: stream-grid frames it
+        // changes are recomputed once into G2 (only rows not yet tagged with f*: in steady state the new rows)
+        {
+            const DenseTmplDev& tp0 = A.t[0];
+            const long long jl0 = hs + nh - 1 - tp0.n;
+            if (warp == 0) {
+                float wmax = -INFINITY;
+                if (jl0 >= 0) {
+                    const int j0 = (int)(jl0 % A.DG);
+                    const float* ek0 = edge + (nh - 1) * 4 * ROW;
+                    for (int t = lane; t < tp0.F; t += 32) wmax = fmaxf(wmax, dense_row(G, ek0, tp0, A.DG, j0, t)[N_MFCC + 1]);
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(FULL, wmax, o));
+                if (lane == 0) *fstar_s = jl0 >= 0 ? __float_as_int(wmax - 80.0f) : 0x7fc00002;
+            }
+            __syncthreads();
+            const int fbits = *fstar_s;
+            const float fstar = __int_as_float(fbits);
+            const int span = (int)(g_hi - g_lo + 1);
+            const int row_lo = span > 0 ? (int)(g_lo % A.DG) : 0;
+            const int glo_rel = (int)(g_lo - hs);
+            if (fbits != 0x7fc00002)
+                for (int i = warp; i < span; i += DENSE_WARPS) {
+                    int r = row_lo + i; if (r >= A.DG) r -= A.DG;
+                    if (!(G[r * ROW + N_MFCC] < fstar) || g2tag[r] == fbits) continue;      // warp-uniform
+                    int pos = hs_pos + 160 * (glo_rel + i) - N_FFT / 2;
+                    pos %= B.P; if (pos < 0) pos += B.P;
+                    rd.start = pos; rd.len = N_FFT;
+                    float2 x[8];
+                    load_frame_pairs_at(rd, 0, lane, x);
+                    float mn, mx;
+                    warp_frame_mfcc(x, *ft, scr, lane, fstar, G2 + r * N_MFCC, mn, mx);
+                    if (lane == 0) g2tag[r] = fbits;
+                }
+            __syncthreads();
+        }
 
         // ---- windows of this sub-chunk, one warp per (template, hop)
         for (int w = warp; w < A.T * nh; w += DENSE_WARPS) {
@@ -177,12 +223,25 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                 n_aff += __popc(m);
             }
             __syncwarp();
+            // G2 serves this window's floored stream-grid frames when its floor is the stream's current one
+            const bool ringp = n_aff && __float_as_int(floor_db) == *fstar_s;
             if (n_aff) {
                 // recompute the floored frames (window-local PCM view), keep the first PATCH_CAP of them
+                // (ring-patched windows: only their edge frames, into slot = edge index)
                 { int pos = hs_pos + 160 * (hl - tp.n); pos %= B.P; if (pos < 0) pos += B.P; rd.start = pos; }
                 rd.len = tp.L;
                 int slot = 0;
-                for (int c = 0; c * 32 < tp.F && slot < PATCH_CAP; c++) {
+                if (ringp) {
+                    for (int e = 0; e < 2 + tp.r; e++) {
+                        const int t = e < 2 ? e : tp.t_hi + 1 + (e - 2);
+                        if (!((masks[t >> 5] >> (t & 31)) & 1u)) continue;
+                        float2 x[8];
+                        load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
+                        float mn, mx;
+                        warp_frame_mfcc(x, *ft, scr, lane, floor_db, patch + e * N_MFCC, mn, mx);
+                    }
+                }
+                for (int c = 0; !ringp && c * 32 < tp.F && slot < PATCH_CAP; c++) {
                     unsigned m = masks[c];
                     while (m && slot < PATCH_CAP) {
                         const int t = c * 32 + __ffs(m) - 1;
@@ -223,8 +282,14 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                             bool patched = false;
                             const unsigned m = masks[t >> 5];
                             if ((m >> (t & 31)) & 1u) {
-                                const int sl = (int)masks[8 + (t >> 5)] + __popc(m & ((1u << (t & 31)) - 1u));
-                                if (sl < PATCH_CAP) { v = *reinterpret_cast<const float2*>(patch + sl * N_MFCC + 2 * c2); patched = true; }
+                                if (ringp) {
+                                    if (t >= 2 && t <= tp.t_hi) { int r = j + t; if (r >= A.DG) r -= A.DG; v = *reinterpret_cast<const float2*>(G2 + r * N_MFCC + 2 * c2); }
+                                    else v = *reinterpret_cast<const float2*>(patch + (t < 2 ? t : 2 + t - tp.t_hi - 1) * N_MFCC + 2 * c2);
+                                    patched = true;
+                                } else {
+                                    const int sl = (int)masks[8 + (t >> 5)] + __popc(m & ((1u << (t & 31)) - 1u));
+                                    if (sl < PATCH_CAP) { v = *reinterpret_cast<const float2*>(patch + sl * N_MFCC + 2 * c2); patched = true; }
+                                }
                             }
                             if (!patched) v = *reinterpret_cast<const float2*>(dense_row(G, ekh, tp, A.DG, j, t) + 2 * c2);
                             if (pass == 0) { acc.x += v.x; acc.y += v.y; }
@@ -239,7 +304,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                 else var = make_float2(ax / (float)tp.F, ay / (float)tp.F);
             }
             // floored frames beyond the patch capacity: fold their corrections in by recomputation (rare)
-            if (n_aff > PATCH_CAP) {
+            if (!ringp && n_aff > PATCH_CAP) {
                 // second-order exactness is kept by redoing both passes with on-the-fly recomputation
                 float2 m2 = make_float2(0.f, 0.f), v2 = make_float2(0.f, 0.f);
                 for (int pass = 0; pass < 2; pass++) {
