@@ -412,7 +412,7 @@ void ewk_ctx::release_streams() {
         if (p) cudaFree(p);
     bank = BankView{};
     own_results = nullptr;
-    b_stage.free(); b_trace.free(); b_read.free(); b_dense.free();
+    b_trace.free(); b_read.free(); b_dense.free();
     for (auto& p : prof_pairs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : prof_free) cudaEventDestroy(e);
     prof_pairs.clear(); prof_free.clear();
