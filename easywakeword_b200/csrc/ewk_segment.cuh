@@ -156,11 +156,14 @@ __device__ __forceinline__ void load_frame_pairs_at(const PcmReader& rd, int f0,
             if (i >= 0 && i < rd.len) {
                 int p = p0 + off;
                 if (rd.ring && p >= rd.ring) p -= rd.ring;
-                if (rd.q) {
-                    const unsigned u = __ldg(reinterpret_cast<const unsigned*>(rd.q + p));
-                    v = make_float2((float)(short)(u & 0xffff) * (1.0f / 32768.0f), (float)((int)u >> 16) * (1.0f / 32768.0f));
-                } else v = __ldg(reinterpret_cast<const float2*>(rd.f + p));
-                if (i + 1 >= rd.len) v.y = 0.f;
+                if (i + 1 < rd.len) {
+                    if (rd.q) {
+                        const unsigned u = __ldg(reinterpret_cast<const unsigned*>(rd.q + p));
+                        v = make_float2((float)(short)(u & 0xffff) * (1.0f / 32768.0f), (float)((int)u >> 16) * (1.0f / 32768.0f));
+                    } else v = __ldg(reinterpret_cast<const float2*>(rd.f + p));
+                } else {                                          // last sample of an odd-length window: never read past it
+                    v.x = rd.q ? (float)__ldg(rd.q + p) * (1.0f / 32768.0f) : __ldg(rd.f + p);
+                }
             }
             x[a] = v;
         }
