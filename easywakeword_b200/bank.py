@@ -117,6 +117,18 @@ class WakeWordBank:
         """word_audio of a level-2 event as float32 (what level 3 transcribes)."""
         return self.ctx.read_segment(int(event["stream"]), int(event["seg_start"]), int(event["seg_len"]))
 
+    def dense_sweep(self, blocks: Iterable[np.ndarray], template_first: int = 0, template_count: Optional[int] = None):
+        """Offline sweep (BASELINE config 5): push each [n_streams, n] block (n a multiple of 160) and yield
+        (first_hop, scores[n_streams, n // 160, T]) for the hops it completes — every template scored at every hop."""
+        self.ctx.set_stream_params(-1, **dict(self.params, live=1))     # no ticks here: pushes run free of the gate's guard
+        for blk in blocks:
+            n = blk.shape[-1]
+            if n % 160:
+                raise ValueError("dense_sweep blocks must hold a multiple of 160 samples")
+            hop0 = self.samples_pushed // 160 + 1
+            self.push(blk)
+            yield hop0, self.dense_scores(hop0, n // 160, template_first, template_count)
+
     def prepare_for_transcription(self, events) -> list:
         """Batched level-3 pre-processing on the device (wakeword.py:1020-1025) of the word_audio of `events`
         (any structured rows with stream / seg_start / seg_len): list of float32 arrays ready for the STT backend."""

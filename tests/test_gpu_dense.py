@@ -92,3 +92,39 @@ def test_dense_argument_errors(word):
     with pytest.raises(ValueError, match="No reference word set"):
         ctx.dense_scores(0, 50, 0, 1)
     ctx.close()
+
+
+def test_dense_sweep_multi_template_two_word_phrase(word):
+    """BASELINE config 5 in small: several templates of different lengths (incl. a 2-word phrase of 2.1 s) scored at
+    every hop of a chunked stream; sampled hops against the oracle."""
+    from easywakeword_b200.bank import WakeWordBank
+    from oracle import ewk_oracle as O
+    phrase = np.concatenate([word, np.zeros(2400, np.float32), word[::-1]]).astype(np.float32)   # word + 0.15 s + reversed word
+    short = synth.synthetic_word(seed=9, duration=0.5)
+    tpls = [word, phrase, short]
+    xs = []
+    for i in range(3):
+        x, _ = synth.stream(8100 + i, 9.0, phrase if i == 1 else word, gain=(1.5, 3.0), inserts_per_10s=(2, 2),
+                            zero_gaps=2 if i == 2 else 0)
+        xs.append(synth.from_int16(synth.to_int16(x)))
+    q = np.stack([synth.to_int16(x) for x in xs])
+    bank = WakeWordBank(3, tpls, buffer_seconds=6, max_push_seconds=2.0)
+    got = {}
+    for hop0, sc in bank.dense_sweep(np.ascontiguousarray(q[:, p:p + 24000]) for p in range(0, q.shape[1], 24000)):
+        assert sc.shape == (3, 150, 3)
+        for h in range(sc.shape[1]):
+            got[hop0 + h] = sc[:, h, :]
+    bank.close()
+    assert sorted(got) == list(range(1, 901))
+    rng = np.random.default_rng(2)
+    worst = 0.0
+    for h in sorted(rng.choice(np.arange(215, 900), size=24, replace=False)):
+        for s in range(3):
+            ref = O.dense_scores(xs[s], tpls, [int(h)])[0]
+            worst = max(worst, float(np.nanmax(np.abs(got[int(h)][s] - ref))))
+            assert np.allclose(got[int(h)][s], ref, atol=SCORE_ATOL, equal_nan=True), (h, s, got[int(h)][s], ref)
+    # before a template's first complete window the score is NaN, from then on a number
+    for k, t in enumerate(tpls):
+        nb, _ = O.dense_window(len(t))
+        assert np.isnan(got[nb - 1][0, k]) and not np.isnan(got[nb][0, k])
+    print(f"dense sweep, 3 templates (0.5 s / 0.97 s / 2.1 s): worst |score - oracle| = {worst:.2e}")
