@@ -110,3 +110,17 @@ def test_argument_errors(word):
     with pytest.raises(ValueError):
         _lib.Context(device=0, n_streams=1, ring_samples=10)       # ring shorter than one tick
     ctx.close()
+
+
+@pytest.mark.parametrize("fmt", ["i16", "f32"])
+def test_bulk_staged_gate_path(word, fmt):
+    """frame_size 1600 with half-tick pushes: K1 cannot produce per-block sums (unaligned pushes), every tick is
+    still the aligned single-chunk case, so K2 stages the ticks with cp.async.bulk + mbarrier."""
+    _trace_vs_oracle(word, 1600, fmt, push=800)
+
+
+def test_presummed_and_staged_paths_agree(word):
+    """the same stream through K1 block sums (1 s pushes) and through the staged path (0.05 s pushes): identical"""
+    a = _trace_vs_oracle(word, 1600, "i16", push=16000, seed=99)
+    b = _trace_vs_oracle(word, 1600, "i16", push=800, seed=99)
+    assert a == b
