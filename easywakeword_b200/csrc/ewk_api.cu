@@ -338,6 +338,7 @@ static_assert(sizeof(StreamParams) == sizeof(ewk_stream_params), "ewk_stream_par
 static_assert(sizeof(EventRec) == sizeof(ewk_event), "ewk_event layout");
 static_assert(sizeof(StreamResult) == sizeof(ewk_stream_result), "ewk_stream_result layout");
 constexpr int MIN_FRAME_SIZE = 160;
+constexpr int GATE_SMEM_CHUNKS = 2048;   // storage-order chunks a warp of K2 can hold in shared memory (3 arrays x 4 warps)
 
 extern "C" int ewk_default_stream_params(ewk_stream_params* p) {
     if (!p) return EWK_ERR_ARG;
@@ -401,8 +402,11 @@ int ewk_ctx::init_streams() {
     h_frame_size.assign(n, 0);
     CK(cudaFuncSetAttribute(segment_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
-    CK(cudaFuncSetAttribute(tick_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(sizeof(double) * 3 * (size_t)(chunk_cap + 1) * GATE_WARPS + 2 * TICK * 4 * GATE_WARPS)));
+    {
+        const size_t big = sizeof(double) * 3 * (size_t)(std::min(chunk_cap, GATE_SMEM_CHUNKS) + 1) * GATE_WARPS;
+        const size_t staged = sizeof(double) * 3 * (size_t)130 * GATE_WARPS + (size_t)2 * TICK * 4 * GATE_WARPS;
+        CK(cudaFuncSetAttribute(tick_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(big, staged)));
+    }
     return EWK_OK;
 }
 
@@ -587,6 +591,11 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         tr.state = (unsigned char*)(base + cells * 17);
     }
     int smem_chunks = ctx->gate_chunks();
+    if (smem_chunks > GATE_SMEM_CHUNKS) {
+        ctx->fail("ewk_tick: ring_samples / frame_size = %d chunks; the gate keeps them in shared memory and supports at most %d "
+                  "(use a larger frame_size or a shorter ring)", smem_chunks, GATE_SMEM_CHUNKS);
+        return EWK_ERR_ARG;
+    }
     if (smem_chunks & 1) smem_chunks++;                   // keeps the staging area 16-byte aligned
     // bulk staging of whole ticks pays when chunk arrays are small (frame_size 1600: 100 chunks)
     static const int stage_env = [] { const char* e = getenv("EWK_GATE_STAGE"); return e ? atoi(e) : 1; }();
