@@ -165,3 +165,28 @@ def test_level3_preprocessing_and_vad(word):
     assert O.auto_speech_durations(word) == (pytest.approx(0.69), pytest.approx(1.38))
     assert O.auto_speech_durations(word, user_min=0.5) == (0.5, 1.0)
     assert O.auto_speech_durations(np.zeros(100, np.float32)) [1] >= O.auto_speech_durations(np.zeros(100, np.float32))[0] > 0
+
+
+def test_full_mfcc_front_end_against_torchaudio(word):
+    """Independent implementation of the whole librosa.feature.mfcc chain: torchaudio.transforms.MFCC configured with
+    librosa's defaults (periodic Hann, center + zero padding, power 2, Slaney mel/norm, power_to_db with the global
+    top_db=80 floor, ortho DCT-II).  Agreement to ~1e-6 per-frame relative L2 pins the restated librosa layer to a
+    second code base, including the floor path (digital-silence padding)."""
+    torch = pytest.importorskip("torch")
+    ta = pytest.importorskip("torchaudio")
+    tr = ta.transforms.MFCC(sample_rate=16000, n_mfcc=20, dct_type=2, norm="ortho", log_mels=False,
+                            melkwargs=dict(n_fft=512, hop_length=160, n_mels=128, center=True, pad_mode="constant",
+                                           power=2.0, norm="slaney", mel_scale="slaney", f_min=0.0, f_max=8000.0,
+                                           window_fn=torch.hann_window))
+    cases = {
+        "word": word,
+        "noise": (np.random.default_rng(0).standard_normal(16000) * 0.01).astype(np.float32),
+        "zeros_word_zeros": np.concatenate([np.zeros(3000, np.float32), word, np.zeros(2000, np.float32)]),
+        "sine440": synth.sine(440),
+    }
+    for name, x in cases.items():
+        got = tr(torch.from_numpy(x)).numpy()
+        ref = L.mfcc(x)
+        assert got.shape == ref.shape, name
+        err = np.linalg.norm(got - ref, axis=0) / np.linalg.norm(ref, axis=0)
+        assert err.max() < 2e-5, (name, float(err.max()))
