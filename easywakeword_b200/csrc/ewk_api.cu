@@ -416,7 +416,7 @@ void ewk_ctx::release_streams() {
         if (p) cudaFree(p);
     bank = BankView{};
     own_results = nullptr;
-    b_trace.free(); b_read.free(); b_dense.free();
+    b_trace.free(); b_read.free(); b_dense.free(); b_keep_rows.free(); b_keep_end.free();
     for (auto& p : prof_pairs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : prof_free) cudaEventDestroy(e);
     prof_pairs.clear(); prof_free.clear();
@@ -848,6 +848,13 @@ extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl
     float* d_out = out;
     if (where == EWK_HOST) { CK(ctx->b_dense.ensure(sizeof(float) * n_out)); d_out = (float*)ctx->b_dense.p; }
     A.out = d_out;
+    if (!ctx->b_keep_rows.p) {
+        CK(ctx->b_keep_rows.ensure(sizeof(float) * (size_t)B.n_streams * DENSE_KEEP * ROW));
+        CK(ctx->b_keep_end.ensure(sizeof(long long) * 2 * (size_t)B.n_streams));
+        CK(cudaMemsetAsync(ctx->b_keep_end.p, 0, sizeof(long long) * 2 * (size_t)B.n_streams, ctx->stream));
+    }
+    A.keep_rows = (float*)ctx->b_keep_rows.p;
+    A.keep_end = (long long*)ctx->b_keep_end.p;
     const size_t smem = dense_smem_bytes(A.DG, A.T);
     if (smem > 227 * 1024) { ctx->fail("ewk_dense_scores: templates too long for shared memory (%zu B)", smem); return EWK_ERR_ARG; }
     CK(cudaFuncSetAttribute(dense_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

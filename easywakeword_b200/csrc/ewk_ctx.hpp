@@ -56,7 +56,7 @@ struct ewk_ctx {
     // stream bank
     ewk::BankView bank{};
     void* own_results = nullptr;
-    ewk::DevBuf b_trace, b_read, b_dense;
+    ewk::DevBuf b_trace, b_read, b_dense, b_keep_rows, b_keep_end;
     int chunk_cap = 0;
     bool all_presummed = false;            // K1's block sums cover every sample pushed since the last tick
     int pushes_since_tick = 0;

@@ -31,6 +31,7 @@ constexpr int DENSE_MAX_T = 4;         // templates per launch
 constexpr int DENSE_MAX_F = 224;       // frames per window (templates up to ~2.2 s)
 constexpr int DENSE_MIN_L = 640;       // shorter templates would make a frame both left- and right-masked
 constexpr int ROW = N_MFCC + 2;        // mfcc[20], log-mel min, log-mel max
+constexpr int DENSE_KEEP = 224;        // stream-grid rows carried from one call to the next (>= frames of the longest window)
 constexpr int PATCH_CAP = 6;           // floored frames kept per warp before falling back to recomputation
 
 struct DenseTmplDev {
@@ -44,6 +45,9 @@ struct DenseArgs {
     int DG;                            // rows of the grid-frame ring
     DenseTmplDev t[DENSE_MAX_T];
     float* out;                        // [n_streams][n_hops][T]
+    // carry-over between consecutive calls: the newest stream-grid rows of every stream (functions of the PCM only)
+    float* keep_rows;                  // [n_streams][DENSE_KEEP][ROW], row of grid frame g at g % DENSE_KEEP
+    long long* keep_end;               // [n_streams][2]: grid frames [keep_end[2s], keep_end[2s+1]) are stored (0, 0: nothing)
 };
 
 __host__ __device__ inline size_t dense_smem_bytes(int DG, int T) {
@@ -97,7 +101,26 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
     int max_n = 0, min_n = INT_MAX;
     for (int k = 0; k < A.T; k++) { max_n = max(max_n, A.t[k].n); min_n = min(min_n, A.t[k].n); }
 
-    long long g_done = LLONG_MIN;
+    long long g_done = LLONG_MIN, g_valid_lo = LLONG_MAX;       // ring G holds rows [max(g_valid_lo, g_done - DG), g_done)
+    {
+        // rows computed by the previous call are reused when this call continues where it stopped: the history of
+        // the first window (up to t_hi frames) is loaded instead of recomputed
+        long long need_lo = LLONG_MAX;
+        for (int k = 0; k < A.T; k++) need_lo = min(need_lo, A.hop0 - A.t[k].n + 2);
+        if (need_lo < 2) need_lo = 2;
+        const long long klo = A.keep_rows ? A.keep_end[2 * s] : 0, kend = A.keep_rows ? A.keep_end[2 * s + 1] : 0;
+        if (klo <= need_lo && need_lo < kend && kend - need_lo <= A.DG) {
+            const float* kr = A.keep_rows + (size_t)s * DENSE_KEEP * ROW;
+            const int cnt = (int)(kend - need_lo);
+            for (int i = tid; i < cnt * ROW; i += DENSE_THREADS) {
+                const long long g = need_lo + i / ROW;
+                G[(size_t)(g % A.DG) * ROW + i % ROW] = kr[(size_t)(g % DENSE_KEEP) * ROW + i % ROW];
+            }
+            g_done = kend;
+            g_valid_lo = need_lo;
+        }
+        __syncthreads();
+    }
     for (long long hs = A.hop0; hs < A.hop0 + A.n_hops; hs += DH) {
         const int nh = (int)min((long long)DH, A.hop0 + A.n_hops - hs);
         // ---- frames of this sub-chunk: new stream-grid frames, then the edge frames of every (hop, template)
@@ -108,6 +131,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
         }
         if (g_lo < 2) g_lo = 2;                                   // grid frame g needs samples from 160 g - 256 >= 0
         const long long g_from = max(g_lo, g_done);
+        if (g_valid_lo == LLONG_MAX) g_valid_lo = g_from;
         const int n_g = (int)max(0LL, g_hi - g_from + 1);
         int n_e = 0;
         for (int k = 0; k < A.T; k++) n_e += nh * (2 + A.t[k].r);
@@ -346,6 +370,17 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
             __syncwarp();
         }
         __syncthreads();
+    }
+    if (A.keep_rows && g_done > 2) {
+        // keep the newest rows for the next call
+        float* kr = A.keep_rows + (size_t)s * DENSE_KEEP * ROW;
+        const long long lo = max(g_valid_lo, g_done - min(DENSE_KEEP, A.DG));
+        const int cnt = (int)max(0LL, g_done - lo);
+        for (int i = tid; i < cnt * ROW; i += DENSE_THREADS) {
+            const long long g = lo + i / ROW;
+            kr[(size_t)(g % DENSE_KEEP) * ROW + i % ROW] = G[(size_t)(g % A.DG) * ROW + i % ROW];
+        }
+        if (tid == 0) { A.keep_end[2 * s] = lo; A.keep_end[2 * s + 1] = g_done; }
     }
 }
 
