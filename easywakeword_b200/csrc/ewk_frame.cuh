@@ -85,8 +85,27 @@ __device__ __forceinline__ void load_frame_tables(FrameTables& ft, const DeviceT
     }
 }
 
-__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for both halves of a complex value)
+__device__ __forceinline__ unsigned long long f2_as_u64(float2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 u64_as_f2(unsigned long long a) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a));
+    return r;
+}
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+    return u64_as_f2(r);
+}
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+    return u64_as_f2(r);
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
