@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libewk.so")
     with open(os.path.join(HERE, "libewk.ptxas.log"), "w") as f:
-        f.write(r.stdout + r.stderr)
+        f.write("".join(l for l in (r.stdout + r.stderr).splitlines(True) if "Compile time" not in l))
     return LIB
 
 
