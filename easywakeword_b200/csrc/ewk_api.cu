@@ -120,6 +120,7 @@ int ewk_ctx::init() {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("EWK_SEG_LM")) use_lm = atoi(e) != 0;       // 0: recompute floored frames from the PCM
     if (prop.major < 10) {
         fail("ewk_create: device %d is sm_%d%d; libewk is built for sm_100a only", device, prop.major, prop.minor);
         return EWK_ERR_CUDA;
@@ -151,7 +152,7 @@ void ewk_ctx::release() {
     cudaSetDevice(device);
     if (own_stream) cudaStreamSynchronize(own_stream);
     release_streams();
-    for (DevBuf* b : {&b_pcm, &b_desc, &b_ws, &b_feat, &b_scores, &b_matched, &b_frames, &b_off}) b->free();
+    for (DevBuf* b : {&b_pcm, &b_desc, &b_ws, &b_lm, &b_feat, &b_scores, &b_matched, &b_frames, &b_off}) b->free();
     if (d_tables) cudaFree(d_tables);
     if (d_tmpl) cudaFree(d_tmpl);
     if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
@@ -168,8 +169,8 @@ void ewk_ctx::release() {
 // ------------------------------------------------------------------------------------------
 // Launch K3 over `n_seg` descriptors already on the device.
 int ewk_ctx::launch_segments(const SegDesc* d_segs, int n_seg, int max_frames, long long spill_frames,
-                             int n_tmpl, int tmpl_first, float threshold, float* d_feat, float* d_frames,
-                             float* d_scores, unsigned char* d_matched) {
+                             long long lm_frames, int n_tmpl, int tmpl_first, float threshold, float* d_feat,
+                             float* d_frames, float* d_scores, unsigned char* d_matched) {
     ewk_ctx* ctx = this;
     const int cap = std::min(max_frames, SEG_SMEM_FRAMES);
     float* ws = nullptr;
@@ -177,9 +178,16 @@ int ewk_ctx::launch_segments(const SegDesc* d_segs, int n_seg, int max_frames, l
         CK(b_ws.ensure(sizeof(float) * (size_t)spill_frames * FR_STRIDE));
         ws = (float*)b_ws.p;
     }
+    // log-mel rows of every frame (512 B each), so that the top_db floor costs one DCT per floored frame; beyond
+    // LM_WS_MAX_BYTES the kernel recomputes floored frames from the PCM instead
+    float* lm = nullptr;
+    if (use_lm && lm_frames > 0 && sizeof(float) * (size_t)lm_frames * LM_ROW <= LM_WS_MAX_BYTES) {
+        CK(b_lm.ensure(sizeof(float) * (size_t)lm_frames * LM_ROW));
+        lm = (float*)b_lm.p;
+    }
     cudaEvent_t pe = prof_begin(3);
     segment_mfcc_match_kernel<<<n_seg, SEG_THREADS, seg_smem_bytes(cap), stream>>>(
-        d_tables, d_segs, cap, ws, d_tmpl, n_tmpl, tmpl_first, threshold, d_feat, d_frames, d_scores, d_matched);
+        d_tables, d_segs, cap, ws, lm, d_tmpl, n_tmpl, tmpl_first, threshold, d_feat, d_frames, d_scores, d_matched);
     prof_end(pe, 3);
     CK(cudaGetLastError());
     launches++;
@@ -204,12 +212,13 @@ extern "C" int ewk_extract_mfcc(ewk_ctx* ctx, const float* pcm, int64_t n, int w
     }
     SegDesc sd{};
     sd.base = d_pcm; sd.start = 0; sd.ring = 0; sd.len = (int)n; sd.fmt = 0; sd.ws_frame_off = 0; sd.frames_off = 0;
+    sd.lm_off = 0;
     CK(ctx->b_desc.ensure(sizeof(SegDesc)));
     CK(cudaMemcpyAsync(ctx->b_desc.p, &sd, sizeof(sd), cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx->b_feat.ensure(sizeof(float) * FEAT));
     float* d_frames = nullptr;
     if (frames) { CK(ctx->b_frames.ensure(sizeof(float) * (size_t)F * N_MFCC)); d_frames = (float*)ctx->b_frames.p; }
-    int rc = ctx->launch_segments((const SegDesc*)ctx->b_desc.p, 1, (int)F, F > SEG_SMEM_FRAMES ? F : 0, 0, 0, 0.f,
+    int rc = ctx->launch_segments((const SegDesc*)ctx->b_desc.p, 1, (int)F, F > SEG_SMEM_FRAMES ? F : 0, F, 0, 0, 0.f,
                                   (float*)ctx->b_feat.p, d_frames, nullptr, nullptr);
     if (rc != EWK_OK) return rc;
     float feat[FEAT];
@@ -292,7 +301,7 @@ extern "C" int ewk_similarity_batch(ewk_ctx* ctx, int slot, const void* pcm, int
         return EWK_ERR_ARG;
     }
     const size_t esz = pcm_format == EWK_PCM_I16 ? 2 : 4;
-    int64_t extent = 0, spill = 0;
+    int64_t extent = 0, spill = 0, lm_frames = 0;
     int max_frames = 1;
     std::vector<SegDesc> sd(n_seg);
     for (int i = 0; i < n_seg; i++) {
@@ -307,6 +316,8 @@ extern "C" int ewk_similarity_batch(ewk_ctx* ctx, int slot, const void* pcm, int
         sd[i].start = offsets[i]; sd[i].ring = 0; sd[i].len = (int)lens[i]; sd[i].fmt = pcm_format == EWK_PCM_I16 ? 1 : 0;
         sd[i].ws_frame_off = (int)spill;
         if (F > SEG_SMEM_FRAMES) spill += F;
+        sd[i].lm_off = lm_frames;
+        lm_frames += F;
     }
     CK(cudaSetDevice(ctx->device));
     const void* d_pcm = pcm;
@@ -321,7 +332,7 @@ extern "C" int ewk_similarity_batch(ewk_ctx* ctx, int slot, const void* pcm, int
     CK(ctx->b_feat.ensure(sizeof(float) * FEAT * (size_t)n_seg));
     CK(ctx->b_scores.ensure(sizeof(float) * (size_t)n_seg));
     CK(ctx->b_matched.ensure((size_t)n_seg));
-    rc = ctx->launch_segments((const SegDesc*)ctx->b_desc.p, n_seg, max_frames, spill, 1, slot, threshold,
+    rc = ctx->launch_segments((const SegDesc*)ctx->b_desc.p, n_seg, max_frames, spill, lm_frames, 1, slot, threshold,
                               (float*)ctx->b_feat.p, nullptr, (float*)ctx->b_scores.p, (unsigned char*)ctx->b_matched.p);
     if (rc != EWK_OK) return rc;
     CK(cudaMemcpyAsync(scores, ctx->b_scores.p, sizeof(float) * (size_t)n_seg, cudaMemcpyDeviceToHost, ctx->stream));
@@ -382,6 +393,7 @@ int ewk_ctx::init_streams() {
     CK(cudaMalloc(&bank.block_ss, sizeof(double) * (size_t)n * std::max(1, bank.NB)));
     CK(cudaMalloc(&own_results, sizeof(StreamResult) * (size_t)n));
     bank.results = (StreamResult*)own_results;
+    if (use_lm) CK(cudaMalloc(&bank.lm_ws, sizeof(float) * (size_t)queue_grid() * SEG_SMEM_FRAMES * LM_ROW));
     std::vector<StreamState> st(n);
     std::memset(st.data(), 0, sizeof(StreamState) * n);
     for (auto& x : st) x.thr = 0.01;                                                // wakeword.py:431
@@ -412,7 +424,7 @@ int ewk_ctx::init_streams() {
 
 void ewk_ctx::release_streams() {
     for (void* p : {bank.ring, (void*)bank.st, (void*)bank.prm, (void*)bank.chunk_ms, (void*)bank.events,
-                    (void*)bank.ev_count, (void*)bank.block_ss, own_results})
+                    (void*)bank.ev_count, (void*)bank.block_ss, (void*)bank.lm_ws, own_results})
         if (p) cudaFree(p);
     bank = BankView{};
     own_results = nullptr;
@@ -610,7 +622,7 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     }
     ctx->prof_end(pe, 1);
     CK(cudaGetLastError());
-    const int grid = std::max(1, 2 * ctx->sm_count);
+    const int grid = ctx->queue_grid();
     pe = ctx->prof_begin(2);
     segment_queue_kernel<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ctx->stream>>>(
         ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);

@@ -35,6 +35,7 @@ struct DevBuf {
 struct ewk_ctx {
     int device = 0;
     int sm_count = 0;
+    bool use_lm = true;          // keep log-mel rows of K3 frames in a global workspace (EWK_SEG_LM=0 disables)
     ewk_config cfg{};
     std::string err;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
@@ -48,7 +49,7 @@ struct ewk_ctx {
     ewk::DeviceTables* d_tables = nullptr;
     ewk::TemplateFeat* d_tmpl = nullptr;
     std::vector<ewk::TemplateFeat> h_tmpl;
-    ewk::DevBuf b_pcm, b_desc, b_ws, b_feat, b_scores, b_matched, b_frames, b_off;
+    ewk::DevBuf b_pcm, b_desc, b_ws, b_lm, b_feat, b_scores, b_matched, b_frames, b_off;
 
     void fail(const char* fmt, ...);
     int init();
@@ -79,7 +80,9 @@ struct ewk_ctx {
     int prof_collect();
     int init_streams();
     void release_streams();
-    int launch_segments(const ewk::SegDesc* d_segs, int n_seg, int max_frames, long long spill_frames, int n_tmpl,
-                        int tmpl_first, float threshold, float* d_feat, float* d_frames, float* d_scores,
-                        unsigned char* d_matched);
+    int launch_segments(const ewk::SegDesc* d_segs, int n_seg, int max_frames, long long spill_frames,
+                        long long lm_frames, int n_tmpl, int tmpl_first, float threshold, float* d_feat, float* d_frames,
+                        float* d_scores, unsigned char* d_matched);
+    int queue_grid() const { return sm_count > 0 ? 2 * sm_count : 1; }     // persistent K3 CTAs (2 per SM)
+    static constexpr size_t LM_WS_MAX_BYTES = (size_t)4 << 30;
 };

@@ -268,12 +268,14 @@ __device__ __forceinline__ float warp_dct20(const float (&x)[4], const FrameTabl
 }
 
 // One warp, one frame: PCM -> 20 MFCCs written to out[0..19]; the frame's log-mel min / max (before
-// flooring) are returned in every lane.  floor_db = -INFINITY disables the power_to_db floor.
+// flooring) are returned in every lane.  floor_db = -INFINITY disables the power_to_db floor.  When lm_out is
+// given, the frame's 128 un-floored log-mel values are stored there (band b at lm_out[b]) so that a later floor
+// costs a DCT (warp_refloor_mfcc) instead of the whole pipeline.
 // Deliberately NOT inlined: every kernel shares one copy of the ~1.5k-instruction pipeline, which keeps the
 // kernels inside the instruction cache.
 __device__ __noinline__ float2 warp_frame_mfcc(float2 x0, float2 x1, float2 x2, float2 x3, float2 x4, float2 x5, float2 x6,
                                                float2 x7, const FrameTables* __restrict__ ftp, float* scr,
-                                               float floor_db, float* __restrict__ out) {
+                                               float floor_db, float* __restrict__ out, float* __restrict__ lm_out) {
     const int lane = threadIdx.x & 31;
     const FrameTables& ft = *ftp;
     const float2 x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
@@ -287,6 +289,10 @@ __device__ __noinline__ float2 warp_frame_mfcc(float2 x0, float2 x1, float2 x2, 
         mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
         mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
     }
+    if (lm_out) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) __stcg(lm_out + lane + 32 * j, v[j]);
+    }
 #pragma unroll
     for (int j = 0; j < 4; j++) v[j] = fmaxf(v[j], floor_db);
     const float cft = warp_dct20(v, ft, lane);
@@ -296,10 +302,25 @@ __device__ __noinline__ float2 warp_frame_mfcc(float2 x0, float2 x1, float2 x2, 
 }
 
 __device__ __forceinline__ void warp_frame_mfcc(const float2 (&x)[8], const FrameTables& ft, float* scr, int lane,
-                                                float floor_db, float* __restrict__ out, float& fmin_o, float& fmax_o) {
-    const float2 r = warp_frame_mfcc(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], &ft, scr, floor_db, out);
+                                                float floor_db, float* __restrict__ out, float& fmin_o, float& fmax_o,
+                                                float* __restrict__ lm_out = nullptr) {
+    const float2 r = warp_frame_mfcc(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], &ft, scr, floor_db, out, lm_out);
     fmin_o = r.x;
     fmax_o = r.y;
+}
+
+// One warp: a frame's stored log-mel values (warp_frame_mfcc's lm_out) -> its 20 MFCCs under floor_db.  Same
+// arithmetic as the tail of warp_frame_mfcc, so the result is bit-identical to recomputing the frame with the floor.
+__device__ __noinline__ void warp_refloor_mfcc(const float* __restrict__ lm, const FrameTables* __restrict__ ftp,
+                                               float floor_db, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const FrameTables& ft = *ftp;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = fmaxf(__ldcg(lm + lane + 32 * j), floor_db);
+    const float cft = warp_dct20(v, ft, lane);
+    const int k = ft.coef_of_lane[lane];
+    if (k >= 0) out[k] = cft;
 }
 
 __device__ __forceinline__ void init_warp_scratch(float*, int) {}

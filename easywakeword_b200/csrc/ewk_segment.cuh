@@ -28,7 +28,10 @@ struct SegDesc {
     int fmt;               // 0 f32, 1 i16
     int ws_frame_off;      // frame offset into the global workspace (used when frames > smem cap)
     long long frames_off;  // frame offset into frames_out (when requested)
+    long long lm_off;      // frame offset into the log-mel workspace
 };
+
+constexpr int LM_ROW = N_MELS;                 // floats per frame in the log-mel workspace
 
 struct TemplateFeat {
     float mean[N_MFCC];
@@ -185,7 +188,8 @@ __device__ __forceinline__ void load_frame_pairs(const PcmReader& rd, int t, int
 // frames whose min lies below the floor are recomputed with it (none in the common case); mean / std over
 // frames (two-pass, ddof 0).  Returns a shared-memory pointer to mean[20] ++ std[20] (valid until the next call).
 __device__ __forceinline__ float* segment_finish(const PcmReader& rd, int F, const SegSmem& m, float* mf, float* fmn,
-                                                 const float* fmx, float* __restrict__ frames_out, long long frames_off) {
+                                                 const float* fmx, float* __restrict__ frames_out, long long frames_off,
+                                                 const float* __restrict__ lm) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* scr = m.scratch + warp * SCR_WARP;
     // ---- phase B
@@ -202,6 +206,10 @@ __device__ __forceinline__ float* segment_finish(const PcmReader& rd, int F, con
     // ---- phase C
     for (int t = warp; t < F; t += SEG_WARPS) {
         if (!(fmn[t] < floor_db)) continue;                   // warp-uniform: only floored frames are redone
+        if (lm) {                                             // from the frame's stored log-mel values: one DCT
+            warp_refloor_mfcc(lm + (size_t)t * LM_ROW, m.ft, floor_db, mf + (size_t)t * N_MFCC);
+            continue;
+        }
         float2 x[8];
         load_frame_pairs(rd, t, lane, x);
         float mn, mx;
@@ -248,9 +256,11 @@ __device__ __forceinline__ float* segment_finish(const PcmReader& rd, int F, con
 
 // Phases A-D for one segment by the whole CTA.  All threads must call it.
 //   A  every frame -> MFCC without the power_to_db floor, plus the frame's log-mel min / max; B-D: segment_finish
+// lm: this segment's rows of the log-mel workspace ([F][LM_ROW] floats, L2-resident scratch) or null (floored frames
+// are then recomputed from the PCM).
 __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegSmem& m,
                                                    int cap_frames, float* __restrict__ ws,
-                                                   float* __restrict__ frames_out) {
+                                                   float* __restrict__ frames_out, float* __restrict__ lm) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = 1 + sd.len / HOP;
     float* mf = m.mf;
@@ -270,17 +280,19 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
         float2 x[8];
         load_frame_pairs(rd, t, lane, x);
         float mn, mx;
-        warp_frame_mfcc(x, *m.ft, scr, lane, -INFINITY, mf + (size_t)t * N_MFCC, mn, mx);
+        warp_frame_mfcc(x, *m.ft, scr, lane, -INFINITY, mf + (size_t)t * N_MFCC, mn, mx,
+                        lm ? lm + (size_t)t * LM_ROW : nullptr);
         if (lane == 0) { fmn[t] = mn; fmx[t] = mx; }
     }
     __syncthreads();
-    return segment_finish(rd, F, m, mf, fmn, fmx, frames_out, sd.frames_off);
+    return segment_finish(rd, F, m, mf, fmn, fmx, frames_out, sd.frames_off, lm);
 }
 
 // K3, batch form: one CTA per caller-described segment (extract_mfcc / calculate_similarity / matches).
 __global__ void __launch_bounds__(SEG_THREADS, 2)
 segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __restrict__ segs,
                           int cap_frames, float* __restrict__ ws,           // global spill [frames][22]
+                          float* __restrict__ lm_ws,                         // log-mel workspace [frames][128] or null
                           const TemplateFeat* __restrict__ tmpl, int n_tmpl, int tmpl_first,
                           float threshold,
                           float* __restrict__ feat_out,                      // [n_seg][40] or null
@@ -293,7 +305,8 @@ segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __r
     seg_prologue(T, m);
     const int tid = threadIdx.x;
     const SegDesc sd = segs[blockIdx.x];
-    const float* feat = segment_features(sd, m, cap_frames, ws, frames_out);
+    const float* feat = segment_features(sd, m, cap_frames, ws, frames_out,
+                                         lm_ws ? lm_ws + (size_t)sd.lm_off * LM_ROW : nullptr);
     if (feat_out && tid < FEAT) feat_out[(size_t)blockIdx.x * FEAT + tid] = feat[tid];
     if (scores && tid < n_tmpl) {
         const TemplateFeat& tf = tmpl[tmpl_first + tid];

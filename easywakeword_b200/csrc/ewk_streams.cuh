@@ -84,6 +84,7 @@ struct BankView {
     int* ev_count;          // [0] count, [1] dropped
     StreamResult* results;
     double* block_ss;       // [n_streams][NB]: sum of squares of absolute block b = a / 1600 at b % NB (written by K1)
+    float* lm_ws;           // K3 log-mel workspace: [segment_queue CTAs][SEG_SMEM_FRAMES][LM_ROW]
     int n_streams, R, P, fmt, chunk_cap, max_events, NB;
 };
 
@@ -804,7 +805,8 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
         sd.base = (const char*)B.ring + (size_t)e.stream * B.P * esz;
         sd.start = e.seg_start % B.P; sd.ring = B.P; sd.len = e.seg_len; sd.fmt = B.fmt;
         sd.ws_frame_off = 0; sd.frames_off = 0;
-        const float* feat = segment_features(sd, m, SEG_SMEM_FRAMES, nullptr, nullptr);
+        const float* feat = segment_features(sd, m, SEG_SMEM_FRAMES, nullptr, nullptr,
+                                             B.lm_ws ? B.lm_ws + (size_t)blockIdx.x * SEG_SMEM_FRAMES * LM_ROW : nullptr);
         const StreamParams& prm = B.prm[e.stream];
         const int t0 = max(0, prm.template_first);
         const int nt = max(0, min(prm.template_count, n_tmpl_slots - t0));

@@ -122,3 +122,44 @@ def test_batch_of_many_segments_vs_oracle(ctx, word):
             assert bool(matched[i]) == bool(ok)
         mean, std = O.extract_mfcc(seg)
         assert np.linalg.norm(feats[i, :20] - mean) <= 1e-4 * np.linalg.norm(mean)
+
+
+def test_floor_from_stored_logmel_is_bit_identical_to_recompute(ctx, golden_matcher, word, monkeypatch):
+    """K3 floors a frame by re-running the DCT on its stored log-mel row; with EWK_SEG_LM=0 it recomputes the
+    frame from the PCM.  Both must give the same bits (frames, features, scores, queue path included)."""
+    from easywakeword_b200 import _lib
+    from easywakeword_b200.bank import WakeWordBank
+    from easywakeword_b200.synth import stream_batch
+    g = golden_matcher
+    names = [str(n) for n in g["names"]]
+    monkeypatch.setenv("EWK_SEG_LM", "0")
+    plain = _lib.Context(device=0, n_streams=0, max_templates=1)
+    monkeypatch.delenv("EWK_SEG_LM")
+    try:
+        plain.set_template(0, word)
+        ctx.set_template(0, word)
+        for n in names:
+            a = g[f"in_{n}"]
+            m0, s0, f0 = plain.extract_mfcc(a, want_frames=True)
+            m1, s1, f1 = ctx.extract_mfcc(a, want_frames=True)
+            assert np.array_equal(f0, f1) and np.array_equal(m0, m1) and np.array_equal(s0, s1), n
+    finally:
+        plain.close()
+    # queue form (K2 -> K3 on the device rings)
+    pcm16 = stream_batch(900, 8, 20.0, word, zero_gaps=2)
+    events = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("EWK_SEG_LM", flag)
+        bank = WakeWordBank(8, [word], device=0)
+        try:
+            evs = []
+            for b in range(0, pcm16.shape[1], 16000):
+                bank.step(np.ascontiguousarray(pcm16[:, b:b + 16000]))
+                evs.append(bank.poll())
+            events.append(np.concatenate(evs))
+        finally:
+            bank.close()
+    monkeypatch.delenv("EWK_SEG_LM")
+    assert len(events[0]) == len(events[1]) and len(events[0]) > 0
+    for f in events[0].dtype.names:
+        assert np.array_equal(events[0][f], events[1][f], equal_nan=events[0][f].dtype.kind == "f"), f
