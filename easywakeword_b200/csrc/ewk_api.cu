@@ -677,7 +677,7 @@ extern "C" int ewk_poll(ewk_ctx* ctx, ewk_event* out, int cap, int* dropped) {
     if (n > 0) {
         CK(cudaMemcpyAsync(out, B.events, sizeof(EventRec) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    CK(cudaMemsetAsync(B.ev_count, 0, sizeof(int) * 2, ctx->stream));
+    CK(cudaMemsetAsync(B.ev_count, 0, sizeof(int) * 4, ctx->stream));     // count, dropped, K3 work counter, scored watermark
     CK(cudaStreamSynchronize(ctx->stream));
     std::sort(out, out + n, [](const ewk_event& a, const ewk_event& b) {
         if (a.tick != b.tick) return a.tick < b.tick;

@@ -64,6 +64,20 @@ struct PcmReader {
         if (q ? ((size_t)q & 3) : ((size_t)f & 7)) return -1;
         return p;
     }
+    // Same, for frames that start on an ODD buffer position (segments are cut at arbitrary samples): int16 pairs
+    // are assembled from two aligned words (the second reaches one sample past the frame, which must exist),
+    // float pairs from two scalar loads.
+    __device__ __forceinline__ long long odd_base(int f0) const {
+        if (f0 < 0 || f0 + N_FFT > len) return -1;
+        long long p = start + f0;
+        if (ring) { if (p >= ring) p -= ring; if (p + N_FFT > ring) return -1; }
+        if (!(p & 1)) return -1;
+        if (q) {
+            if ((size_t)q & 3) return -1;
+            if (!ring && f0 + N_FFT + 1 > len) return -1;     // rings are even-sized: sample p + 512 is inside
+        }
+        return p;
+    }
 };
 
 // scipy.spatial.distance.cosine + the reference's mixing and rescale (wakeword.py:615-623), in the
@@ -94,23 +108,26 @@ __device__ __forceinline__ float similarity_score(const float* ref_mean, const f
 }
 
 // Dynamic shared memory layout:
-//   FrameTables | scratch[SEG_WARPS*SCR_WARP] | red[64] | mfcc[cap*20] | fmin[cap] | fmax[cap]
+//   FrameTables | scratch[SEG_WARPS*SCR_WARP] | part[SEG_PART] | mfcc[cap*20] | fmin[cap] | fmax[cap]
 constexpr int FR_STRIDE = N_MFCC + 2;          // per-frame record in the global spill: mfcc[20], min, max
+constexpr int SEG_PART = SEG_WARPS * 2 * N_MFCC + 2 * N_MFCC + 32;   // per-warp (mean, M2)[20], feat[40], red[32]
 __host__ __device__ inline size_t seg_smem_bytes(int cap_frames) {
-    return sizeof(FrameTables) + sizeof(float) * ((size_t)SEG_WARPS * SCR_WARP + 64 + (size_t)cap_frames * FR_STRIDE);
+    return sizeof(FrameTables) + sizeof(float) * ((size_t)SEG_WARPS * SCR_WARP + SEG_PART + (size_t)cap_frames * FR_STRIDE);
 }
 
 struct SegSmem {
     FrameTables* ft;
-    float *scratch, *red, *mf, *fmin, *fmax;
+    float *scratch, *part, *feat, *red, *mf, *fmin, *fmax;
 };
 
 __device__ __forceinline__ SegSmem seg_carve(float* smem, int cap_frames) {
     SegSmem m;
     m.ft = reinterpret_cast<FrameTables*>(smem);
     m.scratch = smem + sizeof(FrameTables) / sizeof(float);
-    m.red = m.scratch + SEG_WARPS * SCR_WARP;
-    m.mf = m.red + 64;
+    m.part = m.scratch + SEG_WARPS * SCR_WARP;
+    m.feat = m.part + SEG_WARPS * 2 * N_MFCC;
+    m.red = m.feat + 2 * N_MFCC;
+    m.mf = m.part + SEG_PART;
     m.fmin = m.mf + (size_t)cap_frames * N_MFCC;
     m.fmax = m.fmin + cap_frames;
     return m;
@@ -139,6 +156,22 @@ __device__ __forceinline__ void load_frame_pairs_at(const PcmReader& rd, int f0,
             const float2* w = reinterpret_cast<const float2*>(rd.f + base);
 #pragma unroll
             for (int a = 0; a < 8; a++) x[a] = __ldg(w + lane + 32 * a);
+        }
+        return;
+    }
+    const long long ob = rd.odd_base(f0);
+    if (ob >= 0) {
+        if (rd.q) {
+            const unsigned* w = reinterpret_cast<const unsigned*>(rd.q + (ob - 1));
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                const unsigned lo = __ldg(w + lane + 32 * a), hi = __ldg(w + lane + 32 * a + 1);
+                x[a] = make_float2((float)((int)lo >> 16) * (1.0f / 32768.0f), (float)(short)(hi & 0xffff) * (1.0f / 32768.0f));
+            }
+        } else {
+            const float* w = rd.f + ob + 2 * lane;
+#pragma unroll
+            for (int a = 0; a < 8; a++) x[a] = make_float2(__ldg(w + 64 * a), __ldg(w + 64 * a + 1));
         }
         return;
     }
@@ -183,81 +216,16 @@ __device__ __forceinline__ void load_frame_pairs(const PcmReader& rd, int t, int
     load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
 }
 
-// Phases B-D for one segment whose un-floored MFCC rows (mf[F][20]) and per-frame log-mel min / max are in
-// place: block max -> floor = max - 80 (librosa.power_to_db(top_db=80) couples all frames of a segment); only
-// frames whose min lies below the floor are recomputed with it (none in the common case); mean / std over
-// frames (two-pass, ddof 0).  Returns a shared-memory pointer to mean[20] ++ std[20] (valid until the next call).
-__device__ __forceinline__ float* segment_finish(const PcmReader& rd, int F, const SegSmem& m, float* mf, float* fmn,
-                                                 const float* fmx, float* __restrict__ frames_out, long long frames_off,
-                                                 const float* __restrict__ lm) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* scr = m.scratch + warp * SCR_WARP;
-    // ---- phase B
-    float vmax = -INFINITY;
-    for (int t = tid; t < F; t += SEG_THREADS) vmax = fmaxf(vmax, fmx[t]);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
-    if (lane == 0) m.red[warp] = vmax;
-    __syncthreads();
-    float gmax = m.red[0];
-#pragma unroll
-    for (int w = 1; w < SEG_WARPS; w++) gmax = fmaxf(gmax, m.red[w]);
-    const float floor_db = gmax - 80.0f;                      // librosa.power_to_db(top_db=80)
-    // ---- phase C
-    for (int t = warp; t < F; t += SEG_WARPS) {
-        if (!(fmn[t] < floor_db)) continue;                   // warp-uniform: only floored frames are redone
-        if (lm) {                                             // from the frame's stored log-mel values: one DCT
-            warp_refloor_mfcc(lm + (size_t)t * LM_ROW, m.ft, floor_db, mf + (size_t)t * N_MFCC);
-            continue;
-        }
-        float2 x[8];
-        load_frame_pairs(rd, t, lane, x);
-        float mn, mx;
-        warp_frame_mfcc(x, *m.ft, scr, lane, floor_db, mf + (size_t)t * N_MFCC, mn, mx);
-    }
-    __syncthreads();
-    if (frames_out)
-        for (int i = tid; i < F * N_MFCC; i += SEG_THREADS) frames_out[frames_off * N_MFCC + i] = mf[i];
-
-    // ---- phase D: mean / std over frames; thread = (slice of frames, coefficient)
-    constexpr int SL = 12;                       // 12 * 20 = 240 active threads
-    float* part = m.scratch;                     // [SL][20], the FFT scratch is free now
-    float* feat = m.scratch + SL * N_MFCC;       // mean[20] ++ std[20]
-    const int k = tid % N_MFCC, sl = tid / N_MFCC;
-    if (sl < SL) {
-        float s = 0.f;
-        for (int t = sl; t < F; t += SL) s += mf[(size_t)t * N_MFCC + k];
-        part[sl * N_MFCC + k] = s;
-    }
-    __syncthreads();
-    if (tid < N_MFCC) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < SL; i++) s += part[i * N_MFCC + tid];
-        feat[tid] = s / (float)F;
-    }
-    __syncthreads();
-    if (sl < SL) {
-        const float mu = feat[k];
-        float s = 0.f;
-        for (int t = sl; t < F; t += SL) { const float d = mf[(size_t)t * N_MFCC + k] - mu; s = fmaf(d, d, s); }
-        part[sl * N_MFCC + k] = s;
-    }
-    __syncthreads();
-    if (tid < N_MFCC) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < SL; i++) s += part[i * N_MFCC + tid];
-        feat[N_MFCC + tid] = sqrtf(s / (float)F);
-    }
-    __syncthreads();
-    return feat;
-}
-
-// Phases A-D for one segment by the whole CTA.  All threads must call it.
-//   A  every frame -> MFCC without the power_to_db floor, plus the frame's log-mel min / max; B-D: segment_finish
-// lm: this segment's rows of the log-mel workspace ([F][LM_ROW] floats, L2-resident scratch) or null (floored frames
-// are then recomputed from the PCM).
+// One segment by the whole CTA (all threads must call it); returns a shared-memory pointer to mean[20] ++ std[20]
+// (valid until the next call).  Warp w owns frames w, w + 16, ...:
+//   A  every frame -> MFCC without the power_to_db floor, plus the frame's log-mel min / max          | barrier
+//   B  floor = (max over frames of the log-mel max) - 80 (librosa.power_to_db(top_db=80) couples all frames of a
+//      segment); every warp reduces the F maxima itself (F is small; long inputs use a block reduction)
+//   C  the warp's own frames whose min lies below the floor are redone with it (none in the common case): from the
+//      stored log-mel row (lm, one DCT) or, without the workspace, from the PCM
+//   D  mean / std over frames (ddof 0): two-pass mean and M2 over the warp's own frames                | barrier
+//      then one warp pools the 16 partials (Chan et al.), in fixed order                               | barrier
+// lm: this segment's rows of the log-mel workspace ([F][LM_ROW] floats, L2-resident scratch) or null.
 __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegSmem& m,
                                                    int cap_frames, float* __restrict__ ws,
                                                    float* __restrict__ frames_out, float* __restrict__ lm) {
@@ -276,6 +244,7 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
     rd.q = sd.fmt == 1 ? (const short*)sd.base : nullptr;
     rd.ring = sd.ring; rd.len = sd.len; rd.start = sd.start;
     float* scr = m.scratch + warp * SCR_WARP;
+    // ---- A
     for (int t = warp; t < F; t += SEG_WARPS) {
         float2 x[8];
         load_frame_pairs(rd, t, lane, x);
@@ -285,7 +254,67 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
         if (lane == 0) { fmn[t] = mn; fmx[t] = mx; }
     }
     __syncthreads();
-    return segment_finish(rd, F, m, mf, fmn, fmx, frames_out, sd.frames_off, lm);
+    // ---- B
+    float vmax = -INFINITY;
+    if (F <= 64 * 32) {
+        for (int t = lane; t < F; t += 32) vmax = fmaxf(vmax, fmx[t]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
+    } else {
+        for (int t = tid; t < F; t += SEG_THREADS) vmax = fmaxf(vmax, fmx[t]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
+        if (lane == 0) m.red[warp] = vmax;
+        __syncthreads();
+        vmax = m.red[0];
+#pragma unroll
+        for (int w = 1; w < SEG_WARPS; w++) vmax = fmaxf(vmax, m.red[w]);
+    }
+    const float floor_db = vmax - 80.0f;                      // librosa.power_to_db(top_db=80)
+    // ---- C + D over the warp's own frames
+    float sum = 0.f;
+    int nw = 0;
+    for (int t = warp; t < F; t += SEG_WARPS, nw++) {
+        if (fmn[t] < floor_db) {                              // warp-uniform
+            if (lm) warp_refloor_mfcc(lm + (size_t)t * LM_ROW, m.ft, floor_db, mf + (size_t)t * N_MFCC);
+            else {
+                float2 x[8];
+                load_frame_pairs(rd, t, lane, x);
+                float mn, mx;
+                warp_frame_mfcc(x, *m.ft, scr, lane, floor_db, mf + (size_t)t * N_MFCC, mn, mx);
+            }
+            __syncwarp();
+        }
+        if (lane < N_MFCC) {
+            const float v = mf[(size_t)t * N_MFCC + lane];
+            sum += v;
+            if (frames_out) frames_out[(sd.frames_off + t) * N_MFCC + lane] = v;
+        }
+    }
+    if (lane < N_MFCC) {
+        const float mu = nw ? sum / (float)nw : 0.f;
+        float m2 = 0.f;
+        for (int t = warp; t < F; t += SEG_WARPS) { const float d = mf[(size_t)t * N_MFCC + lane] - mu; m2 = fmaf(d, d, m2); }
+        m.part[warp * 2 * N_MFCC + lane] = mu;
+        m.part[warp * 2 * N_MFCC + N_MFCC + lane] = m2;
+    }
+    __syncthreads();
+    if (tid < N_MFCC) {
+        float n = 0.f, mean = 0.f, M2 = 0.f;
+#pragma unroll 1
+        for (int w = 0; w < SEG_WARPS; w++) {
+            if (w >= F) break;
+            const float cw = (float)((F - w + SEG_WARPS - 1) / SEG_WARPS);
+            const float delta = m.part[w * 2 * N_MFCC + tid] - mean, nn = n + cw;
+            mean = fmaf(delta, cw / nn, mean);
+            M2 += m.part[w * 2 * N_MFCC + N_MFCC + tid] + delta * delta * (n * cw / nn);
+            n = nn;
+        }
+        m.feat[tid] = mean;
+        m.feat[N_MFCC + tid] = sqrtf(M2 / (float)F);
+    }
+    __syncthreads();
+    return m.feat;
 }
 
 // K3, batch form: one CTA per caller-described segment (extract_mfcc / calculate_similarity / matches).

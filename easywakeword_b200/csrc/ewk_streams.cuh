@@ -81,7 +81,7 @@ struct BankView {
     StreamParams* prm;
     double* chunk_ms;       // [n_streams][chunk_cap] mean square per storage-order chunk
     EventRec* events;
-    int* ev_count;          // [0] count, [1] dropped
+    int* ev_count;          // [0] count, [1] dropped, [2] K3 work counter, [3] events below this index are scored, [4] K3 CTAs done
     StreamResult* results;
     double* block_ss;       // [n_streams][NB]: sum of squares of absolute block b = a / 1600 at b % NB (written by K1)
     float* lm_ws;           // K3 log-mel workspace: [segment_queue CTAs][SEG_SMEM_FRAMES][LM_ROW]
@@ -789,24 +789,39 @@ segment_prepare_kernel(BankView B, const PrepDesc* __restrict__ d, float* __rest
 // ------------------------------------------------------------------------------------ K3 (queue form)
 // Persistent CTAs drain the segments K2 queued: PCM straight from the stream's device ring ->
 // fused MFCC + template match -> score written back into the event record and the per-stream result.
+// Scheduling: segments differ in length (0.3 .. 3 s) and there are only a few per CTA, so CTAs take them
+// dynamically — first index = watermark + blockIdx.x, then an atomic counter (ev_count[2]) — which bounds the
+// tail by one segment instead of a static share.  Events below the watermark ev_count[3] were scored by earlier
+// launches and are not visited again; the last CTA to finish advances it and zeroes the counters.
+
 __global__ void __launch_bounds__(SEG_THREADS, 2)
 segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, int n_tmpl_slots) {
     extern __shared__ __align__(16) float smem[];
     const SegSmem m = seg_carve(smem, SEG_SMEM_FRAMES);
-    seg_prologue(T, m);
     __shared__ float sc_s[EWK_MAX_TEMPLATES];
+    __shared__ int next_s;
     const int tid = threadIdx.x;
     const int n = min(B.ev_count[0], B.max_events);
+    const int lo = min(B.ev_count[3], n);
+    int r = lo + blockIdx.x;
+    if (r < n) seg_prologue(T, m);                                       // tables; ends with __syncthreads()
     const size_t esz = B.fmt == 1 ? 2 : 4;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    float* lm = B.lm_ws ? B.lm_ws + (size_t)blockIdx.x * SEG_SMEM_FRAMES * LM_ROW : nullptr;
+    while (r < n) {
+        const int i = r;
         const EventRec e = B.events[i];
-        if (e.kind != EV_PENDING) continue;                             // uniform across the CTA
+        if (tid == 0) next_s = lo + gridDim.x + atomicAdd(B.ev_count + 2, 1);
+        if (e.kind != EV_PENDING) {                                     // uniform across the CTA
+            __syncthreads();
+            r = next_s;
+            __syncthreads();
+            continue;
+        }
         SegDesc sd;
         sd.base = (const char*)B.ring + (size_t)e.stream * B.P * esz;
         sd.start = e.seg_start % B.P; sd.ring = B.P; sd.len = e.seg_len; sd.fmt = B.fmt;
-        sd.ws_frame_off = 0; sd.frames_off = 0;
-        const float* feat = segment_features(sd, m, SEG_SMEM_FRAMES, nullptr, nullptr,
-                                             B.lm_ws ? B.lm_ws + (size_t)blockIdx.x * SEG_SMEM_FRAMES * LM_ROW : nullptr);
+        sd.ws_frame_off = 0; sd.frames_off = 0; sd.lm_off = 0;
+        const float* feat = segment_features(sd, m, SEG_SMEM_FRAMES, nullptr, nullptr, lm);
         const StreamParams& prm = B.prm[e.stream];
         const int t0 = max(0, prm.template_first);
         const int nt = max(0, min(prm.template_count, n_tmpl_slots - t0));
@@ -824,12 +839,21 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
             const int ok = best >= prm.similarity_threshold ? 1 : 0;
             EventRec* o = B.events + i;
             o->score = best; o->tmpl = arg; o->matched = ok; o->kind = EV_SCORED;
-            StreamResult r = B.results[e.stream];
-            r.score = best;
-            r.flags = (r.flags & ~1u) | (unsigned)ok;
-            B.results[e.stream] = r;
+            StreamResult res = B.results[e.stream];
+            res.score = best;
+            res.flags = (res.flags & ~1u) | (unsigned)ok;
+            B.results[e.stream] = res;
         }
+        r = next_s;
         __syncthreads();
+    }
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(B.ev_count + 4, 1) == (int)gridDim.x - 1) {       // every other CTA has read the counters
+            B.ev_count[3] = n;
+            B.ev_count[2] = 0;
+            B.ev_count[4] = 0;
+        }
     }
 }
 
