@@ -56,6 +56,7 @@ def load():
         "ewk_clear_template": (C.c_int, [vp, i32]),
         "ewk_similarity_batch": (C.c_int, [vp, i32, vp, i32, i32, _p(i64), _p(i64), i32, C.c_float, f32p,
                                            _p(C.c_uint8), f32p]),
+        "ewk_analyze_templates": (C.c_int, [vp, f32p, i32, _p(i64), _p(i64), i32, vp, f32p, i64]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -180,8 +181,34 @@ class Context:
                                                f32ptr(feats) if want_features else None))
         return (scores, matched.astype(bool), feats) if want_features else (scores, matched.astype(bool))
 
+    def analyze_templates(self, audios, want_rms=False):
+        """Batched WakeWord._analyze_reference_audio_duration (wakeword.py:872-893) on the device (K6).
+        audios: sequence of float32 16 kHz arrays.  -> structured array (VAD_DTYPE), one row per template
+        [, list of per-template frame-RMS arrays]."""
+        audios = [np.ascontiguousarray(a, dtype=np.float32).reshape(-1) for a in audios]
+        n = len(audios)
+        out = np.zeros(n, dtype=VAD_DTYPE)
+        if n == 0:
+            return (out, []) if want_rms else out
+        lens = np.array([len(a) for a in audios], np.int64)
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+        pcm = np.concatenate(audios) if lens.sum() else np.zeros(1, np.float32)
+        frames = 1 + lens // 160
+        rms = np.empty(int(frames.sum()), np.float32) if want_rms else None
+        self._ck(self.lib.ewk_analyze_templates(self.h, f32ptr(pcm), HOST, i64ptr(offs), i64ptr(lens), n,
+                                                out.ctypes.data, f32ptr(rms) if want_rms else None,
+                                                len(rms) if want_rms else 0))
+        if want_rms:
+            cuts = np.cumsum(frames)[:-1]
+            return out, np.split(rms, cuts)
+        return out
+
     def synchronize(self):
         self._ck(self.lib.ewk_synchronize(self.h))
+
+
+VAD_DTYPE = np.dtype([("duration_s", "<f8"), ("max_rms", "<f4"), ("threshold", "<f4"), ("first_frame", "<i4"),
+                      ("last_frame", "<i4"), ("n_frames", "<i4"), ("voiced", "<i4")])      # ewk_vad_result
 
 
 # ------------------------------------------------------------------------------------------

@@ -15,7 +15,7 @@ from typing import Callable, Iterable, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from .wakeword import WakeWord, analyze_reference_audio_duration, load_wav_16k
+from .wakeword import WakeWord, load_wav_16k
 
 TICK_SAMPLES = 1600
 EV_TIMEOUT, EV_SCORED = _lib.EV_TIMEOUT, _lib.EV_SCORED
@@ -58,9 +58,12 @@ class WakeWordBank:
                 np.ascontiguousarray(t, dtype=np.float32)
             self.ctx.set_template(slot, audio)
             self.templates.append(audio)
+        # voice-activity duration of every template on the device (K6); the bank's default timing follows the first
+        # template, as the reference's single-template WakeWord does (tests/test_wakeword_simulated.py:687-775)
+        self.template_vad = self.ctx.analyze_templates(self.templates)
         if speech_duration_min is None:
-            d = analyze_reference_audio_duration(self.templates[0])
-            speech_duration_min = float(d) if d is not None else 0.3
+            d = float(self.template_vad["duration_s"][0]) if self.template_vad["voiced"][0] else None
+            speech_duration_min = d if d is not None else 0.3
             if speech_duration_max is None:
                 speech_duration_max = 2.0 * speech_duration_min if d is not None else 2.0
         elif speech_duration_max is None:

@@ -342,6 +342,48 @@ extern "C" int ewk_similarity_batch(ewk_ctx* ctx, int slot, const void* pcm, int
     return EWK_OK;
 }
 
+extern "C" int ewk_analyze_templates(ewk_ctx* ctx, const float* pcm, int where, const int64_t* offsets,
+                                     const int64_t* lens, int n, ewk_vad_result* out, float* rms_out, int64_t rms_cap) {
+    static_assert(sizeof(ewk_vad_result) == sizeof(VadResult) && sizeof(VadResult) == 32, "ewk_vad_result layout");
+    if (!ctx) return EWK_ERR_ARG;
+    if (n == 0) return EWK_OK;
+    if (!pcm || !offsets || !lens || n < 0 || !out) { ctx->fail("ewk_analyze_templates: bad arguments"); return EWK_ERR_ARG; }
+    int64_t extent = 0, frames = 0;
+    std::vector<VadDesc> vd(n);
+    for (int i = 0; i < n; i++) {
+        if (offsets[i] < 0 || lens[i] < 0 || lens[i] > (int64_t)1 << 32) {
+            ctx->fail("ewk_analyze_templates: template %d has offset %lld len %lld", i, (long long)offsets[i], (long long)lens[i]);
+            return EWK_ERR_ARG;
+        }
+        extent = std::max(extent, offsets[i] + lens[i]);
+        vd[i].start = offsets[i]; vd[i].len = lens[i]; vd[i].rms_off = frames;
+        frames += 1 + lens[i] / VAD_HOP;
+    }
+    if (rms_out && rms_cap < frames) { ctx->fail("ewk_analyze_templates: rms_cap %lld < %lld frames", (long long)rms_cap, (long long)frames); return EWK_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    const float* d_pcm = pcm;
+    if (where == EWK_HOST) {
+        CK(ctx->b_pcm.ensure(sizeof(float) * (size_t)std::max<int64_t>(extent, 1)));
+        CK(cudaMemcpyAsync(ctx->b_pcm.p, pcm, sizeof(float) * (size_t)extent, cudaMemcpyHostToDevice, ctx->stream));
+        d_pcm = (const float*)ctx->b_pcm.p;
+    }
+    for (int i = 0; i < n; i++) vd[i].base = d_pcm;
+    CK(ctx->b_desc.ensure(sizeof(VadDesc) * (size_t)n));
+    CK(cudaMemcpyAsync(ctx->b_desc.p, vd.data(), sizeof(VadDesc) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->b_feat.ensure(sizeof(VadResult) * (size_t)n));
+    CK(ctx->b_frames.ensure(sizeof(float) * (size_t)frames));
+    cudaEvent_t pe = ctx->prof_begin(3);
+    template_vad_kernel<<<n, VAD_THREADS, 0, ctx->stream>>>((const VadDesc*)ctx->b_desc.p, (VadResult*)ctx->b_feat.p,
+                                                            (float*)ctx->b_frames.p);
+    ctx->prof_end(pe, 3);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, ctx->b_feat.p, sizeof(VadResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rms_out) CK(cudaMemcpyAsync(rms_out, ctx->b_frames.p, sizeof(float) * (size_t)frames, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EWK_OK;
+}
+
 // ==========================================================================================
 // stream bank
 // ==========================================================================================

@@ -9,6 +9,7 @@
 #include "ewk_segment.cuh"
 #include "ewk_streams.cuh"
 #include "ewk_dense.cuh"
+#include "ewk_vad.cuh"
 #include "ewk_tables.hpp"
 
 #define EWK_MAX_TEMPLATES 64

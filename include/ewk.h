@@ -137,6 +137,14 @@ typedef struct ewk_stream_result {  /* dense per-stream record, 8 bytes: what mu
                                        ewk_tick | bits 8..31 events so far                               */
 } ewk_stream_result;
 
+typedef struct ewk_vad_result {     /* template voice-activity analysis, 32 bytes                          */
+    double duration_s;              /* max((last - first) * 160 / 16000, 0.2); 0 when voiced == 0         */
+    float max_rms, threshold;       /* max frame RMS and max_rms * 0.1 (float32)                          */
+    int32_t first_frame, last_frame;/* first / last frame with rms > threshold (-1 when none)             */
+    int32_t n_frames;               /* 1 + len / 160                                                      */
+    int32_t voiced;                 /* 0: no frame above the threshold (the reference returns None)       */
+} ewk_vad_result;
+
 /* defaults of the reference (wakeword.py:31-48, 408-409, 676) with audio-clock ticks */
 int ewk_default_stream_params(ewk_stream_params* out);
 /* stream == -1 applies to every stream. */
@@ -170,6 +178,15 @@ int ewk_read_segment(ewk_ctx* ctx, int stream, int64_t seg_start, int64_t seg_le
  * already overwritten in its ring. */
 int ewk_prepare_segments(ewk_ctx* ctx, int n_seg, const int32_t* streams, const int64_t* starts, const int64_t* lens,
                          const int64_t* out_offsets, float* out, int64_t out_len, int where);
+/* Template analysis, batched: WakeWord._analyze_reference_audio_duration
+ * (wakeword.py:872-893) for n templates at once — librosa.feature.rms with 25 ms frames every 10 ms (zero-padded
+ * centring), frames above 0.1 * max RMS, first-to-last span, floor 0.2 s.  Template i is the float32 samples
+ * pcm[offsets[i] : offsets[i] + lens[i]] (16 kHz; `where` says host or device).  rms_out (nullable, host) receives
+ * the frame RMS values of all templates back to back (n_frames each; rms_cap = its capacity in floats).  The
+ * caller derives speech_duration_min/max from duration_s as the reference's tests pin it
+ * (tests/test_wakeword_simulated.py:687-775: min = duration or 0.3, max = 2 * min or 2.0). */
+int ewk_analyze_templates(ewk_ctx* ctx, const float* pcm, int where, const int64_t* offsets, const int64_t* lens,
+                          int n, ewk_vad_result* out, float* rms_out, int64_t rms_cap);
 /* Dense per-hop scoring (usage shape of examples/tune_threshold.py:86-116 at hop
  * granularity): for every stream, every hop h in [hop0, hop0 + n_hops) (hop h <-> 160*h samples pushed)
  * and every template slot k in [template_first, template_first + template_count), the value

@@ -179,6 +179,57 @@ def gen_dense(mod, word):
     return {k: (float(np.nanmin(v)), float(np.nanmax(v))) for k, v in out.items() if k.endswith("_scores")}
 
 
+def gen_vad(mod, word):
+    """WakeWord._analyze_reference_audio_duration (wakeword.py:854-898), the reference's own method run on PCM16
+    WAV files (the only template format its loader is given), plus librosa.feature.rms frame values through
+    the shim.  Stored: the int16 samples of every case, the returned duration (NaN for None) and the frame RMS."""
+    import tempfile
+    import types
+    import wave
+
+    import librosa  # shim
+
+    def i16(x):
+        return np.clip(np.rint(np.asarray(x, np.float64) * 32767.0), -32768, 32767).astype(np.int16)
+
+    rng = np.random.default_rng(11)
+    cases = {
+        "word": np.rint(word.astype(np.float64) * 32768.0).astype(np.int16),
+        "zeros_word_zeros": i16(np.concatenate([np.zeros(3000), word, np.zeros(2000)])),
+        "speech_like": i16(synth.speech_like(1.0)),
+        "sine440": i16(synth.sine(440)),
+        "noise": i16(rng.standard_normal(16000) * 0.05),
+        "quiet_then_burst": i16(np.concatenate([rng.standard_normal(8000) * 0.001, rng.standard_normal(4000) * 0.2,
+                                                rng.standard_normal(6000) * 0.001])),
+        "all_zeros": np.zeros(8000, np.int16),
+        "tiny_100": i16(rng.standard_normal(100) * 0.1),
+        "short_click": i16(np.concatenate([np.zeros(4000), [0.9, -0.9, 0.9], np.zeros(4000)])),
+        "synth_word_1": i16(synth.synthetic_word(seed=1, duration=0.45)),
+        "synth_word_2": i16(synth.synthetic_word(seed=2, duration=1.3)),
+        "word_in_noise": i16(np.concatenate([rng.standard_normal(5000) * 0.004, 0.8 * word + rng.standard_normal(len(word)) * 0.004,
+                                             rng.standard_normal(7000) * 0.004])),
+        "two_bursts": i16(np.concatenate([np.zeros(1600), rng.standard_normal(3200) * 0.3, np.zeros(6400),
+                                          rng.standard_normal(1600) * 0.3, np.zeros(3200)])),
+    }
+    out, summary = {"names": np.array(list(cases))}, {}
+    with tempfile.TemporaryDirectory() as td:
+        for name, pcm in cases.items():
+            path = os.path.join(td, name + ".wav")
+            with wave.open(path, "wb") as w:
+                w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm.tobytes())
+            stub = types.SimpleNamespace(wavword=path, _log=lambda *a, **k: None)
+            dur = mod.WakeWord._analyze_reference_audio_duration(stub)
+            audio, sr = librosa.load(path, sr=None)
+            assert sr == 16000 and np.array_equal(audio, pcm.astype(np.float32) / np.float32(32768.0))
+            rms = librosa.feature.rms(y=audio, frame_length=400, hop_length=160)[0]
+            out[f"pcm_{name}"] = pcm
+            out[f"duration_{name}"] = np.float64(np.nan if dur is None else dur)
+            out[f"rms_{name}"] = rms.astype(np.float32)
+            summary[name] = None if dur is None else float(dur)
+    np.savez_compressed(os.path.join(GOLDEN, "vad.npz"), **out)
+    return summary
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     mod = H.import_reference()
@@ -204,6 +255,7 @@ def main():
     manifest["matcher_scores_vs_word"] = gen_matcher(mod, word)
     manifest["detect"] = gen_detect(word)
     manifest["dense"] = gen_dense(mod, word)
+    manifest["vad_durations"] = gen_vad(mod, word)
     with open(os.path.join(GOLDEN, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, default=str)
     print(json.dumps(manifest, indent=1, default=str))

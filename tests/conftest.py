@@ -69,3 +69,8 @@ def golden_detect():
 @pytest.fixture(scope="session")
 def golden_dense():
     return load_golden("dense.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_vad():
+    return load_golden("vad.npz")

@@ -190,3 +190,24 @@ def test_full_mfcc_front_end_against_torchaudio(word):
         assert got.shape == ref.shape, name
         err = np.linalg.norm(got - ref, axis=0) / np.linalg.norm(ref, axis=0)
         assert err.max() < 2e-5, (name, float(err.max()))
+
+
+def test_vad_duration_matches_reference_goldens(golden_vad):
+    """oracle.analyze_reference_audio_duration / librosa_restated.rms and the package's host rule against the
+    values WakeWord._analyze_reference_audio_duration (wakeword.py:854-898) returned for the same WAVs."""
+    from oracle import ewk_oracle as O, librosa_restated as L
+    from easywakeword_b200.wakeword import analyze_reference_audio_duration as host_rule
+    g = golden_vad
+    for name in [str(n) for n in g["names"]]:
+        audio = g[f"pcm_{name}"].astype(np.float32) / np.float32(32768.0)
+        ref = float(g[f"duration_{name}"])
+        for fn in (O.analyze_reference_audio_duration, host_rule):
+            d = fn(audio)
+            if np.isnan(ref):
+                assert d is None, name
+            else:
+                assert d is not None and d == ref, (name, d, ref)
+        rms = L.rms(y=audio, frame_length=400, hop_length=160)[0]
+        assert np.array_equal(rms.astype(np.float32), g[f"rms_{name}"]), name
+        smin, smax = O.auto_speech_durations(audio)
+        assert (smin, smax) == ((0.3, 2.0) if np.isnan(ref) else (ref, 2.0 * ref)), name
