@@ -57,6 +57,9 @@ def load():
         "ewk_similarity_batch": (C.c_int, [vp, i32, vp, i32, i32, _p(i64), _p(i64), i32, C.c_float, f32p,
                                            _p(C.c_uint8), f32p]),
         "ewk_analyze_templates": (C.c_int, [vp, f32p, i32, _p(i64), _p(i64), i32, vp, f32p, i64]),
+        "ewk_resample_info": (C.c_int, [i32, _p(C.c_int32), _p(C.c_int32), _p(C.c_int32)]),
+        "ewk_resample_out_len": (i64, [i64, i32]),
+        "ewk_resample": (C.c_int, [vp, vp, i32, i32, i32, i64, i64, i32, i64, i64, i64, vp, i64, i32]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -203,8 +206,42 @@ class Context:
             return out, np.split(rms, cuts)
         return out
 
+    def resample(self, y, sr_in, *, in_first=0, out_first=0, n_out=None, out_device_ptr=None):
+        """K7: y[rows, n] or y[n] (float32 / int16, host) at sr_in -> float32 at 16 kHz (absolute output samples
+        [out_first, out_first + n_out); default: the one-shot length ceil(n * 16000 / sr_in)).  A device input is
+        (ptr, rows, n, stride) with the dtype given as a 5th element (np.int16 / np.float32)."""
+        if isinstance(y, tuple):
+            ptr, rows, n, stride, dt = y
+            fmt, where_in, one_d = (PCM_I16 if np.dtype(dt) == np.int16 else PCM_F32), DEVICE, False
+        else:
+            y = np.asarray(y)
+            one_d = y.ndim == 1
+            y = np.ascontiguousarray(y.reshape(1, -1) if one_d else y)
+            if y.dtype != np.int16:
+                y = y.astype(np.float32, copy=False)
+            fmt, where_in = (PCM_I16 if y.dtype == np.int16 else PCM_F32), HOST
+            ptr, rows, n, stride = y.ctypes.data, y.shape[0], y.shape[1], y.shape[1]
+        if n_out is None:
+            n_out = max(0, int(self.lib.ewk_resample_out_len(n, int(sr_in))) - out_first)
+        if out_device_ptr is not None:
+            self._ck(self.lib.ewk_resample(self.h, ptr, fmt, where_in, rows, n, stride, int(sr_in), in_first, out_first,
+                                           n_out, out_device_ptr, n_out, DEVICE))
+            return None
+        out = np.empty((rows, n_out), np.float32)
+        self._ck(self.lib.ewk_resample(self.h, ptr, fmt, where_in, rows, n, stride, int(sr_in), in_first, out_first,
+                                       n_out, out.ctypes.data, n_out, HOST))
+        return out[0] if one_d else out
+
     def synchronize(self):
         self._ck(self.lib.ewk_synchronize(self.h))
+
+
+def resample_info(sr_in):
+    """-> (half_width, up, down) of the 16 kHz conversion filter for sr_in, or raises ValueError."""
+    w, up, dn = C.c_int32(), C.c_int32(), C.c_int32()
+    if load().ewk_resample_info(int(sr_in), C.byref(w), C.byref(up), C.byref(dn)) != 0:
+        raise ValueError(f"{sr_in} Hz -> 16000 Hz is not supported")
+    return w.value, up.value, dn.value
 
 
 VAD_DTYPE = np.dtype([("duration_s", "<f8"), ("max_rms", "<f4"), ("threshold", "<f4"), ("first_frame", "<i4"),

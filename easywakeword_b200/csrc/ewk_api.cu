@@ -153,6 +153,9 @@ void ewk_ctx::release() {
     if (own_stream) cudaStreamSynchronize(own_stream);
     release_streams();
     for (DevBuf* b : {&b_pcm, &b_desc, &b_ws, &b_lm, &b_feat, &b_scores, &b_matched, &b_frames, &b_off}) b->free();
+    for (auto& kv : rs_tables) if (kv.second.H) cudaFree(kv.second.H);
+    rs_tables.clear();
+    b_rs_in.free(); b_rs_out.free();
     if (d_tables) cudaFree(d_tables);
     if (d_tmpl) cudaFree(d_tmpl);
     if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
@@ -381,6 +384,91 @@ extern "C" int ewk_analyze_templates(ewk_ctx* ctx, const float* pcm, int where, 
     CK(cudaMemcpyAsync(out, ctx->b_feat.p, sizeof(VadResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     if (rms_out) CK(cudaMemcpyAsync(rms_out, ctx->b_frames.p, sizeof(float) * (size_t)frames, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return EWK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ K7 resampling
+extern "C" int ewk_resample_info(int sr_in, int32_t* half_width, int32_t* up, int32_t* down) {
+    ResampleDesign d;
+    if (sr_in < 1000 || sr_in > 768000 || !rs_design(sr_in, d)) return EWK_ERR_ARG;
+    if (half_width) *half_width = d.W;
+    if (up) *up = d.L;
+    if (down) *down = d.M;
+    return EWK_OK;
+}
+
+extern "C" int64_t ewk_resample_out_len(int64_t n_in, int sr_in) {
+    if (n_in <= 0 || sr_in <= 0) return 0;
+    return (int64_t)std::ceil((double)n_in * RS_TARGET / (double)sr_in);     // librosa.resample: int(np.ceil(n * ratio))
+}
+
+int ewk_ctx::resample_table(int sr_in, const ResampleTable** out) {
+    ewk_ctx* ctx = this;
+    auto it = rs_tables.find(sr_in);
+    if (it == rs_tables.end()) {
+        ResampleTable t;
+        if (sr_in < 1000 || sr_in > 768000 || !rs_design(sr_in, t.d)) {
+            fail("ewk_resample: %d Hz -> 16000 Hz is not supported (needs more than %d filter phases)", sr_in, RS_MAX_PHASES);
+            return EWK_ERR_ARG;
+        }
+        std::vector<float> H;
+        rs_build_table(t.d, H);
+        CK(cudaMalloc(&t.H, sizeof(float) * H.size()));
+        CK(cudaMemcpyAsync(t.H, H.data(), sizeof(float) * H.size(), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        it = rs_tables.emplace(sr_in, t).first;
+    }
+    *out = &it->second;
+    return EWK_OK;
+}
+
+extern "C" int ewk_resample(ewk_ctx* ctx, const void* in, int pcm_format, int where_in, int n_rows, int64_t n_in,
+                            int64_t in_stride, int sr_in, int64_t in_first, int64_t out_first, int64_t n_out, float* out,
+                            int64_t out_stride, int where_out) {
+    if (!ctx) return EWK_ERR_ARG;
+    if (n_rows == 0 || n_out == 0) return EWK_OK;
+    if (!in || !out || n_rows < 0 || n_in < 0 || n_out < 0 || in_stride < n_in || out_stride < n_out || out_first < 0 ||
+        (pcm_format != EWK_PCM_F32 && pcm_format != EWK_PCM_I16) || n_in > (int64_t)1 << 34 || n_out > (int64_t)1 << 34) {
+        ctx->fail("ewk_resample: bad arguments");
+        return EWK_ERR_ARG;
+    }
+    if (sr_in == RS_TARGET) { ctx->fail("ewk_resample: input is already at 16000 Hz"); return EWK_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    const ewk_ctx::ResampleTable* t = nullptr;
+    int rc = ctx->resample_table(sr_in, &t);
+    if (rc) return rc;
+    const size_t esz = pcm_format == EWK_PCM_I16 ? 2 : 4;
+    ResampleArgs A{};
+    A.in = in; A.in_stride = in_stride;
+    if (where_in == EWK_HOST) {
+        CK(ctx->b_rs_in.ensure(esz * (size_t)n_rows * (size_t)std::max<int64_t>(n_in, 1)));
+        if (n_in > 0)
+            CK(cudaMemcpy2DAsync(ctx->b_rs_in.p, esz * (size_t)n_in, in, esz * (size_t)in_stride, esz * (size_t)n_in,
+                                 (size_t)n_rows, cudaMemcpyHostToDevice, ctx->stream));
+        A.in = ctx->b_rs_in.p; A.in_stride = n_in;
+    }
+    A.out = out; A.out_stride = out_stride;
+    if (where_out == EWK_HOST) {
+        CK(ctx->b_rs_out.ensure(sizeof(float) * (size_t)n_rows * (size_t)n_out));
+        A.out = (float*)ctx->b_rs_out.p; A.out_stride = n_out;
+    }
+    A.H = t->H; A.n_in = n_in; A.in_first = in_first; A.out_first = out_first; A.n_out = n_out;
+    A.L = t->d.L; A.M = t->d.M; A.Minv = t->d.Minv; A.W = t->d.W; A.fmt = pcm_format == EWK_PCM_I16 ? 1 : 0;
+    const long long g0 = out_first / A.L, g1 = (out_first + n_out + A.L - 1) / A.L;
+    const long long threads = (g1 - g0) * A.L;
+    const dim3 grid((unsigned)((threads + RS_THREADS - 1) / RS_THREADS), (unsigned)n_rows);
+    if (n_rows > 65535) { ctx->fail("ewk_resample: at most 65535 rows per call"); return EWK_ERR_ARG; }
+    cudaEvent_t pe = ctx->prof_begin(3);
+    if (A.fmt == 1) resample_kernel<short><<<grid, RS_THREADS, 0, ctx->stream>>>(A);
+    else resample_kernel<float><<<grid, RS_THREADS, 0, ctx->stream>>>(A);
+    ctx->prof_end(pe, 3);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (where_out == EWK_HOST) {
+        CK(cudaMemcpy2DAsync(out, sizeof(float) * (size_t)out_stride, ctx->b_rs_out.p, sizeof(float) * (size_t)n_out,
+                             sizeof(float) * (size_t)n_out, (size_t)n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     return EWK_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -10,6 +11,7 @@
 #include "ewk_streams.cuh"
 #include "ewk_dense.cuh"
 #include "ewk_vad.cuh"
+#include "ewk_resample.cuh"
 #include "ewk_tables.hpp"
 
 #define EWK_MAX_TEMPLATES 64
@@ -86,4 +88,9 @@ struct ewk_ctx {
                         float* d_scores, unsigned char* d_matched);
     int queue_grid() const { return sm_count > 0 ? 2 * sm_count : 1; }     // persistent K3 CTAs (2 per SM)
     static constexpr size_t LM_WS_MAX_BYTES = (size_t)4 << 30;
+    // K7 filter tables, one per input rate seen
+    struct ResampleTable { ewk::ResampleDesign d; float* H = nullptr; };
+    std::map<int, ResampleTable> rs_tables;
+    ewk::DevBuf b_rs_in, b_rs_out;
+    int resample_table(int sr_in, const ResampleTable** out);
 };

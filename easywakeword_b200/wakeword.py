@@ -16,7 +16,6 @@ import logging
 import os
 import threading
 import time
-import wave
 from typing import Callable, Dict, Optional, Union
 
 import numpy as np
@@ -52,21 +51,13 @@ def shared_matcher_context(device: int = 0):
         return _shared_ctx
 
 
-def load_wav_16k(path: str, sample_rate: int = 16000) -> np.ndarray:
-    """What ``librosa.load(path, sr=16000)`` yields for the PCM16 WAVs the reference uses
-    (wakeword.py:588): float32 = int16 / 32768, mono mix-down.  Other rates: see SURVEY §8(f) N3."""
-    with wave.open(str(path), "rb") as w:
-        width, sr, ch = w.getsampwidth(), w.getframerate(), w.getnchannels()
-        raw = w.readframes(w.getnframes())
-    if width != 2:
-        raise ValueError(f"{path}: only 16-bit PCM WAV is supported (sample width {width})")
-    y = np.frombuffer(raw, dtype="<i2").astype(np.float32) / np.float32(32768.0)
-    if ch > 1:
-        y = y.reshape(-1, ch).mean(axis=1, dtype=np.float32)
-    if sr != sample_rate:
-        from .resample import resample_to_16k
-        y = resample_to_16k(y, sr, sample_rate)
-    return y
+def load_wav_16k(path: str, sample_rate: int = 16000, *, ctx=None) -> np.ndarray:
+    """What ``librosa.load(path, sr=16000)`` yields (wakeword.py:588): float32 = PCM / full scale, mono
+    mix-down, and — for files at another rate — conversion to 16 kHz on the device (resample.py, K7)."""
+    if sample_rate != 16000:
+        raise ValueError("easywakeword_b200 works at 16000 Hz (SoundBuffer.FREQUENCY)")
+    from .resample import load_16k
+    return load_16k(str(path), ctx=ctx)
 
 
 class WordMatcher:

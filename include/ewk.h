@@ -187,6 +187,24 @@ int ewk_prepare_segments(ewk_ctx* ctx, int n_seg, const int32_t* streams, const 
  * (tests/test_wakeword_simulated.py:687-775: min = duration or 0.3, max = 2 * min or 2.0). */
 int ewk_analyze_templates(ewk_ctx* ctx, const float* pcm, int where, const int64_t* offsets, const int64_t* lens,
                           int n, ewk_vad_result* out, float* rms_out, int64_t rms_cap);
+/* Ingest at other sample rates: conversion to 16 kHz on the device, the step the reference
+ * delegates to librosa.load(sr=16000) / librosa.resample (wakeword.py:588, 866-870; examples/tune_threshold.py:
+ * 33-47; soxr HQ).  The filter meets soxr HQ's published specification (linear phase, pass-band to 0.913 of the
+ * lower Nyquist, stop-band from 1.0, 125 dB) as one Kaiser-windowed-sinc polyphase stage; it is NOT soxr bit for
+ * bit (oracle/resample_restated.py: parity unpinned).  Framing follows librosa.resample: output sample n sits at
+ * input time n * sr_in / 16000, zeros outside the input, no gain rescale, one-shot length ceil(n_in*16000/sr_in).
+ *
+ * ewk_resample computes, for each of n_rows rows, absolute output samples [out_first, out_first + n_out) from
+ * the absolute input samples [in_first, in_first + n_in) it is given (zeros elsewhere): one-shot use passes
+ * in_first = out_first = 0; streaming use passes each chunk with half_width samples of history and emits only
+ * outputs whose half_width samples of look-ahead are present, which reproduces the one-shot result exactly.
+ * in: float32 or int16 (pcm_format), rows in_stride samples apart; out: float32, rows out_stride apart.
+ * Supported rates: those with 16000 / gcd(sr_in, 16000) <= 4096 (every standard rate). */
+int ewk_resample_info(int sr_in, int32_t* half_width, int32_t* up, int32_t* down);
+int64_t ewk_resample_out_len(int64_t n_in, int sr_in);
+int ewk_resample(ewk_ctx* ctx, const void* in, int pcm_format, int where_in, int n_rows, int64_t n_in, int64_t in_stride,
+                 int sr_in, int64_t in_first, int64_t out_first, int64_t n_out, float* out, int64_t out_stride,
+                 int where_out);
 /* Dense per-hop scoring (usage shape of examples/tune_threshold.py:86-116 at hop
  * granularity): for every stream, every hop h in [hop0, hop0 + n_hops) (hop h <-> 160*h samples pushed)
  * and every template slot k in [template_first, template_first + template_count), the value

@@ -211,3 +211,42 @@ def test_vad_duration_matches_reference_goldens(golden_vad):
         assert np.array_equal(rms.astype(np.float32), g[f"rms_{name}"]), name
         smin, smax = O.auto_speech_durations(audio)
         assert (smin, smax) == ((0.3, 2.0) if np.isnan(ref) else (ref, 2.0 * ref)), name
+
+
+# ---- N3: the resampling oracle (parity unpinned vs soxr; arithmetic pinned here)
+@pytest.mark.parametrize("sr", [8000, 22050, 44100, 48000])
+def test_resample_oracle_matches_scipy_polyphase_with_same_filter(sr):
+    """oracle.resample_restated evaluates out[n] = sum_k x[k] g(n M / L - k); scipy.signal.upfirdn(h, x, L, M) with
+    h[i] = g((i - c) / L) is an independent implementation of the same sum."""
+    from scipy import signal
+    from oracle import resample_restated as R
+    rng = np.random.default_rng(sr)
+    x = rng.standard_normal(3000)
+    d = R.design(sr)
+    L, M, W = d["L"], d["M"], d["W"]
+    c = W * L                                               # prototype centre
+    h = R.kernel((np.arange(2 * c + 1) - c) / L, d)
+    full = signal.upfirdn(h, x, up=L, down=1)               # full[i] = sum_k x[k] h[i - k L] = sum_k x[k] g((i - c)/L - k)
+    n_out = R.out_len(len(x), sr)
+    ref = full[c + np.arange(n_out) * M]                    # time n M / L
+    got = R.resample(x, sr, table_dtype=np.float64).astype(np.float64)
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()   # float32 rounding of the oracle's output
+
+
+@pytest.mark.parametrize("sr", [11025, 44100, 48000, 96000])
+def test_resample_oracle_tones(sr):
+    """Pass-band tones come out at unit gain and the right phase (ideal band-limited interpolation), content above
+    8 kHz is rejected by > 120 dB, and the output length is librosa's ceil(n * 16000 / sr)."""
+    from oracle import resample_restated as R
+    n = sr // 2
+    t = np.arange(n) / sr
+    lower = min(sr, 16000)
+    for f in (300.0, 0.45 * lower * 0.9):
+        y = R.resample(np.sin(2 * np.pi * f * t), sr)
+        assert len(y) == int(np.ceil(n * 16000 / sr))
+        to = np.arange(len(y)) / 16000
+        mid = slice(700, len(y) - 700)
+        assert np.abs(y[mid] - np.sin(2 * np.pi * f * to)[mid]).max() < 5e-6
+    if sr > 2 * 9000:
+        y = R.resample(np.sin(2 * np.pi * 9000.0 * t), sr)
+        assert np.abs(y[700:-700]).max() < 1e-6             # < -120 dB
