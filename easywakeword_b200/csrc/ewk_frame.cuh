@@ -7,9 +7,11 @@
 // FFT: the 512 real samples are packed as 256 complex points z[n] = x[2n] + i x[2n+1]; the warp runs
 // a 256-point complex FFT as radix 8 x 8 x 4 with 8 points per lane in registers and two
 // conflict-free shared-memory transposes, then untangles Z[k], Z[256-k] (one shuffle pair per bin)
-// into the 257 real-FFT bins.  Mel: each lane owns four bands (lane + 32 j).  DCT: each lane forms
-// the partial sums of its four bands for all 20 coefficients (80 FMAs, weights as 16-byte shared
-// loads) and a halving shuffle butterfly (21 exchanges) leaves coefficient k in one lane.
+// into the 257 real-FFT bins.  Mel: each lane owns four bands (lane + 32 j).  DCT: the rows of the
+// DCT-II are (anti)symmetric about the middle of the 128 bands, so the bands are folded first
+// (x[b] +- x[127-b], two shuffles); the lower half-warp forms the even coefficients, the upper the odd
+// ones (40 FMAs per lane, weights as ten 16-byte shared loads) and a halving shuffle butterfly
+// (11 exchanges) leaves coefficient k in one lane.
 // Window taps, twiddles, mel weights and the DCT matrix live in shared memory (one copy per CTA) so
 // the kernel stays under ~80 registers and several CTAs fit on an SM.
 #pragma once
@@ -32,7 +34,7 @@ constexpr int MEL_TAPS = MEL_TAPS0 + MEL_TAPS1 + MEL_TAPS2 + MEL_TAPS3;
 constexpr int SCR_PLANE = 320;            // floats per re / im transpose plane (8 rows x 40)
 constexpr int SCR_P = 264;                // power spectrum, 257 bins padded; aliases the re plane (dead by then)
 constexpr int SCR_WARP = 2 * SCR_PLANE;   // floats of scratch per warp (2560 B)
-constexpr int DCT_ROW4 = 7;                // float4 per band row of the shared DCT table (odd: conflict-free)
+constexpr int DCT_LANE4 = 11;              // float4 per lane row of the shared DCT table (40 weights + 4 pad: conflict-free)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float TEN_LOG10_2 = 3.01029995663981195f;   // 10 * log10(2)
 
@@ -59,7 +61,7 @@ struct FrameTables {
     float melp[MEL_TAPS * 32];    // zero-padded mel taps, [tap][lane]
     int mfirst[4 * 32];           // first FFT bin of band lane + 32 j, [j][lane]
     int coef_of_lane[32];         // which MFCC coefficient the lane holds after warp_dct20 (-1: none)
-    float4 dct[N_MELS * DCT_ROW4];     // per band: coefficients 0-9 (+2 pad) | 10-19 (+2 pad) | pad: 7 float4
+    float4 dct[32 * DCT_LANE4];        // per lane: [band slot s < 4][m < 10] = dct(k = 2 m + (lane >> 4), band_s), see warp_dct20
 };
 
 __device__ __forceinline__ void load_frame_tables(FrameTables& ft, const DeviceTables* __restrict__ T, int tid, int nthr) {
@@ -73,15 +75,17 @@ __device__ __forceinline__ void load_frame_tables(FrameTables& ft, const DeviceT
     for (int i = tid; i < MEL_TAPS * 32; i += nthr) ft.melp[i] = T->mel_pad[i];
     for (int i = tid; i < 4 * 32; i += nthr) ft.mfirst[i] = T->mel_first[i];
     float* dd = reinterpret_cast<float*>(ft.dct);
-    for (int i = tid; i < N_MELS * DCT_ROW4 * 4; i += nthr) {
-        const int b = i / (DCT_ROW4 * 4), r = i - b * (DCT_ROW4 * 4);      // r < 28: [half 0: 12][half 1: 12][pad 4]
-        const int half = r / 12, c = r - half * 12;
-        dd[i] = (half < 2 && c < 10) ? T->dct_t[b * N_MFCC + 10 * half + c] : 0.f;
+    for (int i = tid; i < 32 * DCT_LANE4 * 4; i += nthr) {
+        const int lane = i / (DCT_LANE4 * 4), r = i - lane * (DCT_LANE4 * 4);
+        const int sl = r / 10, m = r - sl * 10;                                // band slot, coefficient pair index
+        const int owner = sl < 2 ? lane : (lane ^ 16);                          // slots 2, 3: the partner lane's bands
+        const int b = owner + 32 * (sl & 1);                                    // folded band (< 64)
+        dd[i] = r < 40 ? T->dct_t[b * N_MFCC + 2 * m + (lane >> 4)] : 0.f;
     }
     for (int i = tid; i < 32; i += nthr) {
         const int w = i & 7;
         const int within = w == 0 ? 0 : w == 1 ? 1 : w == 2 ? 2 : w == 4 ? 3 : w == 5 ? 4 : -1;
-        ft.coef_of_lane[i] = within < 0 ? -1 : 10 * ((i >> 4) & 1) + 5 * ((i >> 3) & 1) + within;
+        ft.coef_of_lane[i] = within < 0 ? -1 : 2 * (5 * ((i >> 3) & 1) + within) + ((i >> 4) & 1);
     }
 }
 
@@ -221,27 +225,27 @@ __device__ __forceinline__ void warp_log_mel(const float* __restrict__ P, const 
 // (80 FMAs, 24 16-byte shared loads); a halving shuffle butterfly over the 16 lanes of a half
 // (10 -> 5 -> 3 -> 2 -> 1 values, 11 exchanges) leaves coefficient ft.coef_of_lane[lane] in the lane.
 __device__ __forceinline__ float warp_dct20(const float (&x)[4], const FrameTables& ft, int lane) {
-    float xp[4];
+    // fold: c(k, 127 - b) = (-1)^k c(k, b), so C[k] = sum_{b<64} c(k, b) (x[b] + (-1)^k x[127 - b]).  Band 127 - b of
+    // the lane's bands b = lane, lane + 32 sits in lane 31 - lane (registers 3, 2).
+    const float y3 = __shfl_sync(FULL, x[3], 31 - lane), y2 = __shfl_sync(FULL, x[2], 31 - lane);
+    const bool half = lane & 16;                              // lower half-warp: even k, upper: odd k
+    const float s0 = x[0] + y3, d0 = x[0] - y3, s1 = x[1] + y2, d1 = x[1] - y2;
+    float v[4];
+    v[0] = half ? d0 : s0;
+    v[1] = half ? d1 : s1;
+    v[2] = __shfl_xor_sync(FULL, half ? s0 : d0, 16);         // the partner's folded values of MY parity
+    v[3] = __shfl_xor_sync(FULL, half ? s1 : d1, 16);
+    float acc[10];
 #pragma unroll
-    for (int j = 0; j < 4; j++) xp[j] = __shfl_xor_sync(FULL, x[j], 16);
-    const int half = lane >> 4;
-    float acc[12];
+    for (int m = 0; m < 10; m++) acc[m] = 0.f;
+    const float4* row = ft.dct + lane * DCT_LANE4;
 #pragma unroll
-    for (int k = 0; k < 12; k++) acc[k] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const float4* r0 = ft.dct + (lane + 32 * j) * DCT_ROW4 + 3 * half;
-        const float4* r1 = ft.dct + ((lane ^ 16) + 32 * j) * DCT_ROW4 + 3 * half;
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            const float4 w0 = r0[q], w1 = r1[q];
-            acc[4 * q + 0] = fmaf(w0.x, x[j], fmaf(w1.x, xp[j], acc[4 * q + 0]));
-            acc[4 * q + 1] = fmaf(w0.y, x[j], fmaf(w1.y, xp[j], acc[4 * q + 1]));
-            if (q < 2) {
-                acc[4 * q + 2] = fmaf(w0.z, x[j], fmaf(w1.z, xp[j], acc[4 * q + 2]));
-                acc[4 * q + 3] = fmaf(w0.w, x[j], fmaf(w1.w, xp[j], acc[4 * q + 3]));
-            }
-        }
+    for (int q = 0; q < 10; q++) {
+        const float4 w = row[q];
+        acc[(4 * q + 0) % 10] = fmaf(w.x, v[(4 * q + 0) / 10], acc[(4 * q + 0) % 10]);
+        acc[(4 * q + 1) % 10] = fmaf(w.y, v[(4 * q + 1) / 10], acc[(4 * q + 1) % 10]);
+        acc[(4 * q + 2) % 10] = fmaf(w.z, v[(4 * q + 2) / 10], acc[(4 * q + 2) % 10]);
+        acc[(4 * q + 3) % 10] = fmaf(w.w, v[(4 * q + 3) / 10], acc[(4 * q + 3) % 10]);
     }
     // halving butterfly over lane bits 3..0: 10 -> 5 -> (6) 3 -> (4) 2 -> 1 values per lane
     float a5[6], a3[4], a2[2];
