@@ -390,7 +390,10 @@ def run_ours(args):
                        if world > 1 else "1 GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * STEP_SAMPLES * 2,
-                    "d2h_bytes_per_step": int(8 + ev_per_step * 40), "ms_per_step": ms_e2e / K},
+                    "d2h_bytes_per_step": int(8 + ev_per_step * 40), "ms_per_step": ms_e2e / K,
+                    "h2d_gbs_per_gpu": n * STEP_SAMPLES * 2 / (ms_e2e / K * 1e-3) / 1e9,
+                    "bound": "host->device copy (PCIe): the PCM of a step is 131 MB per GPU and every step pays its own "
+                             "copy; kernels take ~10 % of the step and overlap the next copy"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,

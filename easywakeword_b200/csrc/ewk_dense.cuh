@@ -15,7 +15,12 @@
 //   * floor = (max log-mel over the window's frames) - 80.  Frames are first computed un-floored
 //     together with their log-mel min / max; a window whose min is below its floor recomputes just
 //     the affected frames with the floor ("patches"), everything else is reused.
-//   * mean / std over the F frames (two-pass), cosine vs the template, p^1.5/10.
+//   * mean / std over the F frames, cosine vs the template, p^1.5/10.  Consecutive windows share all but one of
+//     their stream-grid frames, so the statistics are pooled from blocks: (mean, M2) of every aligned block of 8
+//     stream-grid rows is computed once per sub-chunk, and a window combines, in a fixed order, its left edge
+//     frames, the loose rows before the first aligned block, the blocks, the loose rows after the last one and
+//     its right edge frames with the pairwise update of Chan et al. (n, mean, M2) — about 25 items instead of
+//     100 rows, no cancellation, and bit-identical for every way of cutting the request into calls or sub-chunks.
 #pragma once
 #include <climits>
 
@@ -32,7 +37,8 @@ constexpr int DENSE_MAX_F = 224;       // frames per window (templates up to ~2.
 constexpr int DENSE_MIN_L = 640;       // shorter templates would make a frame both left- and right-masked
 constexpr int ROW = N_MFCC + 2;        // mfcc[20], log-mel min, log-mel max
 constexpr int DENSE_KEEP = 224;        // stream-grid rows carried from one call to the next (>= frames of the longest window)
-constexpr int PATCH_CAP = 6;           // floored frames kept per warp before falling back to recomputation
+constexpr int PATCH_CAP = 5;           // per-warp rows recomputed with a floor: 4 edge frames + 1 stream-grid frame
+constexpr int BLK = 8;                 // stream-grid rows per statistics block (aligned at absolute multiples of BLK)
 
 struct DenseTmplDev {
     int L, n, F, t_hi, r, slot;        // r = F - 1 - t_hi right-edge frames
@@ -50,11 +56,13 @@ struct DenseArgs {
     long long* keep_end;               // [n_streams][2]: grid frames [keep_end[2s], keep_end[2s+1]) are stored (0, 0: nothing)
 };
 
+__host__ __device__ inline int dense_nblk(int DG) { return DG / BLK + 2; }     // ring of block statistics
+
 __host__ __device__ inline size_t dense_smem_bytes(int DG, int T) {
     return sizeof(FrameTables) +
            sizeof(float) * ((size_t)DENSE_WARPS * SCR_WARP + (size_t)DG * ROW + (size_t)T * DH * 4 * ROW +
-                            (size_t)DENSE_WARPS * (PATCH_CAP * N_MFCC + 2 * N_MFCC + 16) +
-                            (size_t)DG * (N_MFCC + 1) + 4);
+                            (size_t)DENSE_WARPS * PATCH_CAP * N_MFCC + (size_t)DG * (N_MFCC + 1) + 8 +
+                            (size_t)2 * dense_nblk(DG) * 2 * N_MFCC);
 }
 
 // frame `t` of the window of template `tp` starting at grid index j: pointer to its ROW
@@ -66,6 +74,25 @@ __device__ __forceinline__ const float* dense_row(const float* G, const float* e
     return edge_kh + (2 + t - tp.t_hi - 1) * ROW;
 }
 
+// (mean, M2 = sum of squared deviations) of BLK values, two passes, fixed order
+__device__ __forceinline__ void block_mean_m2(const float (&v)[BLK], float& mu, float& m2) {
+    float sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < BLK; q++) sum += v[q];
+    mu = sum * (1.0f / BLK);
+    m2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < BLK; q++) { const float d = v[q] - mu; m2 = fmaf(d, d, m2); }
+}
+
+// pooled update (Chan, Golub, LeVeque): fold an item (nb values, mean mb, M2 m2b) into the running (n, mean, M2)
+__device__ __forceinline__ void pool_item(float& n, float& mean, float& M2, float nb, float mb, float m2b) {
+    const float nn = n + nb, f = __fdividef(nb, nn), delta = mb - mean;
+    mean = fmaf(delta, f, mean);
+    M2 += fmaf(delta * delta, n * f, m2b);
+    n = nn;
+}
+
 __global__ void __launch_bounds__(DENSE_THREADS, 2)
 dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, DenseArgs A) {
     extern __shared__ __align__(16) float smem[];
@@ -73,12 +100,16 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
     float* scratch = smem + sizeof(FrameTables) / sizeof(float);
     float* G = scratch + DENSE_WARPS * SCR_WARP;                 // [DG][ROW]
     float* edge = G + (size_t)A.DG * ROW;                        // [T][DH][4][ROW]
-    float* wbuf = edge + (size_t)A.T * DH * 4 * ROW;             // per warp: patch[PATCH_CAP][20], feat[40], masks[16]
+    float* wbuf = edge + (size_t)A.T * DH * 4 * ROW;             // per warp: patch[PATCH_CAP][20]
     // alternate ring: rows of G recomputed with ONE floor value (the current one of the stream), tagged per row, so
     // that a floored stream-grid frame is recomputed once per floor value and not once per window that contains it
-    float* G2 = wbuf + (size_t)DENSE_WARPS * (PATCH_CAP * N_MFCC + 2 * N_MFCC + 16);   // [DG][20]
+    float* G2 = wbuf + (size_t)DENSE_WARPS * PATCH_CAP * N_MFCC;                        // [DG][20]
     int* g2tag = reinterpret_cast<int*>(G2 + (size_t)A.DG * N_MFCC);                    // [DG] floor bits of the row
     int* fstar_s = g2tag + A.DG;                                                        // [1] floor bits served by G2
+    // statistics of aligned blocks of BLK stream-grid rows, (mean[20], M2[20]) each, block g / BLK at (g / BLK) % NBLK:
+    // BS[0] over the un-floored rows G, BS[1] over the rows as floored by the stream's current floor (G2 where it applies)
+    const int NBLK = dense_nblk(A.DG);
+    float* BS = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(fstar_s + 4) + 15) & ~(uintptr_t)15);   // [2][NBLK][40]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.x;
@@ -88,9 +119,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
     for (int i = tid; i < A.DG; i += DENSE_THREADS) g2tag[i] = 0x7fc00001;     // matches no floor
     __syncthreads();
 
-    float* patch = wbuf + (size_t)warp * (PATCH_CAP * N_MFCC + 2 * N_MFCC + 16);
-    float* feat = patch + PATCH_CAP * N_MFCC;
-    unsigned* masks = reinterpret_cast<unsigned*>(feat + 2 * N_MFCC);   // [8] floored-frame bit masks, [8] prefix counts
+    float* patch = wbuf + (size_t)warp * PATCH_CAP * N_MFCC;
 
     const size_t esz = B.fmt == 1 ? 2 : 4;
     PcmReader rd;
@@ -212,162 +241,131 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
             __syncthreads();
         }
 
-        // ---- windows of this sub-chunk, one warp per (template, hop)
+        // ---- statistics of the span's aligned blocks (both variants), one warp per block
+        // blocks [b_lo, b_lo + n_blk) lie inside the span; 32-bit ring positions of the first one
+        const long long b_lo = (g_lo + BLK - 1) / BLK;
+        const int n_blk = (int)max(0LL, (g_hi + 1) / BLK - b_lo);
+        const int blk_row_lo = (int)((b_lo * BLK) % A.DG), blk_idx_lo = (int)(b_lo % NBLK);
+        {
+            const int fb = *fstar_s;
+            const float fstar = __int_as_float(fb);
+            for (int i = warp; i < 2 * n_blk; i += DENSE_WARPS) {
+                const int var = i & 1;
+                int r = blk_row_lo + (i >> 1) * BLK; if (r >= A.DG) r -= A.DG;       // n_blk * BLK <= DG
+                int bi = blk_idx_lo + (i >> 1); if (bi >= NBLK) bi -= NBLK;
+                float v[BLK];
+#pragma unroll
+                for (int q = 0; q < BLK; q++) {
+                    const float* src = G + r * ROW;
+                    if (var && src[N_MFCC] < fstar && g2tag[r] == fb) src = G2 + r * N_MFCC;
+                    v[q] = lane < N_MFCC ? src[lane] : 0.f;
+                    r++; if (r >= A.DG) r -= A.DG;
+                }
+                float mu, m2;
+                block_mean_m2(v, mu, m2);
+                float* dst = BS + ((size_t)var * NBLK + (size_t)bi) * 2 * N_MFCC;
+                if (lane < N_MFCC) { dst[lane] = mu; dst[N_MFCC + lane] = m2; }
+            }
+        }
+        __syncthreads();
+
+        // ---- windows of this sub-chunk, one warp per (template, hop): window max -> floor; class of the window
+        //   0: no stream-grid frame of the window is floored            -> block statistics over G
+        //   1: floored, and the floor is the stream's current one (f*)  -> block statistics over G2 | G
+        //   2: floored with another floor: blocks are formed here, floored rows recomputed on the fly
+        // All three give the same bits for the same window: same items, same order, same arithmetic.
         for (int w = warp; w < A.T * nh; w += DENSE_WARPS) {
             const int k = w / nh, hl = w - k * nh;
             const DenseTmplDev tp = A.t[k];
             const long long jl = hs + hl - tp.n;
             float* outp = A.out + ((size_t)s * A.n_hops + (size_t)(hs - A.hop0 + hl)) * A.T + k;
-            if (jl < 0) { if (lane == 0) *outp = __int_as_float(0x7fc00000); continue; }
+            const TemplateFeat& tf = tmpl[tp.slot];
+            if (jl < 0 || !tf.valid) { if (lane == 0) *outp = __int_as_float(0x7fc00000); continue; }
             const int j = (int)(jl % A.DG);                            // ring row base of this window
             const float* ekh = edge + (k * DH + hl) * 4 * ROW;
-            // window max of the frames' log-mel max -> floor (librosa.power_to_db(top_db=80) on this window);
-            // lanes walk the frames 32 at a time and keep their rows' min for the floored-frame test
-            float wmax = -INFINITY;
-            float fmin_c[DENSE_MAX_F / 32];
-#pragma unroll
-            for (int c = 0; c < DENSE_MAX_F / 32; c++) {
-                const int t = c * 32 + lane;
-                fmin_c[c] = INFINITY;
-                if (t < tp.F) {
-                    const float* row = dense_row(G, ekh, tp, A.DG, j, t);
-                    fmin_c[c] = row[N_MFCC];
-                    wmax = fmaxf(wmax, row[N_MFCC + 1]);
-                }
+            float wmax = -INFINITY, rmin = INFINITY;                   // max over all frames, min over the ring frames
+            for (int t = 2 + lane; t <= tp.t_hi; t += 32) {
+                int r = j + t; if (r >= A.DG) r -= A.DG;
+                rmin = fminf(rmin, G[r * ROW + N_MFCC]);
+                wmax = fmaxf(wmax, G[r * ROW + N_MFCC + 1]);
             }
+            const int n_edge = 2 + tp.r;
+            const float emin = lane < n_edge ? ekh[lane * ROW + N_MFCC] : INFINITY;
+            if (lane < n_edge) wmax = fmaxf(wmax, ekh[lane * ROW + N_MFCC + 1]);
 #pragma unroll
-            for (int o = 16; o; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(FULL, wmax, o));
-            const float floor_db = wmax - 80.0f;
-            // frames that the floor changes
-            int n_aff = 0;
-#pragma unroll
-            for (int c = 0; c < DENSE_MAX_F / 32; c++) {
-                const unsigned m = __ballot_sync(FULL, fmin_c[c] < floor_db);
-                if (lane == 0) { masks[c] = m; masks[8 + c] = (unsigned)n_aff; }
-                n_aff += __popc(m);
+            for (int o = 16; o; o >>= 1) {
+                wmax = fmaxf(wmax, __shfl_xor_sync(FULL, wmax, o));
+                rmin = fminf(rmin, __shfl_xor_sync(FULL, rmin, o));
+            }
+            const float floor_db = wmax - 80.0f;                       // librosa.power_to_db(top_db=80) on this window
+            const unsigned emask = __ballot_sync(FULL, emin < floor_db);   // floored edge frames
+            const int cls = !(rmin < floor_db) ? 0 : (__float_as_int(floor_db) == *fstar_s ? 1 : 2);
+            { int pos = hs_pos + 160 * (hl - tp.n); pos %= B.P; if (pos < 0) pos += B.P; rd.start = pos; }
+            rd.len = tp.L;
+            // floored edge frames are recomputed with the floor (window-local PCM view) into patch slots 0..3
+            for (unsigned mm = emask; mm; mm &= mm - 1) {
+                const int e = __ffs(mm) - 1;
+                const int t = e < 2 ? e : tp.t_hi + 1 + (e - 2);
+                float2 x[8];
+                load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
+                float mn, mx;
+                warp_frame_mfcc(x, *ft, scr, lane, floor_db, patch + e * N_MFCC, mn, mx);
             }
             __syncwarp();
-            // G2 serves this window's floored stream-grid frames when its floor is the stream's current one
-            const bool ringp = n_aff && __float_as_int(floor_db) == *fstar_s;
-            if (n_aff) {
-                // recompute the floored frames (window-local PCM view), keep the first PATCH_CAP of them
-                // (ring-patched windows: only their edge frames, into slot = edge index)
-                { int pos = hs_pos + 160 * (hl - tp.n); pos %= B.P; if (pos < 0) pos += B.P; rd.start = pos; }
-                rd.len = tp.L;
-                int slot = 0;
-                if (ringp) {
-                    for (int e = 0; e < 2 + tp.r; e++) {
-                        const int t = e < 2 ? e : tp.t_hi + 1 + (e - 2);
-                        if (!((masks[t >> 5] >> (t & 31)) & 1u)) continue;
-                        float2 x[8];
-                        load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
-                        float mn, mx;
-                        warp_frame_mfcc(x, *ft, scr, lane, floor_db, patch + e * N_MFCC, mn, mx);
-                    }
-                }
-                for (int c = 0; !ringp && c * 32 < tp.F && slot < PATCH_CAP; c++) {
-                    unsigned m = masks[c];
-                    while (m && slot < PATCH_CAP) {
-                        const int t = c * 32 + __ffs(m) - 1;
-                        m &= m - 1;
-                        float2 x[8];
-                        load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
-                        float mn, mx;
-                        warp_frame_mfcc(x, *ft, scr, lane, floor_db, patch + slot * N_MFCC, mn, mx);
-                        slot++;
-                    }
-                }
+            // value of ring frame t (row r) under this window's floor, coefficient = lane
+            auto ring_value = [&](int t, int r) -> float {
+                if (cls == 0 || !(G[r * ROW + N_MFCC] < floor_db)) return lane < N_MFCC ? G[r * ROW + lane] : 0.f;
+                if (cls == 1) return lane < N_MFCC ? G2[r * N_MFCC + lane] : 0.f;
+                float2 x[8];
+                load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
+                float mn, mx;
                 __syncwarp();
+                warp_frame_mfcc(x, *ft, scr, lane, floor_db, patch + 4 * N_MFCC, mn, mx);
+                __syncwarp();
+                return lane < N_MFCC ? patch[4 * N_MFCC + lane] : 0.f;
+            };
+            auto edge_value = [&](int e) -> float {
+                if (lane >= N_MFCC) return 0.f;
+                return ((emask >> e) & 1u) ? patch[e * N_MFCC + lane] : ekh[e * ROW + lane];
+            };
+            // pooled statistics, fixed order: left edges, loose rows, aligned blocks, loose rows, right edges.
+            // Ring frames t = 2 .. t_hi are grid frames jl + t; t0 = first t on a block boundary.
+            float n = 1.f, mean = edge_value(0), M2 = 0.f;
+            pool_item(n, mean, M2, 1.f, edge_value(1), 0.f);
+            const int t0 = min(tp.t_hi + 1, 2 + ((BLK - (((int)(jl & (BLK - 1)) + 2) & (BLK - 1))) & (BLK - 1)));
+            int t = 2, r = j + 2; if (r >= A.DG) r -= A.DG;
+            for (; t < t0; t++) {
+                pool_item(n, mean, M2, 1.f, ring_value(t, r), 0.f);
+                r++; if (r >= A.DG) r -= A.DG;
             }
-            // mean / std over the F frames: lane = (group g3 of 3, coefficient pair c2 of 10); three frames per step
-            const int g3 = lane / 10, c2 = lane - 10 * g3;
-            const bool act = lane < 30;
-            float2 mean = make_float2(0.f, 0.f), var = make_float2(0.f, 0.f);
-            for (int pass = 0; pass < 2; pass++) {
-                float2 acc = make_float2(0.f, 0.f);
-                if (act) {
-                    if (!n_aff) {
-                        // fast path: two left-edge rows, a run of ring rows, the right-edge rows
-                        auto add = [&](const float* row) {
-                            const float2 v = *reinterpret_cast<const float2*>(row + 2 * c2);
-                            if (pass == 0) { acc.x += v.x; acc.y += v.y; }
-                            else { const float dx = v.x - mean.x, dy = v.y - mean.y; acc.x = fmaf(dx, dx, acc.x); acc.y = fmaf(dy, dy, acc.y); }
-                        };
-                        if (g3 < 2) add(ekh + g3 * ROW);                               // t = 0, 1
-                        if (g3 < tp.r) add(ekh + (2 + g3) * ROW);                      // t = t_hi+1 ..
-                        int r = j + 2 + g3; if (r >= A.DG) r -= A.DG;
-                        for (int t = 2 + g3; t <= tp.t_hi; t += 3) {
-                            add(G + r * ROW);
-                            r += 3; if (r >= A.DG) r -= A.DG;
-                        }
-                    } else {
-                        for (int t = g3; t < tp.F; t += 3) {
-                            float2 v;
-                            bool patched = false;
-                            const unsigned m = masks[t >> 5];
-                            if ((m >> (t & 31)) & 1u) {
-                                if (ringp) {
-                                    if (t >= 2 && t <= tp.t_hi) { int r = j + t; if (r >= A.DG) r -= A.DG; v = *reinterpret_cast<const float2*>(G2 + r * N_MFCC + 2 * c2); }
-                                    else v = *reinterpret_cast<const float2*>(patch + (t < 2 ? t : 2 + t - tp.t_hi - 1) * N_MFCC + 2 * c2);
-                                    patched = true;
-                                } else {
-                                    const int sl = (int)masks[8 + (t >> 5)] + __popc(m & ((1u << (t & 31)) - 1u));
-                                    if (sl < PATCH_CAP) { v = *reinterpret_cast<const float2*>(patch + sl * N_MFCC + 2 * c2); patched = true; }
-                                }
-                            }
-                            if (!patched) v = *reinterpret_cast<const float2*>(dense_row(G, ekh, tp, A.DG, j, t) + 2 * c2);
-                            if (pass == 0) { acc.x += v.x; acc.y += v.y; }
-                            else { const float dx = v.x - mean.x, dy = v.y - mean.y; acc.x = fmaf(dx, dx, acc.x); acc.y = fmaf(dy, dy, acc.y); }
-                        }
-                    }
+            const float* bs = BS + (size_t)(cls == 1 ? NBLK : 0) * 2 * N_MFCC;
+            int bi = blk_idx_lo + (int)(((jl + t0) >> 3) - b_lo); if (bi >= NBLK) bi -= NBLK;
+            static_assert(BLK == 8, "block index uses >> 3");
+            for (; t + BLK - 1 <= tp.t_hi; t += BLK) {
+                float mu, m2;
+                if (cls < 2) {
+                    const float* src = bs + (size_t)bi * 2 * N_MFCC;
+                    mu = lane < N_MFCC ? src[lane] : 0.f;
+                    m2 = lane < N_MFCC ? src[N_MFCC + lane] : 0.f;
+                    r += BLK; if (r >= A.DG) r -= A.DG;
+                } else {
+                    float v[BLK];
+#pragma unroll
+                    for (int q = 0; q < BLK; q++) { v[q] = ring_value(t + q, r); r++; if (r >= A.DG) r -= A.DG; }
+                    block_mean_m2(v, mu, m2);
                 }
-                // combine the three frame groups (lanes c2, c2+10, c2+20)
-                const float ax = __shfl_sync(FULL, acc.x, c2) + __shfl_sync(FULL, acc.x, c2 + 10) + __shfl_sync(FULL, acc.x, c2 + 20);
-                const float ay = __shfl_sync(FULL, acc.y, c2) + __shfl_sync(FULL, acc.y, c2 + 10) + __shfl_sync(FULL, acc.y, c2 + 20);
-                if (pass == 0) mean = make_float2(ax / (float)tp.F, ay / (float)tp.F);
-                else var = make_float2(ax / (float)tp.F, ay / (float)tp.F);
+                pool_item(n, mean, M2, (float)BLK, mu, m2);
+                bi++; if (bi >= NBLK) bi -= NBLK;
             }
-            // floored frames beyond the patch capacity: fold their corrections in by recomputation (rare)
-            if (!ringp && n_aff > PATCH_CAP) {
-                // second-order exactness is kept by redoing both passes with on-the-fly recomputation
-                float2 m2 = make_float2(0.f, 0.f), v2 = make_float2(0.f, 0.f);
-                for (int pass = 0; pass < 2; pass++) {
-                    float accx = 0.f, accy = 0.f;
-                    for (int t = 0; t < tp.F; t++) {
-                        const unsigned m = masks[t >> 5];
-                        const bool a = (m >> (t & 31)) & 1u;
-                        const float* src;
-                        if (a) {
-                            float2 x[8];
-                            load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
-                            float mn, mx;
-                            warp_frame_mfcc(x, *ft, scr, lane, floor_db, patch, mn, mx);
-                            __syncwarp();
-                            src = patch;
-                        } else src = dense_row(G, ekh, tp, A.DG, j, t);
-                        if (lane < 10) {
-                            const float2 v = *reinterpret_cast<const float2*>(src + 2 * lane);
-                            if (pass == 0) { accx += v.x; accy += v.y; }
-                            else { const float dx = v.x - m2.x, dy = v.y - m2.y; accx = fmaf(dx, dx, accx); accy = fmaf(dy, dy, accy); }
-                        }
-                        __syncwarp();
-                    }
-                    if (pass == 0) m2 = make_float2(accx / (float)tp.F, accy / (float)tp.F);
-                    else v2 = make_float2(accx / (float)tp.F, accy / (float)tp.F);
-                }
-                mean = make_float2(__shfl_sync(FULL, m2.x, c2), __shfl_sync(FULL, m2.y, c2));
-                var = make_float2(__shfl_sync(FULL, v2.x, c2), __shfl_sync(FULL, v2.y, c2));
+            for (; t <= tp.t_hi; t++) {
+                pool_item(n, mean, M2, 1.f, ring_value(t, r), 0.f);
+                r++; if (r >= A.DG) r -= A.DG;
             }
-            if (lane < 10) {
-                feat[2 * lane] = mean.x; feat[2 * lane + 1] = mean.y;
-                feat[N_MFCC + 2 * lane] = sqrtf(var.x); feat[N_MFCC + 2 * lane + 1] = sqrtf(var.y);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                const TemplateFeat& tf = tmpl[tp.slot];
-                *outp = tf.valid ? similarity_score(tf.mean, tf.std, feat, feat + N_MFCC) : __int_as_float(0x7fc00000);
-            }
-            __syncwarp();
+            for (int e = 2; e < n_edge; e++) pool_item(n, mean, M2, 1.f, edge_value(e), 0.f);
+            const float sd = sqrtf(M2 / (float)tp.F);
+            const float sc = similarity_score_warp(lane < N_MFCC ? tf.mean[lane] : 0.f, lane < N_MFCC ? tf.std[lane] : 0.f,
+                                                   lane < N_MFCC ? mean : 0.f, lane < N_MFCC ? sd : 0.f);
+            if (lane == 0) *outp = sc;
         }
         __syncthreads();
     }

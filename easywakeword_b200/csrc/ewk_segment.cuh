@@ -98,6 +98,32 @@ __device__ __forceinline__ float one_minus_cosine(const float* u, const float* v
     return __fsub_rn(1.0f, dist);
 }
 
+// The same score with one feature component per lane (lanes >= 20 pass zeros); every lane returns it.  The three
+// dot products of each cosine are butterfly sums, so u == v gives uv == uu == vv bit for bit and a self-match
+// scores exactly 100.
+__device__ __forceinline__ float one_minus_cosine_warp(float u, float v) {
+    float uv = u * v, uu = u * u, vv = v * v;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        uv += __shfl_xor_sync(0xffffffffu, uv, o);
+        uu += __shfl_xor_sync(0xffffffffu, uu, o);
+        vv += __shfl_xor_sync(0xffffffffu, vv, o);
+    }
+    const float prod = __fmul_rn(uu, vv);
+    const float q = (float)((double)uv / sqrt((double)prod));
+    float dist = __fsub_rn(1.0f, q);
+    dist = dist < 0.f ? 0.f : (dist > 2.f ? 2.f : dist);
+    return __fsub_rn(1.0f, dist);
+}
+
+__device__ __forceinline__ float similarity_score_warp(float ref_mean, float ref_std, float mean, float std) {
+    const float sim_mean = one_minus_cosine_warp(ref_mean, mean);
+    const float sim_std = one_minus_cosine_warp(ref_std, std);
+    const float combined = __fadd_rn(__fmul_rn(sim_mean, 0.7f), __fmul_rn(sim_std, 0.3f));
+    const float p = __fmul_rn(combined, 100.0f);
+    return __fdiv_rn(__fmul_rn(p, sqrtf(p)), 10.0f);
+}
+
 __device__ __forceinline__ float similarity_score(const float* ref_mean, const float* ref_std,
                                                   const float* mean, const float* std) {
     const float sim_mean = one_minus_cosine(ref_mean, mean);
