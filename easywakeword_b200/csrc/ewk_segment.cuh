@@ -207,6 +207,26 @@ __device__ __forceinline__ void load_frame_pairs_at(const PcmReader& rd, int f0,
     const long long p00 = rd.start + f0;                        // may be negative by up to N_FFT/2
     const bool even = ((p00 & 1) == 0) && (rd.ring == 0 || (rd.ring & 1) == 0) &&
                       !(rd.q ? ((size_t)rd.q & 3) : ((size_t)rd.f & 7));
+    if (even && rd.ring) {
+        // ring reader: every ring position is valid memory, so the pairs are loaded unconditionally (one wrap) and the
+        // window mask is applied afterwards — frame-relative sample m is inside the segment iff mlo <= m < mhi
+        int p0 = (int)p00;
+        if (p0 < 0) p0 += rd.ring; else if (p0 >= rd.ring) p0 -= rd.ring;
+        const unsigned mlo = (unsigned)max(0, -f0), span = (unsigned)max(0, min(N_FFT, rd.len - f0) - (int)mlo);
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            const int m = 2 * lane + 64 * a;
+            int p = p0 + m;
+            if (p >= rd.ring) p -= rd.ring;
+            float2 v;
+            if (rd.q) {
+                const unsigned u = __ldg(reinterpret_cast<const unsigned*>(rd.q + p));
+                v = make_float2((float)(short)(u & 0xffff) * (1.0f / 32768.0f), (float)((int)u >> 16) * (1.0f / 32768.0f));
+            } else v = __ldg(reinterpret_cast<const float2*>(rd.f + p));
+            x[a] = make_float2((unsigned)m - mlo < span ? v.x : 0.f, (unsigned)(m + 1) - mlo < span ? v.y : 0.f);
+        }
+        return;
+    }
     if (even) {
         int p0 = (int)p00;                                       // |p00| < 2^31 for rings; linear buffers < 2^30 samples
         if (rd.ring) { if (p0 < 0) p0 += rd.ring; else if (p0 >= rd.ring) p0 -= rd.ring; }
