@@ -971,6 +971,10 @@ extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl
         max_n = std::max(max_n, t.n);
     }
     A.DG = DH + max_n + 2;
+    if ((long long)B.P < 160LL * (max_n + DH + 4) + N_FFT) {        // the kernel wraps ring positions once
+        ctx->fail("ewk_dense_scores: ring of %d samples is too short for a template of %d hops", B.P, max_n);
+        return EWK_ERR_ARG;
+    }
     // the audio of every requested window must be resident
     const long long need_hi = 160LL * (hop0 + n_hops - 1);
     const long long need_lo = std::max<long long>(0, 160LL * (hop0 - max_n) - N_FFT / 2);

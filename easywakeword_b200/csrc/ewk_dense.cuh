@@ -163,7 +163,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
         if (g_valid_lo == LLONG_MAX) g_valid_lo = g_from;
         const int n_g = (int)max(0LL, g_hi - g_from + 1);
         int n_e = 0;
-        for (int k = 0; k < A.T; k++) n_e += nh * (2 + A.t[k].r);
+        for (int k = 0; k < A.T; k++) n_e += DH * (2 + A.t[k].r);        // job = (template, edge e, hop slot): slots >= nh are skipped
         // 32-bit bases for this sub-chunk: ring position of sample 160*hs and ring row of grid frame g_from
         const int hs_pos = (int)((160 * hs) % B.P);
         const int gfrom_row = n_g > 0 ? (int)(g_from % A.DG) : 0;
@@ -173,8 +173,8 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
             int f0;
             if (job < n_g) {
                 // absolute first sample 160 g - 256 (unmasked frame of the stream grid)
-                int pos = hs_pos + 160 * (gfrom_rel + job) - N_FFT / 2;
-                pos %= B.P; if (pos < 0) pos += B.P;
+                int pos = hs_pos + 160 * (gfrom_rel + job) - N_FFT / 2;       // |offset| < P: one wrap
+                if (pos < 0) pos += B.P; else if (pos >= B.P) pos -= B.P;
                 rd.start = pos; rd.len = N_FFT;
                 f0 = 0;
                 int r = gfrom_row + job; if (r >= A.DG) r -= A.DG;
@@ -182,14 +182,13 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                 if (lane == 0) g2tag[r] = 0x7fc00001;
             } else {
                 int rem = job - n_g, k = 0;
-                while (rem >= nh * (2 + A.t[k].r)) { rem -= nh * (2 + A.t[k].r); k++; }
+                while (rem >= DH * (2 + A.t[k].r)) { rem -= DH * (2 + A.t[k].r); k++; }
                 const DenseTmplDev& tp = A.t[k];
-                const int per = 2 + tp.r;
-                const int hl = rem / per, e = rem - hl * per;
-                if (hs + hl - tp.n < 0) continue;                   // window starts before the stream
+                const int e = rem / DH, hl = rem % DH;              // DH is a power of two
+                if (hl >= nh || hs + hl - tp.n < 0) continue;       // unused slot / window starts before the stream
                 const int t = e < 2 ? e : tp.t_hi + 1 + (e - 2);
                 int pos = hs_pos + 160 * (hl - tp.n);
-                pos %= B.P; if (pos < 0) pos += B.P;
+                if (pos < 0) pos += B.P; else if (pos >= B.P) pos -= B.P;
                 rd.start = pos; rd.len = tp.L;                      // zeros outside the window
                 f0 = t * HOP - N_FFT / 2;
                 row = edge + ((k * DH + hl) * 4 + e) * ROW;
@@ -230,7 +229,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                     int r = row_lo + i; if (r >= A.DG) r -= A.DG;
                     if (!(G[r * ROW + N_MFCC] < fstar) || g2tag[r] == fbits) continue;      // warp-uniform
                     int pos = hs_pos + 160 * (glo_rel + i) - N_FFT / 2;
-                    pos %= B.P; if (pos < 0) pos += B.P;
+                    if (pos < 0) pos += B.P; else if (pos >= B.P) pos -= B.P;
                     rd.start = pos; rd.len = N_FFT;
                     float2 x[8];
                     load_frame_pairs_at(rd, 0, lane, x);
@@ -300,7 +299,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
             const float floor_db = wmax - 80.0f;                       // librosa.power_to_db(top_db=80) on this window
             const unsigned emask = __ballot_sync(FULL, emin < floor_db);   // floored edge frames
             const int cls = !(rmin < floor_db) ? 0 : (__float_as_int(floor_db) == *fstar_s ? 1 : 2);
-            { int pos = hs_pos + 160 * (hl - tp.n); pos %= B.P; if (pos < 0) pos += B.P; rd.start = pos; }
+            { int pos = hs_pos + 160 * (hl - tp.n); if (pos < 0) pos += B.P; else if (pos >= B.P) pos -= B.P; rd.start = pos; }
             rd.len = tp.L;
             // floored edge frames are recomputed with the floor (window-local PCM view) into patch slots 0..3
             for (unsigned mm = emask; mm; mm &= mm - 1) {
