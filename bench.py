@@ -358,11 +358,13 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic.get(dom), "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "share_of_kernel_time": share,
-                    "note": "the dominant kernel (fused MFCC+match on candidate segments) is FP32-issue bound, ~55 flop per "
-                            "PCM byte (DESIGN.md §4): its HBM fraction is small by construction; `compute` gives its FP32 "
-                            "rate and `hbm_bound_kernel` the roofline of the HBM-bound kernel of the step (K1 fused push+sums)",
-                    "compute": {"frames_per_launch": frames_per_step, "flop_per_frame": 17700,
-                                "achieved_tflops": frames_per_step * 17700 / (avg_ms * 1e-3) / 1e12 if dom == "segment_queue" else None,
+                    "note": "the dominant kernel (fused MFCC+match on candidate segments) does ~45 flop per PCM byte "
+                            "(DESIGN.md §4) and is bound on the SM, not on HBM: ncu shows the shared-memory data pipe "
+                            "(l1tex lsu wavefronts) at ~78 % of peak while an SM is busy (profiles/README.md); its HBM "
+                            "fraction is small by construction.  `compute` gives its FP32 rate and `hbm_bound_kernel` "
+                            "the roofline of the HBM-bound kernel of the step (K1 fused push+sums)",
+                    "compute": {"frames_per_launch": frames_per_step, "flop_per_frame": 15300,
+                                "achieved_tflops": frames_per_step * 15300 / (avg_ms * 1e-3) / 1e12 if dom == "segment_queue" else None,
                                 "fp32_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12},
                     "hbm_bound_kernel": dict(kernel="ring_push", **(kroof("ring_push") or {})),
                     "tick_gate": kroof("tick_gate"),

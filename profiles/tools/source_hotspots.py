@@ -12,7 +12,7 @@ def main():
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     cur = line = src = None
-    tot, samp, text, calls = {}, {}, {}, []
+    tot, samp, text, calls, seen = {}, {}, {}, [], set()
     for r in rows:
         if len(r) >= 2 and r[0] == "File Path":
             cur = r[1].split("/")[-1]
@@ -25,7 +25,8 @@ def main():
             tot[key] = tot.get(key, 0) + int(r[7])
             samp[key] = samp.get(key, 0) + int(r[4])
             text[key] = src
-        elif "CALL" in r[3] and int(r[7]) > 0:
+        elif "CALL" in r[3] and int(r[7]) > 0 and (cur, line, r[2]) not in seen:
+            seen.add((cur, line, r[2]))                       # inlined lines are listed once per file section
             calls.append((cur, line, int(r[7]), src[:80]))
     T, S = sum(tot.values()), sum(samp.values())
     print(f"warp instructions executed {T}   stall samples {S}")
