@@ -211,6 +211,8 @@ def run_ours(args):
     ctx = bank.ctx
     results = torch.zeros(n, 2, dtype=torch.int32, device=dev)          # ewk_stream_result[n]: NCCL send buffer
     ctx.set_results_buffer(results.data_ptr())
+    overlap = not args.no_overlap
+    ctx.set_overlap(overlap)
     gathered = torch.zeros(world * n, 2, dtype=torch.int32, device=dev) if world > 1 else None
 
     def slice_ptr(t, j, esz=2):
@@ -235,6 +237,7 @@ def run_ours(args):
             push_next(where)
         bank.tick(TICKS_PER_STEP)
         if gathered is not None:
+            ctx.join()                                              # the gather reads the records K3 writes
             dist.all_gather_into_tensor(gathered, results)
         return bank.poll() if read_back else None
 
@@ -260,6 +263,7 @@ def run_ours(args):
             ev = step(where, read_back)
             if ev is not None:
                 n_ev += int((ev["kind"] == 2).sum())
+        ctx.join()                                                  # the last step's K3 belongs to the timed region
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -276,7 +280,9 @@ def run_ours(args):
     bank.poll()
     ms_e2e, _, n_events = timed(_lib.HOST, True, K)             # host PCM -> rings -> events on host
 
-    # per-kernel device time (CUDA events on the launching stream), same workload, separate loop
+    # per-kernel device time (CUDA events on the launching stream), same workload, separate loop; sequential order
+    # (no overlap) so that every kernel is timed alone
+    ctx.set_overlap(False)
     ctx.profile(True)
     for _ in range(K):
         step(_lib.DEVICE, False)
@@ -388,6 +394,9 @@ def run_ours(args):
                        "streams_per_gpu": n, "ring_seconds": RING_SECONDS, "step_seconds": STEP_SECONDS,
                        "template": word_name, "pcm": "int16", "params": PARAMS,
                        "l2": "inputs larger than L2: 131 MB of new PCM per step, 1.44 GB of rings per GPU",
+                       "overlap": ("K3 of step i runs on a second stream beside K1 of step i+1 (ewk_set_overlap); the timed "
+                                   "region ends after the last K3 (ewk_join); per-kernel times are taken in sequential order")
+                       if overlap else "off: K1, K2, K3 in sequence on one stream",
                        "parallelism": f"streams sharded {n}/GPU x {world}, all_gather of 8 B/stream results per step"
                        if world > 1 else "1 GPU"},
             "clocks": clocks,
@@ -423,6 +432,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="keep K3 on the context's stream (default: ewk_set_overlap(1), K3 beside the next push)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -232,6 +232,14 @@ class Context:
                                        n_out, out.ctypes.data, n_out, HOST))
         return out[0] if one_d else out
 
+    def set_overlap(self, enable=True):
+        """K3 on a second stream so that the next push runs beside it (see include/ewk.h: ewk_set_overlap)."""
+        self._ck(self.lib.ewk_set_overlap(self.h, 1 if enable else 0))
+
+    def join(self):
+        """Enqueue (no host sync) the wait for an in-flight K3 on the context's stream."""
+        self._ck(self.lib.ewk_join(self.h))
+
     def synchronize(self):
         self._ck(self.lib.ewk_synchronize(self.h))
 
@@ -284,6 +292,8 @@ def _declare_stream_protos(lib):
         "ewk_set_stream_params": (C.c_int, [vp, i32, _p(StreamParams)]),
         "ewk_push": (C.c_int, [vp, i32, i32, vp, i64, i64, i32]),
         "ewk_tick": (C.c_int, [vp, i32]),
+        "ewk_set_overlap": (C.c_int, [vp, i32]),
+        "ewk_join": (C.c_int, [vp]),
         "ewk_tick_trace": (C.c_int, [vp, i32, vp, vp, vp, vp]),
         "ewk_poll": (C.c_int, [vp, vp, i32, _p(C.c_int)]),
         "ewk_stream_status_get": (C.c_int, [vp, i32, _p(StreamStatus)]),

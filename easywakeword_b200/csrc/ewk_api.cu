@@ -102,6 +102,11 @@ extern "C" int ewk_destroy(ewk_ctx* ctx) {
 
 extern "C" int ewk_set_cuda_stream(ewk_ctx* ctx, void* s) {
     if (!ctx) return EWK_ERR_ARG;
+    if (ctx->match_inflight) {                       // results of the old stream's ticks stay ordered before the switch
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaStreamSynchronize(ctx->match_stream));
+        ctx->match_inflight = false;
+    }
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
     return EWK_OK;
 }
@@ -110,6 +115,8 @@ extern "C" int ewk_synchronize(ewk_ctx* ctx) {
     if (!ctx) return EWK_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     if (ctx->bank.n_streams) { int rc = ctx->flush_pending(); if (rc) return rc; }
+    int jr = ctx->join_match();
+    if (jr) return jr;
     CK(cudaStreamSynchronize(ctx->stream));
     return EWK_OK;
 }
@@ -159,6 +166,9 @@ void ewk_ctx::release() {
     if (d_tables) cudaFree(d_tables);
     if (d_tmpl) cudaFree(d_tmpl);
     if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+    if (match_stream) { cudaStreamSynchronize(match_stream); cudaStreamDestroy(match_stream); match_stream = nullptr; }
+    if (ev_gate) { cudaEventDestroy(ev_gate); ev_gate = nullptr; }
+    if (ev_match) { cudaEventDestroy(ev_match); ev_match = nullptr; }
     for (int i = 0; i < 2; i++) {
         if (ev_ready[i]) cudaEventDestroy(ev_ready[i]);
         if (ev_free[i]) cudaEventDestroy(ev_free[i]);
@@ -573,9 +583,40 @@ int ewk_ctx::gate_chunks() const {
     return m;
 }
 
-static int need_streams(ewk_ctx* ctx, const char* who) {
-    if (ctx->bank.n_streams == 0) { ctx->fail("%s: context was created with n_streams = 0", who); return EWK_ERR_STATE; }
+// Makes the context's stream wait for a K3 launch that is still running on the match stream (overlap mode).
+int ewk_ctx::join_match() {
+    ewk_ctx* ctx = this;
+    if (!match_inflight) return EWK_OK;
+    match_inflight = false;
+    CK(cudaStreamWaitEvent(stream, ev_match, 0));
     return EWK_OK;
+}
+
+// Every stream-bank entry point starts here.  All of them except ewk_push order themselves after an in-flight K3.
+static int need_streams(ewk_ctx* ctx, const char* who, bool join = true) {
+    if (ctx->bank.n_streams == 0) { ctx->fail("%s: context was created with n_streams = 0", who); return EWK_ERR_STATE; }
+    if (join) return ctx->join_match();
+    return EWK_OK;
+}
+
+extern "C" int ewk_set_overlap(ewk_ctx* ctx, int enable) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_set_overlap");
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if (enable && !ctx->match_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->match_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_gate, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_match, cudaEventDisableTiming));
+    }
+    ctx->overlap = enable != 0;
+    return EWK_OK;
+}
+
+extern "C" int ewk_join(ewk_ctx* ctx) {
+    if (!ctx) return EWK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return ctx->join_match();
 }
 
 extern "C" int64_t ewk_launch_count(const ewk_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -665,7 +706,7 @@ int ewk_ctx::flush_pending() {
 
 extern "C" int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pcm, int64_t n, int64_t stride, int where) {
     if (!ctx) return EWK_ERR_ARG;
-    int rc = need_streams(ctx, "ewk_push");
+    int rc = need_streams(ctx, "ewk_push", false);        // a push does not wait for the matching of the previous ticks
     if (rc) return rc;
     BankView& B = ctx->bank;
     if (!pcm || n_streams < 1 || stream0 < 0 || stream0 + n_streams > B.n_streams || n < 1 || stride < n) {
@@ -753,11 +794,25 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     ctx->prof_end(pe, 1);
     CK(cudaGetLastError());
     const int grid = ctx->queue_grid();
-    pe = ctx->prof_begin(2);
-    segment_queue_kernel<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ctx->stream>>>(
+    // Overlap mode: K3 only reads ring samples of the last 3 s before the gated position and writes event / result
+    // records, so the next push (K1) may run beside it; the next gate, poll or result read joins it first.  The push
+    // guard keeps un-gated samples within the slack, which protects [visible - R, visible); the segments of these ticks
+    // start at most 3 s + n_ticks x 0.1 s before it, hence the ring-length condition.
+    cudaStream_t ks = ctx->stream;
+    if (ctx->overlap && (long long)B.R >= MAX_SEG + (long long)(n_ticks + 2) * TICK && !want) {
+        CK(cudaEventRecord(ctx->ev_gate, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->match_stream, ctx->ev_gate, 0));
+        ks = ctx->match_stream;
+    }
+    pe = ctx->prof_begin(2, ks);
+    segment_queue_kernel<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ks>>>(
         ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
-    ctx->prof_end(pe, 2);
+    ctx->prof_end(pe, 2, ks);
     CK(cudaGetLastError());
+    if (ks != ctx->stream) {
+        CK(cudaEventRecord(ctx->ev_match, ks));
+        ctx->match_inflight = true;
+    }
     ctx->launches += 1;
     ctx->pushes_since_tick = 0;
     // host mirrors (audio clock): V after these ticks, given what has been pushed
@@ -1062,26 +1117,28 @@ extern "C" int ewk_host_free(void* p) {
 // ==========================================================================================
 // per-kernel event timing
 // ==========================================================================================
-cudaEvent_t ewk_ctx::prof_begin(int) {
+cudaEvent_t ewk_ctx::prof_begin(int, cudaStream_t on) {
     if (!prof_on) return nullptr;
     cudaEvent_t e;
     if (!prof_free.empty()) { e = prof_free.back(); prof_free.pop_back(); }
     else if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
-    cudaEventRecord(e, stream);
+    cudaEventRecord(e, on ? on : stream);
     return e;
 }
 
-void ewk_ctx::prof_end(cudaEvent_t a, int cls) {
+void ewk_ctx::prof_end(cudaEvent_t a, int cls, cudaStream_t on) {
     if (!a) return;
     cudaEvent_t b;
     if (!prof_free.empty()) { b = prof_free.back(); prof_free.pop_back(); }
     else if (cudaEventCreate(&b) != cudaSuccess) { prof_free.push_back(a); return; }
-    cudaEventRecord(b, stream);
+    cudaEventRecord(b, on ? on : stream);
     prof_pairs.push_back({a, b, cls});
 }
 
 int ewk_ctx::prof_collect() {
     ewk_ctx* ctx = this;
+    int jr = join_match();
+    if (jr) return jr;
     CK(cudaStreamSynchronize(stream));
     for (auto& p : prof_pairs) {
         float ms = 0.f;

@@ -44,6 +44,12 @@ struct ewk_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool ev_free_valid[2] = {false, false};
+    // optional overlap of K3 (level-2 matching) with the next push: K3 runs on match_stream after the gate (ev_gate) and the
+    // context's stream joins it (ev_match) at the next call that needs level-2 results
+    cudaStream_t match_stream = nullptr;
+    cudaEvent_t ev_gate = nullptr, ev_match = nullptr;
+    bool overlap = false, match_inflight = false;
+    int join_match();
     int stage_idx = 0;
     struct Pending { bool valid = false; int slot = 0, stream0 = 0, n_streams = 0; long long n = 0; } pending;
     int land(int stream0, int n_streams, const void* d_src, long long d_stride, long long n, int stage_slot);
@@ -78,8 +84,8 @@ struct ewk_ctx {
     std::vector<cudaEvent_t> prof_free;
     double prof_ms[8] = {0};
     long long prof_n[8] = {0};
-    cudaEvent_t prof_begin(int cls);
-    void prof_end(cudaEvent_t a, int cls);
+    cudaEvent_t prof_begin(int cls, cudaStream_t on = nullptr);
+    void prof_end(cudaEvent_t a, int cls, cudaStream_t on = nullptr);
     int prof_collect();
     int init_streams();
     void release_streams();

@@ -178,6 +178,16 @@ int ewk_read_segment(ewk_ctx* ctx, int stream, int64_t seg_start, int64_t seg_le
  * already overwritten in its ring. */
 int ewk_prepare_segments(ewk_ctx* ctx, int n_seg, const int32_t* streams, const int64_t* starts, const int64_t* lens,
                          const int64_t* out_offsets, float* out, int64_t out_len, int where);
+/* Overlap of level-2 matching with the next push (off by default).  When enabled, ewk_tick launches K3 on a second
+ * stream right after the gate: the next ewk_push (K1, HBM-bound) then runs beside K3's tail instead of behind it.
+ * K3 only reads ring samples that the push guard already protects and writes event / result records, and every other
+ * stream-bank call (the next ewk_tick, ewk_poll, ewk_stream_results, ewk_read_*, ...) first makes the context's
+ * stream wait for it, so results are unchanged.  The one visible difference: work that the CALLER enqueues on the
+ * context's stream right after ewk_tick (e.g. an NCCL all-gather of ewk_results_device_ptr) must be preceded by
+ * ewk_join, which enqueues that wait without blocking the host.  Rings shorter than 3 s + the ticks of a call keep the
+ * sequential order. */
+int ewk_set_overlap(ewk_ctx* ctx, int enable);
+int ewk_join(ewk_ctx* ctx);
 /* Template analysis, batched: WakeWord._analyze_reference_audio_duration
  * (wakeword.py:872-893) for n templates at once — librosa.feature.rms with 25 ms frames every 10 ms (zero-padded
  * centring), frames above 0.1 * max RMS, first-to-last span, floor 0.2 s.  Template i is the float32 samples

@@ -134,3 +134,32 @@ def test_read_last_and_segment(word):
     with pytest.raises(Exception):
         ctx.read_segment(1, 1000, 100)    # overwritten
     ctx.close()
+
+
+def test_overlap_mode_gives_identical_events(word):
+    """ewk_set_overlap(1): K3 on a second stream beside the next push.  Events, scores and per-stream results must be
+    bit-identical to the sequential order, with polls at irregular intervals and a ring just long enough for it."""
+    from easywakeword_b200.bank import WakeWordBank
+    from easywakeword_b200.synth import stream_batch
+    pcm16 = stream_batch(4200, 24, 30.0, word, zero_gaps=1, distractor_prob=0.3)
+    out = []
+    for overlap in (False, True):
+        bank = WakeWordBank(24, [word], device=0, buffer_seconds=5, speech_duration_min=0.5, speech_duration_max=1.6)
+        bank.ctx.set_overlap(overlap)
+        try:
+            evs = []
+            for i, b in enumerate(range(0, pcm16.shape[1], 16000)):
+                bank.step(np.ascontiguousarray(pcm16[:, b:b + 16000]))
+                if i % 3 == 2:
+                    evs.append(bank.poll())
+            evs.append(bank.poll())
+            res = bank.ctx.results()
+            out.append((np.concatenate(evs), res))
+        finally:
+            bank.close()
+    (e0, r0), (e1, r1) = out
+    assert len(e0) == len(e1) and (e0["kind"] == 2).sum() > 10
+    for f in e0.dtype.names:
+        assert np.array_equal(e0[f], e1[f], equal_nan=e0[f].dtype.kind == "f"), f
+    for f in r0.dtype.names:
+        assert np.array_equal(r0[f], r1[f], equal_nan=r0[f].dtype.kind == "f"), f
