@@ -394,8 +394,9 @@ def run_ours(args):
                        "streams_per_gpu": n, "ring_seconds": RING_SECONDS, "step_seconds": STEP_SECONDS,
                        "template": word_name, "pcm": "int16", "params": PARAMS,
                        "l2": "inputs larger than L2: 131 MB of new PCM per step, 1.44 GB of rings per GPU",
-                       "overlap": ("K3 of step i runs on a second stream beside K1 of step i+1 (ewk_set_overlap); the timed "
-                                   "region ends after the last K3 (ewk_join); per-kernel times are taken in sequential order")
+                       "overlap": ("K3 of step i runs on a second stream beside K1 of step i+1 (ewk_set_overlap; K1 in its "
+                                   "cp.async.bulk form); the timed region ends after the last K3 (ewk_join); per-kernel "
+                                   "times are taken in sequential order, each kernel alone")
                        if overlap else "off: K1, K2, K3 in sequence on one stream",
                        "parallelism": f"streams sharded {n}/GPU x {world}, all_gather of 8 B/stream results per step"
                        if world > 1 else "1 GPU"},

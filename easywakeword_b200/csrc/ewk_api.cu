@@ -554,6 +554,8 @@ int ewk_ctx::init_streams() {
     h_frame_size.assign(n, 0);
     CK(cudaFuncSetAttribute(segment_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
+    CK(cudaFuncSetAttribute(ring_push_bulk_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    CK(cudaFuncSetAttribute(ring_push_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     {
         const size_t big = sizeof(double) * 3 * (size_t)(std::min(chunk_cap, GATE_SMEM_CHUNKS) + 1) * GATE_WARPS;
         const size_t staged = sizeof(double) * 3 * (size_t)130 * GATE_WARPS + (size_t)2 * TICK * 4 * GATE_WARPS;
@@ -663,7 +665,20 @@ int ewk_ctx::land(int stream0, int n_streams, const void* d_src, long long d_str
     for (int s = stream0; aligned && s < stream0 + n_streams; s++) aligned = (h_written[s] % TICK) == 0;
     if (stage_slot >= 0) CK(cudaStreamWaitEvent(stream, ev_ready[stage_slot], 0));
     cudaEvent_t pe = prof_begin(0);
-    if (aligned) {
+    static const int bulk_env = [] { const char* e = getenv("EWK_PUSH_BULK"); return e ? atoi(e) : 1; }();
+    if (aligned && bulk_env && match_inflight && (long long)n_streams * (n / TICK) >= 4LL * sm_count * PUSH_BULK_WARPS) {
+        // TMA form while K3 is running on the match stream: persistent CTAs of two warps whose bytes in flight sit in
+        // shared-memory stages, small enough (2.5 k registers, 26 KB) to share the SMs with K3's CTAs.  Alone, the
+        // register-staged kernel below is faster (47 vs 60 us at 4096 x 1.0 s), so it keeps the sequential case.
+        static const int env_stages = [] { const char* e = getenv("EWK_PUSH_STAGES"); return e ? atoi(e) : 0; }();
+        static const int env_grid = [] { const char* e = getenv("EWK_PUSH_GRID"); return e ? atoi(e) : 0; }();
+        const int stages = env_stages > 0 ? env_stages : (B.fmt == 1 ? 4 : 2);
+        const size_t smem = (size_t)PUSH_BULK_WARPS * stages * TICK * esz + sizeof(unsigned long long) * PUSH_BULK_WARPS * stages;
+        const int grid = (env_grid > 0 ? env_grid : 2) * sm_count;
+        if (B.fmt == 1) ring_push_bulk_kernel<short><<<grid, PUSH_BULK_WARPS * 32, smem, stream>>>(B, stream0, n_streams, (const short*)d_src, d_stride, (int)n, stages);
+        else ring_push_bulk_kernel<float><<<grid, PUSH_BULK_WARPS * 32, smem, stream>>>(B, stream0, n_streams, (const float*)d_src, d_stride, (int)n, stages);
+        with_sums = 1;
+    } else if (aligned) {
         dim3 grid((unsigned)((n / TICK + 3) / 4), (unsigned)n_streams);
         if (B.fmt == 1) ring_push_sums_kernel<short><<<grid, 128, 0, stream>>>(B, stream0, (const short*)d_src, d_stride, (int)n);
         else ring_push_sums_kernel<float><<<grid, 128, 0, stream>>>(B, stream0, (const float*)d_src, d_stride, (int)n);

@@ -15,7 +15,8 @@
 
 namespace ewk {
 
-constexpr int SEG_THREADS = 512;
+constexpr int SEG_THREADS = 448;           // 14 warps: two CTAs leave 8 k registers per SM for the bulk push that runs beside K3;
+                                           // the frame pipeline is shared-memory bound, so 28 warps per SM are as fast as 32
 constexpr int SEG_WARPS = SEG_THREADS / 32;
 constexpr int SEG_SMEM_FRAMES = 301;           // 1 + 48000/160
 constexpr int FEAT = 2 * N_MFCC;               // mean[20] ++ std[20]
@@ -364,7 +365,7 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
 }
 
 // K3, batch form: one CTA per caller-described segment (extract_mfcc / calculate_similarity / matches).
-__global__ void __launch_bounds__(SEG_THREADS, 2)
+__global__ void __launch_bounds__(512, 2)
 segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __restrict__ segs,
                           int cap_frames, float* __restrict__ ws,           // global spill [frames][22]
                           float* __restrict__ lm_ws,                         // log-mel workspace [frames][128] or null

@@ -407,6 +407,85 @@ __device__ __forceinline__ double warp_sumsq_smem(const void* buf, int fmt, int 
     return acc;
 }
 
+// ------------------------------------------------------------------------------------ K1 (bulk form)
+// The same push + per-block sums as ring_push_sums_kernel, moved by the TMA engine: a persistent kernel of small
+// CTAs whose warps each run a ring of `stages` shared-memory slots — cp.async.bulk global -> shared (mbarrier
+// completion), sum of squares of the staged 0.1 s block, cp.async.bulk shared -> ring (bulk group).  Bandwidth comes
+// from bytes in flight (stages x 3.2 KB per warp), not from resident threads, so the kernel needs ~2 k registers and
+// no issue slots to speak of: it can run beside K3 on the same SMs (ewk_set_overlap) as well as alone.
+// Requires what the fused kernel requires (whole blocks, 16-byte aligned rows) plus rings that are a whole number
+// of blocks, so a block never wraps.
+constexpr int PUSH_BULK_WARPS = 2;
+
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(PUSH_BULK_WARPS * 32)
+ring_push_bulk_kernel(BankView B, int stream0, int n_streams, const T* __restrict__ src, long long stride, int n, int stages) {
+    extern __shared__ __align__(128) unsigned char push_smem[];
+    constexpr unsigned BYTES = TICK * sizeof(T);
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    unsigned char* buf = push_smem + (size_t)wl * stages * BYTES;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(push_smem + (size_t)PUSH_BULK_WARPS * stages * BYTES) + wl * stages;
+    const int nb = n / TICK;
+    // a warp takes whole streams (gw, gw + GW, ...) and walks their nb blocks in order: its k-th item is block k % nb
+    // of its (k / nb)-th stream
+    const int gw = blockIdx.x * PUSH_BULK_WARPS + wl, GW = gridDim.x * PUSH_BULK_WARPS;
+    const int my_streams = gw < n_streams ? (n_streams - gw + GW - 1) / GW : 0;
+    const long long my_items = (long long)my_streams * nb;
+    if (lane == 0) {
+        for (int i = 0; i < stages; i++) mbar_init(full + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // all indices are carried incrementally (no divisions on the single warp's critical path)
+    int ij = 0, ib = 0, ist = 0;                                  // issue cursor: stream ordinal, block, stage
+    long long issued = 0;
+    auto issue = [&]() {                                          // lane 0: start the load of the warp's next item
+        if (issued >= my_items) return;
+        mbar_expect_tx(full + ist, BYTES);
+        bulk_g2s(buf + (size_t)ist * BYTES, src + (size_t)(gw + ij * GW) * stride + (size_t)ib * TICK, BYTES, full + ist);
+        issued++;
+        if (++ist == stages) ist = 0;
+        if (++ib == nb) { ib = 0; ij++; }
+    };
+    if (lane == 0) for (int k = 0; k < stages; k++) issue();
+    long long w_next = my_streams ? B.st[stream0 + gw].written : 0;
+    int j = 0, b = 0, st = 0, p0 = 0, bi = 0;
+    unsigned phase = 0;
+    for (long long k = 0; k < my_items; k++) {
+        const int s = stream0 + gw + j * GW;
+        if (b == 0) {
+            const long long w_cur = w_next;
+            p0 = (int)(w_cur % B.P);                                        // once per stream
+            bi = (int)((w_cur / TICK) % B.NB);
+            if (j + 1 < my_streams) w_next = B.st[s + GW].written;          // needed nb items from now
+        }
+        mbar_wait(full + st, phase);
+        const double acc = warp_sumsq_smem(buf + (size_t)st * BYTES, sizeof(T) == 2 ? 1 : 0, lane);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads of the slot precede its async reuse
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g((T*)B.ring + (size_t)s * B.P + p0, buf + (size_t)st * BYTES, BYTES);   // P % TICK == 0: no wrap inside the block
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            B.block_ss[(size_t)s * B.NB + bi] = acc;
+            if (k >= 1) {
+                // the store of the previous item has read its slot: refill it
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                issue();
+            }
+        }
+        __syncwarp();
+        if (++st == stages) { st = 0; phase ^= 1u; }
+        p0 += TICK; if (p0 >= B.P) p0 -= B.P;
+        if (++bi == B.NB) bi = 0;
+        if (++b == nb) { b = 0; j++; }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 struct GatePlan {                                   // one per warp (= per stream)
     long long V[GATE_MAX_TICKS];                    // samples visible at each tick
     double pv[GATE_MAX_TICKS][GATE_MAXP + 1];       // piece values; [GATE_MAXP] = recent-window sum of squares
@@ -794,7 +873,7 @@ segment_prepare_kernel(BankView B, const PrepDesc* __restrict__ d, float* __rest
 // tail by one segment instead of a static share.  Events below the watermark ev_count[3] were scored by earlier
 // launches and are not visited again; the last CTA to finish advances it and zeroes the counters.
 
-__global__ void __launch_bounds__(SEG_THREADS, 2)
+__global__ void __launch_bounds__(512, 2)
 segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, int n_tmpl_slots) {
     extern __shared__ __align__(16) float smem[];
     const SegSmem m = seg_carve(smem, SEG_SMEM_FRAMES);

@@ -163,3 +163,42 @@ def test_overlap_mode_gives_identical_events(word):
         assert np.array_equal(e0[f], e1[f], equal_nan=e0[f].dtype.kind == "f"), f
     for f in r0.dtype.names:
         assert np.array_equal(r0[f], r1[f], equal_nan=r0[f].dtype.kind == "f"), f
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.float32])
+def test_overlap_mode_bulk_push_matches_sequential(word, dtype):
+    """With enough streams the overlapped push takes the TMA (cp.async.bulk) form of K1.  Ring contents, adaptive
+    thresholds (exact block sums), events and results must equal the sequential run bit for bit."""
+    from easywakeword_b200.bank import WakeWordBank
+    from easywakeword_b200.synth import stream_batch
+    n = 160
+    pcm = stream_batch(7000, n, 14.0, word, as_int16=dtype == np.int16, distractor_prob=0.2)
+    out = []
+    for overlap in (False, True):
+        bank = WakeWordBank(n, [word], device=0, buffer_seconds=6, pcm_dtype=dtype, speech_duration_min=0.5,
+                            speech_duration_max=1.6)
+        bank.ctx.set_overlap(overlap)
+        try:
+            import torch
+            from easywakeword_b200 import _lib
+            evs = []
+            blocks = [torch.from_numpy(np.ascontiguousarray(pcm[:, b:b + 16000])).cuda() for b in range(0, pcm.shape[1], 16000)]
+            torch.cuda.synchronize()
+            for t in blocks:                                     # device-resident PCM: K1 is launched at push time
+                bank.step((t.data_ptr(), n, 16000, 16000), where=_lib.DEVICE)
+            evs.append(bank.poll())
+            st = [bank.ctx.status(s) for s in (0, 1, n // 2, n - 1)]
+            rings = [bank.ctx.read_last(s, 16000 * 5) for s in (0, n - 1)]
+            out.append((np.concatenate(evs), bank.ctx.results(), st, rings))
+        finally:
+            bank.close()
+    (e0, r0, s0, g0), (e1, r1, s1, g1) = out
+    assert (e0["kind"] == 2).sum() > 20
+    for f in e0.dtype.names:
+        assert np.array_equal(e0[f], e1[f], equal_nan=e0[f].dtype.kind == "f"), f
+    for f in r0.dtype.names:
+        assert np.array_equal(r0[f], r1[f], equal_nan=r0[f].dtype.kind == "f"), f
+    for a, b in zip(s0, s1):
+        assert bytes(a) == bytes(b)
+    for a, b in zip(g0, g1):
+        assert np.array_equal(a, b)
