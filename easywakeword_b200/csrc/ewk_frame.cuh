@@ -26,10 +26,14 @@ constexpr int N_BINS = 257;
 constexpr int N_MELS = 128;
 constexpr int N_MFCC = 20;
 constexpr int MEL_NNZ_CAP = 512;          // 504 used for sr=16000, n_fft=512, 128 bands
-// Lane l owns mel bands l + 32 j (j = 0..3).  The Slaney bank's non-zero counts grow with the band index:
-// the widest band of each group of 32 has 2 / 3 / 6 / 12 taps, so padding every band of a group with zero
-// weights to that length gives branch-free, fully unrolled loops of 23 taps per lane (checked on the host).
-constexpr int MEL_TAPS0 = 2, MEL_TAPS1 = 3, MEL_TAPS2 = 6, MEL_TAPS3 = 12;
+// Lane l owns mel bands l + 32 j (j = 0..3).  A triangular band is a rising edge over the interval
+// I_b = [f_b, f_b+1) of the mel grid and a falling edge over I_b+1, and neighbouring bands share their intervals
+// (I_b+1 is the falling edge of band b AND the rising edge of band b + 1).  So the lane sums over ONE interval,
+// I_(b+1), with two weights per bin — the falling weight of band b and the rising weight of band b + 1 — and receives
+// the rising part of its own band from lane l - 1: every power-spectrum bin is read once instead of twice.  The
+// widest interval of each group of 32 has 1 / 2 / 3 / 6 bins; shorter ones are padded with zero weights, which gives
+// branch-free, fully unrolled loops of 12 taps per lane (checked on the host).
+constexpr int MEL_TAPS0 = 1, MEL_TAPS1 = 2, MEL_TAPS2 = 3, MEL_TAPS3 = 6;
 constexpr int MEL_TAPS = MEL_TAPS0 + MEL_TAPS1 + MEL_TAPS2 + MEL_TAPS3;
 constexpr int SCR_PLANE = 320;            // floats per re / im transpose plane (8 rows x 40)
 constexpr int SCR_P = 264;                // power spectrum, 257 bins padded; aliases the re plane (dead by then)
@@ -48,8 +52,9 @@ struct DeviceTables {
     int mel_off[N_MELS];          // offset into mel_w
     float mel_w[MEL_NNZ_CAP];     // librosa.filters.mel(htk=False, norm='slaney'), row-compressed
     float dct_t[N_MELS * N_MFCC]; // ortho DCT-II, transposed: dct_t[b*20 + k]
-    float mel_pad[MEL_TAPS * 32]; // zero-padded taps: mel_pad[tap * 32 + lane], taps grouped by j
-    int mel_first[4 * 32];        // mel_first[j * 32 + lane] = first FFT bin of band lane + 32 j
+    float2 mel_pad[MEL_TAPS * 32];// interval taps: mel_pad[tap * 32 + lane] = (falling weight of band b, rising weight of band
+                                  // b + 1) for the tap's bin of interval b + 1, b = lane + 32 j; zero-padded, taps grouped by j
+    int mel_first[4 * 32];        // mel_first[j * 32 + lane] = first FFT bin of that interval
 };
 
 // Per-CTA shared copy, laid out for conflict-free lane-indexed access.
@@ -58,8 +63,8 @@ struct FrameTables {
     float2 tw1[8 * 32];           // tw1[k*32 + lane]  = W256^(lane k)
     float2 tw3[4 * 32];           // tw3[m*32 + lane]  = W512^(lane + 32 m), m < 4 (bin pairs k, 256-k share it)
     float2 tw2[8 * 4];            // tw2[k*4 + c]      = W32^(c k)
-    float melp[MEL_TAPS * 32];    // zero-padded mel taps, [tap][lane]
-    int mfirst[4 * 32];           // first FFT bin of band lane + 32 j, [j][lane]
+    float2 melp[MEL_TAPS * 32];   // zero-padded interval taps (falling, rising), [tap][lane]
+    int mfirst[4 * 32];           // first FFT bin of interval lane + 32 j + 1, [j][lane]
     int coef_of_lane[32];         // which MFCC coefficient the lane holds after warp_dct20 (-1: none)
     float4 dct[32 * DCT_LANE4];        // per lane: [band slot s < 4][m < 10] = dct(k = 2 m + (lane >> 4), band_s), see warp_dct20
 };
@@ -72,7 +77,7 @@ __device__ __forceinline__ void load_frame_tables(FrameTables& ft, const DeviceT
         if (a < 4) ft.tw3[i] = T->w512[lane + 32 * a];
     }
     for (int i = tid; i < 32; i += nthr) ft.tw2[i] = T->w256[(8 * (i & 3) * (i >> 2)) & 255];
-    for (int i = tid; i < MEL_TAPS * 32; i += nthr) ft.melp[i] = T->mel_pad[i];
+    for (int i = tid; i < MEL_TAPS * 32; i += nthr) ft.melp[i] = T->mel_pad[i];      // float2 (falling, rising)
     for (int i = tid; i < 4 * 32; i += nthr) ft.mfirst[i] = T->mel_first[i];
     float* dd = reinterpret_cast<float*>(ft.dct);
     for (int i = tid; i < 32 * DCT_LANE4 * 4; i += nthr) {
@@ -204,20 +209,37 @@ __device__ __forceinline__ void warp_power_spectrum(const float2 (&x)[8], const 
 
 // One warp: P[0..263] (bins 257..263 hold zeros) -> the lane's four log-mel values (bands lane + 32 j),
 // 10*log10(max(1e-10, S)).  Branch-free: zero-padded taps, compile-time trip counts.
+// falling part of band b (returned) and rising part of band b + 1 (rise) over the lane's interval
 template <int NT>
-__device__ __forceinline__ float mel_band(const float* __restrict__ p, const float* __restrict__ w) {
-    float acc = 0.f;
+__device__ __forceinline__ float mel_interval(const float* __restrict__ p, const float2* __restrict__ w, float& rise) {
+    float fall = 0.f;
+    rise = 0.f;
 #pragma unroll
-    for (int i = 0; i < NT; i++) acc = fmaf(w[i * 32], p[i], acc);
-    return TEN_LOG10_2 * __log2f(fmaxf(acc, 1e-10f));
+    for (int i = 0; i < NT; i++) {
+        const float2 wt = w[i * 32];
+        const float v = p[i];
+        fall = fmaf(wt.x, v, fall);
+        rise = fmaf(wt.y, v, rise);
+    }
+    return fall;
 }
 
 __device__ __forceinline__ void warp_log_mel(const float* __restrict__ P, const FrameTables& ft, int lane, float (&out)[4]) {
-    const float* w = ft.melp + lane;
-    out[0] = mel_band<MEL_TAPS0>(P + ft.mfirst[lane], w);
-    out[1] = mel_band<MEL_TAPS1>(P + ft.mfirst[32 + lane], w + 32 * MEL_TAPS0);
-    out[2] = mel_band<MEL_TAPS2>(P + ft.mfirst[64 + lane], w + 32 * (MEL_TAPS0 + MEL_TAPS1));
-    out[3] = mel_band<MEL_TAPS3>(P + ft.mfirst[96 + lane], w + 32 * (MEL_TAPS0 + MEL_TAPS1 + MEL_TAPS2));
+    const float2* w = ft.melp + lane;
+    float fall[4], rise[4];
+    fall[0] = mel_interval<MEL_TAPS0>(P + ft.mfirst[lane], w, rise[0]);
+    fall[1] = mel_interval<MEL_TAPS1>(P + ft.mfirst[32 + lane], w + 32 * MEL_TAPS0, rise[1]);
+    fall[2] = mel_interval<MEL_TAPS2>(P + ft.mfirst[64 + lane], w + 32 * (MEL_TAPS0 + MEL_TAPS1), rise[2]);
+    fall[3] = mel_interval<MEL_TAPS3>(P + ft.mfirst[96 + lane], w + 32 * (MEL_TAPS0 + MEL_TAPS1 + MEL_TAPS2), rise[3]);
+    // band b = rising part over I_b (held by the lane that owns interval b: lane - 1, or lane 31 of the previous
+    // group; band 0 has none: no bin lies inside I_0) + falling part over I_(b+1) (own)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float r = __shfl_up_sync(FULL, rise[j], 1);
+        const float rw = j > 0 ? __shfl_sync(FULL, rise[j > 0 ? j - 1 : 0], 31) : 0.f;
+        if (lane == 0) r = rw;
+        out[j] = TEN_LOG10_2 * __log2f(fmaxf(r + fall[j], 1e-10f));
+    }
 }
 
 // One warp: log-mel x[4] per lane (bands lane + 32 j, already floored) -> ortho DCT-II.  Lanes 0-15 form

@@ -81,18 +81,50 @@ inline int build_tables(DeviceTables& T) {
         for (int k = 0; k < len; k++) T.mel_w[off + k] = mel[(size_t)i * N_BINS + first + k];
         off += len;
     }
-    // zero-padded taps for the branch-free mel loops (lane l owns bands l + 32 j)
-    const int taps[4] = {MEL_TAPS0, MEL_TAPS1, MEL_TAPS2, MEL_TAPS3};
-    int tap0 = 0;
-    for (int j = 0; j < 4; j++) {
-        for (int lane = 0; lane < 32; lane++) {
-            const int b = lane + 32 * j;
-            if (T.mel_len[b] > taps[j] || T.mel_start[b] + taps[j] > SCR_P) return -1;
-            T.mel_first[j * 32 + lane] = T.mel_start[b];
-            for (int i = 0; i < taps[j]; i++)
-                T.mel_pad[(tap0 + i) * 32 + lane] = i < T.mel_len[b] ? T.mel_w[T.mel_off[b] + i] : 0.f;
+    // interval taps for the mel stage (ewk_frame.cuh: warp_log_mel).  Interval i = [f_i, f_(i+1)) of the mel grid
+    // holds the rising edge of band i and the falling edge of band i - 1; lane l, group j owns interval l + 32 j + 1.
+    // The weights are the entries of the dense bank above, regrouped: a non-zero tap of band b belongs to interval b
+    // when its bin lies below the band's centre f_(b+1), to interval b + 1 otherwise.
+    {
+        const double sr = 16000.0, fmin = 0.0, fmax = sr / 2;
+        std::vector<double> mel_f(N_MELS + 2);
+        const double lo = hz_to_mel_slaney(fmin), hi = hz_to_mel_slaney(fmax), step = (hi - lo) / (N_MELS + 1);
+        for (int i = 0; i < N_MELS + 2; i++) mel_f[i] = mel_to_hz_slaney(i == N_MELS + 1 ? hi : i * step + lo);
+        const double binw = 1.0 / (N_FFT * (1.0 / sr));
+        std::vector<int> ifirst(N_MELS + 2, -1), ilast(N_MELS + 2, -1);
+        auto interval_of = [&](int b, int k) { return k * binw < mel_f[b + 1] ? b : b + 1; };
+        for (int b = 0; b < N_MELS; b++)
+            for (int k = 0; k < N_BINS; k++)
+                if (mel[(size_t)b * N_BINS + k] != 0.f) {
+                    const int i = interval_of(b, k);
+                    if (ifirst[i] < 0 || k < ifirst[i]) ifirst[i] = k;
+                    if (k > ilast[i]) ilast[i] = k;
+                }
+        if (ifirst[0] >= 0 || ifirst[N_MELS + 1] >= 0) return -1;       // band 0 has no rising taps, band 127's falling edge is I_128
+        const int taps[4] = {MEL_TAPS0, MEL_TAPS1, MEL_TAPS2, MEL_TAPS3};
+        int tap0 = 0;
+        for (int j = 0; j < 4; j++) {
+            for (int lane = 0; lane < 32; lane++) {
+                const int i = lane + 32 * j + 1;                           // interval; falling edge of band i - 1, rising edge of band i
+                const int first = ifirst[i] < 0 ? 0 : ifirst[i], len = ifirst[i] < 0 ? 0 : ilast[i] - ifirst[i] + 1;
+                if (len > taps[j] || first + taps[j] > SCR_P) return -1;
+                T.mel_first[j * 32 + lane] = first;
+                for (int q = 0; q < taps[j]; q++) {
+                    float wf = 0.f, wr = 0.f;
+                    const int k = first + q;
+                    if (q < len) {
+                        const float a = mel[(size_t)(i - 1) * N_BINS + k];
+                        if (a != 0.f && interval_of(i - 1, k) == i) wf = a;
+                        if (i < N_MELS) {
+                            const float r = mel[(size_t)i * N_BINS + k];
+                            if (r != 0.f && interval_of(i, k) == i) wr = r;
+                        }
+                    }
+                    T.mel_pad[(tap0 + q) * 32 + lane] = make_float2(wf, wr);
+                }
+            }
+            tap0 += taps[j];
         }
-        tap0 += taps[j];
     }
     build_dct_t(T.dct_t);
     return off;
