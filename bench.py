@@ -237,6 +237,8 @@ def run_ours(args):
             push_next(where)
         bank.tick(TICKS_PER_STEP)
         if gathered is not None:
+            if overlap and where == _lib.DEVICE and pushed[0] == step_no[0]:
+                push_next(where)                                    # next step's K1 goes beside this step's K3, ahead of the gather
             ctx.join()                                              # the gather reads the records K3 writes
             dist.all_gather_into_tensor(gathered, results)
         return bank.poll() if read_back else None
