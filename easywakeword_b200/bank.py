@@ -34,7 +34,7 @@ class WakeWordBank:
                  pre_speech_silence: float = 0.8, speech_duration_min: Optional[float] = None,
                  speech_duration_max: Optional[float] = None, post_speech_silence: float = 0.4,
                  timeout: float = 30.0, max_push_seconds: float = 1.0, max_events: int = 0,
-                 cuda_stream: Optional[int] = None):
+                 cuda_stream: Optional[int] = None, overlap: bool = False):
         if n_streams < 1:
             raise ValueError("n_streams must be at least 1")
         if buffer_seconds <= 0:
@@ -52,6 +52,10 @@ class WakeWordBank:
                                 max_events=max_events or max(4096, 2 * n_streams))
         if cuda_stream is not None:
             self.ctx.set_cuda_stream(cuda_stream)
+        if overlap:
+            # level-2 matching on a second stream beside the next push (include/ewk.h: ewk_set_overlap); work that the
+            # caller enqueues on `cuda_stream` after tick() and that reads the results must follow self.ctx.join()
+            self.ctx.set_overlap(True)
         self.templates = []
         for slot, t in enumerate(templates):
             audio = load_wav_16k(t) if isinstance(t, (str, bytes)) or hasattr(t, "__fspath__") else \

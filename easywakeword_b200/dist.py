@@ -88,6 +88,7 @@ class ShardedBank:
         self.bank.step(pcm_local, where)
 
     def gather(self):
+        self.bank.ctx.join()              # overlap mode: the records are complete once K3 has been joined
         return self.gatherer.gather()
 
     def poll_global(self):
