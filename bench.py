@@ -148,6 +148,21 @@ def cpu_throughput(seconds_per_stream, procs, fast, rounds=1):
     return tot_audio / tot_wall, tot_audio, tot_wall, events
 
 
+def cpu_dense_throughput(seconds=3.0):
+    """A9 on one host core: the oracle's per-hop `calculate_similarity` (SURVEY §8(d) CPU baseline (ii)) over
+    `seconds` of one synthetic stream.  Returns (audio-s/s, windows/s)."""
+    from easywakeword_b200 import synth
+    from oracle import ewk_oracle as O
+    word, _ = load_word()
+    x, _ = synth.stream(SEED0, RING_SECONDS + seconds, word, noise_sigma=0.002, gain=(1.0, 4.0))
+    x = synth.from_int16(synth.to_int16(x))
+    hops = np.arange(RING_SECONDS * 100, RING_SECONDS * 100 + int(seconds * 100))
+    t0 = time.perf_counter()
+    O.dense_scores(x, [word], hops)
+    dt = time.perf_counter() - t0
+    return seconds / dt, len(hops) / dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -192,6 +207,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # pinned staging memory is first-touched below: keep this rank on the CPUs next to its GPU (NUMA / PCIe root)
+    from easywakeword_b200.dist import bind_host_near_gpu
+    host_cpus = bind_host_near_gpu(local_rank) if world > 1 and not args.no_bind else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(3, args.warmup)
@@ -386,6 +404,11 @@ def run_ours(args):
                    "sample": f"{cores} processes x 3.0 s steady-state of one stream each, oracle in the reference's "
                              f"statement order; vectorised oracle variant: {vf:.1f} audio-s/s",
                    "vectorised_port_value": vf}
+        dense_cpu = None
+        if world == 1 and not args.no_cpu:
+            dv, dw = cpu_dense_throughput(3.0)
+            dense_cpu = {"value": dv, "unit": UNIT, "cores": 1, "kind": "port", "windows_per_s": dw,
+                         "sample": "300 hops (3.0 s) of one stream, oracle WordMatcher.calculate_similarity per hop"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -406,6 +429,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * STEP_SAMPLES * 2,
                     "d2h_bytes_per_step": int(8 + ev_per_step * 40), "ms_per_step": ms_e2e / K,
                     "h2d_gbs_per_gpu": n * STEP_SAMPLES * 2 / (ms_e2e / K * 1e-3) / 1e9,
+                    "host_cpus_rank0": (f"{host_cpus[0]}-{host_cpus[-1]} ({len(host_cpus)})" if host_cpus else None),
                     "bound": "host->device copy (PCIe): the PCM of a step is 131 MB per GPU and every step pays its own "
                              "copy; kernels take ~10 % of the step and overlap the next copy"},
             "gpu_launches": int(launches),
@@ -417,7 +441,8 @@ def run_ours(args):
                       "ms_per_step": ms_dense / dense_steps,
                       "kernel_ms": prof_dense["dense_score"]["ms"] / max(1, prof_dense["dense_score"]["launches"]),
                       "windows_per_s": n * 100 * world * dense_steps / (ms_dense * 1e-3),
-                      "hbm_frac": (n * STEP_SAMPLES * 2 + n * 400) * dense_steps / (ms_dense * 1e-3) / 1e9 / hbm_peak},
+                      "hbm_frac": (n * STEP_SAMPLES * 2 + n * 400) * dense_steps / (ms_dense * 1e-3) / 1e9 / hbm_peak,
+                      "cpu_baseline": dense_cpu},
             "level2_events_per_step": ev_per_step,
             "kernel_ms_per_step": {k: v["ms"] / max(1, K) for k, v in kern.items()},
         }
@@ -435,6 +460,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-bind", action="store_true", help="multi-GPU: do not pin each rank to the CPUs next to its GPU")
     ap.add_argument("--no-overlap", action="store_true",
                     help="keep K3 on the context's stream (default: ewk_set_overlap(1), K3 beside the next push)")
     args = ap.parse_args()
