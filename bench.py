@@ -232,6 +232,23 @@ def run_ours(args):
     overlap = not args.no_overlap
     ctx.set_overlap(overlap)
     gathered = torch.zeros(world * n, 2, dtype=torch.int32, device=dev) if world > 1 else None
+    # multi-GPU result exchange: the producing kernels store every record into all ranks' copies over NVLink
+    # (peer-mapped symmetric memory) and a step ends with a barrier behind K3; NCCL all-gather otherwise
+    exchange, exchange_note = None, None
+    if world > 1 and args.gather != "nccl":
+        try:
+            from easywakeword_b200.dist import PeerResultExchange
+            exchange = PeerResultExchange(world * n, world, rank, dev)
+        except Exception as e:                                      # no symmetric memory on this box
+            exchange_note = f"{type(e).__name__}: {e}"[:200]
+        ok = torch.tensor([1 if exchange is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            exchange = None
+            if args.gather == "peer":
+                raise SystemExit(f"bench.py: --gather peer requested but symmetric memory is unavailable: {exchange_note}")
+        else:
+            exchange.install(ctx)
 
     def slice_ptr(t, j, esz=2):
         return (t.data_ptr() + j * n * STEP_SAMPLES * esz, n, STEP_SAMPLES, STEP_SAMPLES)
@@ -257,8 +274,11 @@ def run_ours(args):
         if gathered is not None:
             if overlap and where == _lib.DEVICE and pushed[0] == step_no[0]:
                 push_next(where)                                    # next step's K1 goes beside this step's K3, ahead of the gather
-            ctx.join()                                              # the gather reads the records K3 writes
-            dist.all_gather_into_tensor(gathered, results)
+            if exchange is not None:
+                exchange.barrier(ctx)                               # behind K3 on its stream; the records are already everywhere
+            else:
+                ctx.join()                                          # the gather reads the records K3 writes
+                dist.all_gather_into_tensor(gathered, results)
         return bank.poll() if read_back else None
 
     # fill the rings (10 s) so that every stream is past is_buffer_full and thresholds are adaptive
@@ -284,6 +304,8 @@ def run_ours(args):
             if ev is not None:
                 n_ev += int((ev["kind"] == 2).sum())
         ctx.join()                                                  # the last step's K3 belongs to the timed region
+        if exchange is not None:
+            exchange.finish(stream)                                 # ... and so does its barrier
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -299,6 +321,43 @@ def run_ours(args):
     ms_dev, launches, _ = timed(_lib.DEVICE, False, K)          # inputs resident in HBM
     bank.poll()
     ms_e2e, _, n_events = timed(_lib.HOST, True, K)             # host PCM -> rings -> events on host
+
+    # the exchange on its own ("report gather latency separately"), and a self-check that the
+    # peer-published copy equals an NCCL all-gather of the local records
+    gather_info = None
+    if world > 1:
+        def per_call_us(fn, reps=50):
+            for _ in range(5):
+                fn()
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(reps):
+                fn()
+            g1.record(stream)
+            barrier()
+            t = torch.tensor([g0.elapsed_time(g1) * 1e3 / reps], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        ctx.join()
+        nccl_us = per_call_us(lambda: dist.all_gather_into_tensor(gathered, results))
+        gather_info = {"mode": "nccl all_gather per step", "bytes_per_rank": n * 8, "nccl_all_gather_us": nccl_us,
+                       "note": exchange_note}
+        if exchange is not None:
+            peer_us = per_call_us(lambda: exchange.hdl.barrier())
+            step(_lib.DEVICE, False)
+            ctx.join()
+            exchange.finish(stream)
+            barrier()
+            dist.all_gather_into_tensor(gathered, results)
+            torch.cuda.synchronize(dev)
+            same = bool(torch.equal(exchange.view(ctx.publish_parity()), gathered))
+            flag = torch.tensor([1 if same else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) != 1:
+                raise SystemExit("bench.py: peer-published records differ from the NCCL all-gather of the same step")
+            gather_info.update({"mode": "peer stores by K2/K3 over NVLink (symmetric memory) + one barrier per step behind K3",
+                                "peer_barrier_us": peer_us, "peer_copy_equals_nccl_all_gather": True})
 
     # per-kernel device time (CUDA events on the launching stream), same workload, separate loop; sequential order
     # (no overlap) so that every kernel is timed alone
@@ -423,8 +482,10 @@ def run_ours(args):
                                    "cp.async.bulk form); the timed region ends after the last K3 (ewk_join); per-kernel "
                                    "times are taken in sequential order, each kernel alone")
                        if overlap else "off: K1, K2, K3 in sequence on one stream",
-                       "parallelism": f"streams sharded {n}/GPU x {world}, all_gather of 8 B/stream results per step"
-                       if world > 1 else "1 GPU"},
+                       "parallelism": (f"streams sharded {n}/GPU x {world}, " +
+                                       ("8 B/stream result records stored by K2/K3 into every rank's copy over NVLink, "
+                                        "one barrier per step" if exchange is not None else
+                                        "all_gather of 8 B/stream results per step")) if world > 1 else "1 GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * STEP_SAMPLES * 2,
                     "d2h_bytes_per_step": int(8 + ev_per_step * 40), "ms_per_step": ms_e2e / K,
@@ -433,6 +494,7 @@ def run_ours(args):
                     "bound": "host->device copy (PCIe): the PCM of a step is 131 MB per GPU and every step pays its own "
                              "copy; kernels take ~10 % of the step and overlap the next copy"},
             "gpu_launches": int(launches),
+            "gather": gather_info,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "dense": {"what": "A9 per-hop scoring: 100 hops x 4096 streams per step, 4 FFT frames per hop (1 stream-grid + 3 "
@@ -460,6 +522,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
+                    help="multi-GPU result exchange: peer = K2/K3 store into every rank's copy over NVLink + barrier; "
+                         "nccl = all_gather per step; auto = peer when symmetric memory is available")
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU: do not pin each rank to the CPUs next to its GPU")
     ap.add_argument("--no-overlap", action="store_true",
                     help="keep K3 on the context's stream (default: ewk_set_overlap(1), K3 beside the next push)")

@@ -304,6 +304,9 @@ def _declare_stream_protos(lib):
         "ewk_prepare_segments": (C.c_int, [vp, i32, _p(C.c_int32), _p(i64), _p(i64), _p(i64), f32p, i64, i32]),
         "ewk_results_device_ptr": (C.c_int, [vp, _p(vp)]),
         "ewk_set_results_buffer": (C.c_int, [vp, vp]),
+        "ewk_set_results_peers": (C.c_int, [vp, _p(vp), i32, i64, i64]),
+        "ewk_publish_parity": (C.c_int, [vp]),
+        "ewk_match_stream": (C.c_int, [vp, _p(vp)]),
         "ewk_host_alloc": (C.c_int, [_p(vp), i64]),
         "ewk_host_free": (C.c_int, [vp]),
         "ewk_launch_count": (C.c_int64, [vp]),
@@ -464,6 +467,22 @@ def _bank_methods():
     def set_results_buffer(self, device_ptr):
         self._ck(self.lib.ewk_set_results_buffer(self.h, C.c_void_p(device_ptr)))
 
+    def set_results_peers(self, bases, stride_records=0, offset_records=0):
+        """Peer publication: K2 / K3 also store every result record at bases[p][parity * stride + offset + stream]
+        (device pointers, local or NVLink peer-mapped); an empty list switches it off."""
+        bases = list(bases)
+        arr = (C.c_void_p * max(1, len(bases)))(*[C.c_void_p(int(b)) for b in bases])
+        self._ck(self.lib.ewk_set_results_peers(self.h, arr, len(bases), int(stride_records), int(offset_records)))
+
+    def publish_parity(self):
+        return int(self.lib.ewk_publish_parity(self.h))
+
+    def match_stream(self):
+        """cudaStream_t (as int) the latest tick launched K3 on."""
+        p = C.c_void_p()
+        self._ck(self.lib.ewk_match_stream(self.h, C.byref(p)))
+        return p.value or 0
+
     def set_cuda_stream(self, handle):
         self._ck(self.lib.ewk_set_cuda_stream(self.h, C.c_void_p(handle)))
 
@@ -481,7 +500,7 @@ def _bank_methods():
         return {names[i]: {"ms": ms[i], "launches": int(n[i])} for i in range(len(names))}
 
     for f in (prepare_segments, dense_scores, profile, profile_read, set_stream_params, push, tick, poll, status, read_last, read_segment, results, results_device_ptr,
-              set_results_buffer, set_cuda_stream, launch_count):
+              set_results_buffer, set_results_peers, publish_parity, match_stream, set_cuda_stream, launch_count):
         setattr(Context, f.__name__, f)
 
 

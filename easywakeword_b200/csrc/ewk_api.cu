@@ -798,6 +798,10 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     // bulk staging of whole ticks pays when chunk arrays are small (frame_size 1600: 100 chunks)
     static const int stage_env = [] { const char* e = getenv("EWK_GATE_STAGE"); return e ? atoi(e) : 1; }();
     const int stage_bytes = (stage_env && smem_chunks <= 128 && !ctx->all_presummed) ? TICK * (B.fmt == 1 ? 2 : 4) : 0;
+    if (B.n_pub > 0) {                                    // this call's parity buffer at every destination
+        ctx->publish_parity = ctx->publish_parity == 0 ? 1 : 0;
+        B.pub_parity = ctx->publish_parity;
+    }
     cudaEvent_t pe = ctx->prof_begin(1);
     for (int done = 0; done < n_ticks; done += GATE_MAX_TICKS) {
         const int nt = std::min(GATE_MAX_TICKS, n_ticks - done);
@@ -819,6 +823,7 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         CK(cudaStreamWaitEvent(ctx->match_stream, ctx->ev_gate, 0));
         ks = ctx->match_stream;
     }
+    ctx->last_match_stream = ks;
     pe = ctx->prof_begin(2, ks);
     segment_queue_kernel<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ks>>>(
         ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
@@ -1116,6 +1121,40 @@ extern "C" int ewk_set_results_buffer(ewk_ctx* ctx, void* device_ptr) {
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->bank.results = dst;
     }
+    return EWK_OK;
+}
+
+extern "C" int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bases, int64_t stride_records, int64_t offset_records) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_set_results_peers");
+    if (rc) return rc;
+    BankView& B = ctx->bank;
+    if (n_bases < 0 || n_bases > MAX_PUB || (n_bases > 0 && !bases)) {
+        ctx->fail("ewk_set_results_peers: n_bases must be in [0, %d]", MAX_PUB);
+        return EWK_ERR_ARG;
+    }
+    if (n_bases > 0 && (offset_records < 0 || stride_records < offset_records + B.n_streams)) {
+        ctx->fail("ewk_set_results_peers: stride %lld cannot hold %d records at offset %lld",
+                  (long long)stride_records, B.n_streams, (long long)offset_records);
+        return EWK_ERR_ARG;
+    }
+    for (int p = 0; p < n_bases; p++)
+        if (!bases[p] || ((size_t)bases[p] & 7)) { ctx->fail("ewk_set_results_peers: destination %d is null or not 8-byte aligned", p); return EWK_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));                // kernels in flight keep the destinations they were launched with
+    for (int p = 0; p < MAX_PUB; p++) B.pub[p] = p < n_bases ? (StreamResult*)bases[p] : nullptr;
+    B.n_pub = n_bases;
+    B.pub_stride = n_bases ? stride_records : 0;
+    B.pub_off = n_bases ? offset_records : 0;
+    ctx->publish_parity = -1;
+    return EWK_OK;
+}
+
+extern "C" int ewk_publish_parity(const ewk_ctx* ctx) { return ctx ? ctx->publish_parity : -1; }
+
+extern "C" int ewk_match_stream(ewk_ctx* ctx, void** out) {
+    if (!ctx || !out) return EWK_ERR_ARG;
+    *out = (void*)(ctx->last_match_stream ? ctx->last_match_stream : ctx->stream);
     return EWK_OK;
 }
 

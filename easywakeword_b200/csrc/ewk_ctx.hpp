@@ -49,6 +49,8 @@ struct ewk_ctx {
     cudaStream_t match_stream = nullptr;
     cudaEvent_t ev_gate = nullptr, ev_match = nullptr;
     bool overlap = false, match_inflight = false;
+    int publish_parity = -1;                 // parity buffer of the latest ewk_tick's peer publication (-1: none yet)
+    cudaStream_t last_match_stream = nullptr;   // where the latest ewk_tick launched K3
     int join_match();
     int stage_idx = 0;
     struct Pending { bool valid = false; int slot = 0, stream0 = 0, n_streams = 0; long long n = 0; } pending;

@@ -75,6 +75,8 @@ struct StreamResult {       // dense per-stream record (what multi-GPU runs gath
     unsigned flags;         // bit0 matched(latest) | bit1 silent | bits2-3 state | bit4 event this call | bits 8.. event count
 };
 
+constexpr int MAX_PUB = 16;  // destinations of a peer publication (GPUs of one NVLink domain)
+
 struct BankView {
     void* ring;             // [n_streams][P]
     StreamState* st;
@@ -86,7 +88,21 @@ struct BankView {
     double* block_ss;       // [n_streams][NB]: sum of squares of absolute block b = a / 1600 at b % NB (written by K1)
     float* lm_ws;           // K3 log-mel workspace: [segment_queue CTAs][SEG_SMEM_FRAMES][LM_ROW]
     int n_streams, R, P, fmt, chunk_cap, max_events, NB;
+    // peer publication (ewk_set_results_peers): every record K2 / K3 write into `results` is also stored at
+    // pub[p] + pub_parity * pub_stride + pub_off + stream for each destination p — local or NVLink peer-mapped memory,
+    // so the multi-GPU "gather" is done by the producing kernels themselves.
+    StreamResult* pub[MAX_PUB];
+    int n_pub, pub_parity;
+    long long pub_stride, pub_off;
 };
+
+// One 8-byte store per destination (st.global.b64; remote destinations travel over NVLink as posted writes).
+__device__ __forceinline__ void publish_result(const BankView& B, int s, StreamResult r) {
+    const size_t at = (size_t)B.pub_parity * (size_t)B.pub_stride + (size_t)B.pub_off + (size_t)s;
+    const unsigned long long bits = ((unsigned long long)r.flags << 32) | (unsigned long long)__float_as_uint(r.score);
+    for (int p = 0; p < B.n_pub; p++)
+        *reinterpret_cast<volatile unsigned long long*>(B.pub[p] + at) = bits;
+}
 
 struct TraceView {          // optional per-tick trace for parity tests: [n_streams][n_ticks]
     unsigned char* silent;
@@ -815,6 +831,7 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
         r.flags = (r.flags & 1u) | (st.last_silent ? 2u : 0u) | ((unsigned)st.state << 2) | evflag |
                   ((unsigned)st.n_events << 8);
         B.results[s] = r;
+        publish_result(B, s, r);
     }
 }
 
@@ -922,6 +939,7 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
             res.score = best;
             res.flags = (res.flags & ~1u) | (unsigned)ok;
             B.results[e.stream] = res;
+            publish_result(B, e.stream, res);
         }
         r = next_s;
         __syncthreads();

@@ -126,3 +126,71 @@ def bind_host_near_gpu(device_index: int):
         return cpus
     except Exception:
         return None
+
+
+class PeerResultExchange:
+    """The result "gather" done by the producing kernels: every rank owns a symmetric buffer
+    int32 [2][world * pad][2] (two parity copies of the global record array) that all ranks of the NVLink domain map
+    (torch symmetric memory: CUDA VMM allocations whose handles are exchanged at rendezvous), and K2 / K3 of every
+    rank store each record they write straight into all of them (`ewk_set_results_peers`).  A step then needs only a
+    cross-GPU barrier — enqueued behind K3 on the stream K3 ran on, off the critical path of the next gate — instead
+    of an all-gather launch.  `view(parity)` is this rank's complete copy, global stream order when shards are equal
+    (`index` selects the valid rows otherwise, as in ResultGather)."""
+
+    def __init__(self, n_total: int, world: int, rank: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.torch = torch
+        self.n_total, self.world, self.rank = n_total, world, rank
+        self.first, self.last = shard_range(n_total, world, rank)
+        self.pad = padded_shard(n_total, world)
+        self.device = torch.device(device)
+        self.buf = symm.empty((2, world * self.pad, 2), dtype=torch.int32, device=self.device)
+        self.buf.zero_()
+        torch.cuda.synchronize(self.device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        if len(self.ptrs) != world or not all(self.ptrs):
+            raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+        idx = []
+        for r in range(world):
+            a, b = shard_range(n_total, world, r)
+            idx.extend(range(r * self.pad, r * self.pad + (b - a)))
+        self.index = torch.tensor(idx, dtype=torch.long, device=self.device)
+        self._ext = {}
+        self.last_stream = None
+
+    def install(self, ctx):
+        """Point the context's kernels at every rank's copy (this rank's included)."""
+        ctx.set_results_peers(self.ptrs, stride_records=self.world * self.pad, offset_records=self.rank * self.pad)
+
+    def barrier(self, ctx):
+        """All ranks' records of the latest tick are in every copy once this barrier has passed.  It is enqueued on the
+        stream the tick launched K3 on (the match stream in overlap mode), so the next push and gate do not wait for it."""
+        torch = self.torch
+        h = ctx.match_stream()
+        cur = torch.cuda.current_stream(self.device)
+        if not h or h == cur.cuda_stream:
+            s = cur
+        else:
+            s = self._ext.get(h)
+            if s is None:
+                s = self._ext[h] = torch.cuda.ExternalStream(h, device=self.device)
+        with torch.cuda.stream(s):
+            self.hdl.barrier()
+        self.last_stream = s
+        return s
+
+    def finish(self, stream=None):
+        """Make `stream` (default: the current one) wait for the latest barrier."""
+        if self.last_stream is not None:
+            (stream or self.torch.cuda.current_stream(self.device)).wait_stream(self.last_stream)
+
+    def view(self, parity: int):
+        """int32 [world * pad, 2] records of the tick call that published with `parity` (ctx.publish_parity())."""
+        return self.buf[parity]
+
+    def records(self, parity: int):
+        """-> int32 [n_total, 2] in global stream order."""
+        return self.buf[parity].index_select(0, self.index)

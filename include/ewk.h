@@ -233,6 +233,20 @@ int ewk_stream_results(ewk_ctx* ctx, ewk_stream_result* out);
  * caller-owned device buffer instead (e.g. a registered NCCL send buffer). */
 int ewk_results_device_ptr(ewk_ctx* ctx, void** out);
 int ewk_set_results_buffer(ewk_ctx* ctx, void* device_ptr);
+/* Peer publication — the multi-GPU "gather" done by the producing kernels (the reference's multiroom
+ * shape, examples/multiroom_async.py:14-35, has no exchange at all: N objects report to one host thread).
+ * bases[p], p < n_bases <= 16, are device pointers — local, or peer-mapped over NVLink (CUDA IPC / VMM /
+ * torch symmetric memory) — to arrays of 2 * stride_records ewk_stream_result.  After this call every record that
+ * K2 / K3 write into the results array is also stored, by the same kernel, at
+ *     bases[p][parity * stride_records + offset_records + stream]      for every p,
+ * where parity alternates 0, 1, 0, ... per ewk_tick call (ewk_publish_parity returns the one the latest call used),
+ * so a consumer reads a complete, stable copy of call i while call i + 1 is being produced.  The records are
+ * globally visible once the kernels of the call have completed on ewk_match_stream(); a cross-GPU barrier enqueued
+ * there (not an all-gather) is all a step needs.  n_bases = 0 switches publication off. */
+int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bases, int64_t stride_records, int64_t offset_records);
+int ewk_publish_parity(const ewk_ctx* ctx);
+/* The cudaStream_t the latest ewk_tick launched K3 on: the match stream in overlap mode, else the context's stream. */
+int ewk_match_stream(ewk_ctx* ctx, void** out);
 /* Pinned host memory for asynchronous pushes. */
 int ewk_host_alloc(void** out, int64_t bytes);
 int ewk_host_free(void* p);
