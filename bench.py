@@ -245,7 +245,7 @@ def run_ours(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             exchange = None
-            if args.gather == "peer":
+            if args.gather.startswith("peer"):
                 raise SystemExit(f"bench.py: --gather peer requested but symmetric memory is unavailable: {exchange_note}")
         else:
             exchange.install(ctx)
@@ -275,7 +275,10 @@ def run_ours(args):
             if overlap and where == _lib.DEVICE and pushed[0] == step_no[0]:
                 push_next(where)                                    # next step's K1 goes beside this step's K3, ahead of the gather
             if exchange is not None:
-                exchange.barrier(ctx)                               # behind K3 on its stream; the records are already everywhere
+                if args.gather == "peer-barrier":
+                    exchange.barrier(ctx)                           # lock step: a barrier behind K3 on its stream
+                # default: nothing to do — K2/K3 stored the records into every rank's copy and K3 releases the step's
+                # sequence number into every rank's signal row when it is done
             else:
                 ctx.join()                                          # the gather reads the records K3 writes
                 dist.all_gather_into_tensor(gathered, results)
@@ -305,7 +308,10 @@ def run_ours(args):
                 n_ev += int((ev["kind"] == 2).sum())
         ctx.join()                                                  # the last step's K3 belongs to the timed region
         if exchange is not None:
-            exchange.finish(stream)                                 # ... and so does its barrier
+            if args.gather == "peer-barrier":
+                exchange.finish(stream)                             # ... and so does its barrier
+            else:
+                exchange.wait(ctx)                                  # ... and so does the arrival of every rank's last step
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -348,6 +354,10 @@ def run_ours(args):
             step(_lib.DEVICE, False)
             ctx.join()
             exchange.finish(stream)
+            exchange.wait(ctx)
+            seqs, timed_out = exchange.published(ctx)
+            if timed_out or not (seqs == ctx.publish_seq()).all():
+                raise SystemExit(f"bench.py: peer signals incomplete: {seqs.tolist()} vs {ctx.publish_seq()} (timed out: {timed_out})")
             barrier()
             dist.all_gather_into_tensor(gathered, results)
             torch.cuda.synchronize(dev)
@@ -356,8 +366,12 @@ def run_ours(args):
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()) != 1:
                 raise SystemExit("bench.py: peer-published records differ from the NCCL all-gather of the same step")
-            gather_info.update({"mode": "peer stores by K2/K3 over NVLink (symmetric memory) + one barrier per step behind K3",
-                                "peer_barrier_us": peer_us, "peer_copy_equals_nccl_all_gather": True})
+            gather_info.update({"mode": ("peer stores by K2/K3 over NVLink (symmetric memory) + one barrier per step behind K3"
+                                         if args.gather == "peer-barrier" else
+                                         "put-with-signal: K2/K3 store the records, K3's last CTA releases the step's sequence "
+                                         "number, into every rank's copy over NVLink (symmetric memory); no collective, no "
+                                         "per-step barrier; the timed region ends with a device-side wait for every rank's last step"),
+                                "symm_barrier_us": peer_us, "peer_copy_equals_nccl_all_gather": True})
 
     # per-kernel device time (CUDA events on the launching stream), same workload, separate loop; sequential order
     # (no overlap) so that every kernel is timed alone
@@ -483,8 +497,9 @@ def run_ours(args):
                                    "times are taken in sequential order, each kernel alone")
                        if overlap else "off: K1, K2, K3 in sequence on one stream",
                        "parallelism": (f"streams sharded {n}/GPU x {world}, " +
-                                       ("8 B/stream result records stored by K2/K3 into every rank's copy over NVLink, "
-                                        "one barrier per step" if exchange is not None else
+                                       ("8 B/stream result records + completion signal stored by K2/K3 into every rank's copy "
+                                        "over NVLink" + (", one barrier per step" if args.gather == "peer-barrier" else
+                                                         " (put-with-signal, no collective)") if exchange is not None else
                                         "all_gather of 8 B/stream results per step")) if world > 1 else "1 GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * STEP_SAMPLES * 2,
@@ -522,9 +537,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
-                    help="multi-GPU result exchange: peer = K2/K3 store into every rank's copy over NVLink + barrier; "
-                         "nccl = all_gather per step; auto = peer when symmetric memory is available")
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "peer-barrier", "nccl"],
+                    help="multi-GPU result exchange: peer = K2/K3 store records and a completion signal into every rank's "
+                         "copy over NVLink (no collective, no per-step barrier); peer-barrier = same stores, one "
+                         "symmetric-memory barrier per step; nccl = all_gather per step; auto = peer when symmetric "
+                         "memory is available")
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU: do not pin each rank to the CPUs next to its GPU")
     ap.add_argument("--no-overlap", action="store_true",
                     help="keep K3 on the context's stream (default: ewk_set_overlap(1), K3 beside the next push)")

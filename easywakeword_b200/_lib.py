@@ -304,8 +304,11 @@ def _declare_stream_protos(lib):
         "ewk_prepare_segments": (C.c_int, [vp, i32, _p(C.c_int32), _p(i64), _p(i64), _p(i64), f32p, i64, i32]),
         "ewk_results_device_ptr": (C.c_int, [vp, _p(vp)]),
         "ewk_set_results_buffer": (C.c_int, [vp, vp]),
-        "ewk_set_results_peers": (C.c_int, [vp, _p(vp), i32, i64, i64]),
+        "ewk_set_results_peers": (C.c_int, [vp, _p(vp), i32, i64, i64, _p(vp), i32]),
         "ewk_publish_parity": (C.c_int, [vp]),
+        "ewk_publish_seq": (C.c_int64, [vp]),
+        "ewk_wait_published": (C.c_int, [vp, i32, i64, i32]),
+        "ewk_published_seq": (C.c_int, [vp, i32, _p(C.c_uint64), i32]),
         "ewk_match_stream": (C.c_int, [vp, _p(vp)]),
         "ewk_host_alloc": (C.c_int, [_p(vp), i64]),
         "ewk_host_free": (C.c_int, [vp]),
@@ -467,15 +470,37 @@ def _bank_methods():
     def set_results_buffer(self, device_ptr):
         self._ck(self.lib.ewk_set_results_buffer(self.h, C.c_void_p(device_ptr)))
 
-    def set_results_peers(self, bases, stride_records=0, offset_records=0):
+    def set_results_peers(self, bases, stride_records=0, offset_records=0, signals=None, slot=0):
         """Peer publication: K2 / K3 also store every result record at bases[p][parity * stride + offset + stream]
-        (device pointers, local or NVLink peer-mapped); an empty list switches it off."""
+        (device pointers, local or NVLink peer-mapped); `signals[p]` (uint64 [2][16] per destination) additionally get
+        the call's sequence number in `slot` when K3 is done.  An empty list switches it off."""
         bases = list(bases)
         arr = (C.c_void_p * max(1, len(bases)))(*[C.c_void_p(int(b)) for b in bases])
-        self._ck(self.lib.ewk_set_results_peers(self.h, arr, len(bases), int(stride_records), int(offset_records)))
+        sig = None
+        if signals is not None:
+            signals = list(signals)
+            if len(signals) != len(bases):
+                raise ValueError("one signal row per destination")
+            sig = (C.c_void_p * max(1, len(signals)))(*[C.c_void_p(int(b)) for b in signals])
+        self._ck(self.lib.ewk_set_results_peers(self.h, arr, len(bases), int(stride_records), int(offset_records), sig, int(slot)))
 
     def publish_parity(self):
         return int(self.lib.ewk_publish_parity(self.h))
+
+    def publish_seq(self):
+        return int(self.lib.ewk_publish_seq(self.h))
+
+    def wait_published(self, n_slots, seq, timeout_ms=2000):
+        """Enqueue (context's stream) a bounded device-side wait for the records of call `seq` from slots [0, n_slots)."""
+        self._ck(self.lib.ewk_wait_published(self.h, int(n_slots), int(seq), int(timeout_ms)))
+
+    def published_seq(self, parity, n_slots):
+        """-> (uint64 [n_slots] sequence numbers in this context's own signal row, timed_out flag)."""
+        out = np.zeros(n_slots, np.uint64)
+        rc = self.lib.ewk_published_seq(self.h, int(parity), out.ctypes.data_as(_p(C.c_uint64)), int(n_slots))
+        if rc < 0:
+            self._ck(rc)
+        return out, bool(rc)
 
     def match_stream(self):
         """cudaStream_t (as int) the latest tick launched K3 on."""
@@ -500,7 +525,7 @@ def _bank_methods():
         return {names[i]: {"ms": ms[i], "launches": int(n[i])} for i in range(len(names))}
 
     for f in (prepare_segments, dense_scores, profile, profile_read, set_stream_params, push, tick, poll, status, read_last, read_segment, results, results_device_ptr,
-              set_results_buffer, set_results_peers, publish_parity, match_stream, set_cuda_stream, launch_count):
+              set_results_buffer, set_results_peers, publish_parity, publish_seq, wait_published, published_seq, match_stream, set_cuda_stream, launch_count):
         setattr(Context, f.__name__, f)
 
 

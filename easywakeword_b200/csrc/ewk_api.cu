@@ -163,6 +163,7 @@ void ewk_ctx::release() {
     for (auto& kv : rs_tables) if (kv.second.H) cudaFree(kv.second.H);
     rs_tables.clear();
     b_rs_in.free(); b_rs_out.free();
+    if (d_wait_flag) { cudaFree(d_wait_flag); d_wait_flag = nullptr; }
     if (d_tables) cudaFree(d_tables);
     if (d_tmpl) cudaFree(d_tmpl);
     if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
@@ -798,9 +799,10 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     // bulk staging of whole ticks pays when chunk arrays are small (frame_size 1600: 100 chunks)
     static const int stage_env = [] { const char* e = getenv("EWK_GATE_STAGE"); return e ? atoi(e) : 1; }();
     const int stage_bytes = (stage_env && smem_chunks <= 128 && !ctx->all_presummed) ? TICK * (B.fmt == 1 ? 2 : 4) : 0;
-    if (B.n_pub > 0) {                                    // this call's parity buffer at every destination
-        ctx->publish_parity = ctx->publish_parity == 0 ? 1 : 0;
-        B.pub_parity = ctx->publish_parity;
+    if (B.n_pub > 0) {                                    // this call's sequence number and parity buffer at every destination
+        ctx->publish_seq++;
+        B.pub_seq = (unsigned long long)ctx->publish_seq;
+        B.pub_parity = (int)((ctx->publish_seq - 1) & 1);
     }
     cudaEvent_t pe = ctx->prof_begin(1);
     for (int done = 0; done < n_ticks; done += GATE_MAX_TICKS) {
@@ -1124,7 +1126,8 @@ extern "C" int ewk_set_results_buffer(ewk_ctx* ctx, void* device_ptr) {
     return EWK_OK;
 }
 
-extern "C" int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bases, int64_t stride_records, int64_t offset_records) {
+extern "C" int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bases, int64_t stride_records, int64_t offset_records,
+                                     void* const* signals, int slot) {
     if (!ctx) return EWK_ERR_ARG;
     int rc = need_streams(ctx, "ewk_set_results_peers");
     if (rc) return rc;
@@ -1138,19 +1141,68 @@ extern "C" int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bas
                   (long long)stride_records, B.n_streams, (long long)offset_records);
         return EWK_ERR_ARG;
     }
-    for (int p = 0; p < n_bases; p++)
+    if (n_bases > 0 && signals && (slot < 0 || slot >= n_bases)) {
+        ctx->fail("ewk_set_results_peers: slot %d outside [0, %d)", slot, n_bases);
+        return EWK_ERR_ARG;
+    }
+    for (int p = 0; p < n_bases; p++) {
         if (!bases[p] || ((size_t)bases[p] & 7)) { ctx->fail("ewk_set_results_peers: destination %d is null or not 8-byte aligned", p); return EWK_ERR_ARG; }
+        if (signals && (!signals[p] || ((size_t)signals[p] & 7))) { ctx->fail("ewk_set_results_peers: signal row %d is null or not 8-byte aligned", p); return EWK_ERR_ARG; }
+    }
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));                // kernels in flight keep the destinations they were launched with
-    for (int p = 0; p < MAX_PUB; p++) B.pub[p] = p < n_bases ? (StreamResult*)bases[p] : nullptr;
+    for (int p = 0; p < MAX_PUB; p++) {
+        B.pub[p] = p < n_bases ? (StreamResult*)bases[p] : nullptr;
+        B.pub_sig[p] = (p < n_bases && signals) ? (unsigned long long*)signals[p] : nullptr;
+    }
     B.n_pub = n_bases;
     B.pub_stride = n_bases ? stride_records : 0;
     B.pub_off = n_bases ? offset_records : 0;
-    ctx->publish_parity = -1;
+    B.pub_slot = n_bases && signals ? slot : 0;
+    B.pub_seq = 0;
+    B.pub_parity = 0;
+    ctx->publish_seq = 0;
+    if (n_bases && signals && !ctx->d_wait_flag) {
+        CK(cudaMalloc(&ctx->d_wait_flag, sizeof(int)));
+        CK(cudaMemsetAsync(ctx->d_wait_flag, 0, sizeof(int), ctx->stream));
+    }
     return EWK_OK;
 }
 
-extern "C" int ewk_publish_parity(const ewk_ctx* ctx) { return ctx ? ctx->publish_parity : -1; }
+extern "C" int ewk_publish_parity(const ewk_ctx* ctx) { return ctx && ctx->publish_seq > 0 ? (int)((ctx->publish_seq - 1) & 1) : -1; }
+extern "C" int64_t ewk_publish_seq(const ewk_ctx* ctx) { return ctx ? ctx->publish_seq : 0; }
+
+extern "C" int ewk_wait_published(ewk_ctx* ctx, int n_slots, int64_t seq, int timeout_ms) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_wait_published", false);
+    if (rc) return rc;
+    BankView& B = ctx->bank;
+    if (!B.n_pub || !B.pub_sig[0]) { ctx->fail("ewk_wait_published: no signal rows installed (ewk_set_results_peers)"); return EWK_ERR_STATE; }
+    if (n_slots < 1 || n_slots > B.n_pub || seq < 1 || timeout_ms < 1) { ctx->fail("ewk_wait_published: bad arguments"); return EWK_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    const unsigned long long* row = B.pub_sig[B.pub_slot] + (size_t)((seq - 1) & 1) * MAX_PUB;
+    peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(row, n_slots, (unsigned long long)seq, (unsigned long long)timeout_ms * 1000000ULL,
+                                                ctx->d_wait_flag);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return EWK_OK;
+}
+
+extern "C" int ewk_published_seq(ewk_ctx* ctx, int parity, uint64_t* out, int n_slots) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_published_seq", false);
+    if (rc) return rc;
+    BankView& B = ctx->bank;
+    if (!B.n_pub || !B.pub_sig[0]) { ctx->fail("ewk_published_seq: no signal rows installed (ewk_set_results_peers)"); return EWK_ERR_STATE; }
+    if (!out || n_slots < 1 || n_slots > MAX_PUB || parity < 0 || parity > 1) { ctx->fail("ewk_published_seq: bad arguments"); return EWK_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    int flag = 0;
+    CK(cudaMemcpyAsync(out, B.pub_sig[B.pub_slot] + (size_t)parity * MAX_PUB, sizeof(uint64_t) * (size_t)n_slots, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&flag, ctx->d_wait_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_wait_flag, 0, sizeof(int), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return flag ? 1 : 0;
+}
 
 extern "C" int ewk_match_stream(ewk_ctx* ctx, void** out) {
     if (!ctx || !out) return EWK_ERR_ARG;

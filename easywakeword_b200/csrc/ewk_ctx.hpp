@@ -49,7 +49,8 @@ struct ewk_ctx {
     cudaStream_t match_stream = nullptr;
     cudaEvent_t ev_gate = nullptr, ev_match = nullptr;
     bool overlap = false, match_inflight = false;
-    int publish_parity = -1;                 // parity buffer of the latest ewk_tick's peer publication (-1: none yet)
+    long long publish_seq = 0;               // ewk_tick calls since ewk_set_results_peers (peer publication); parity = (seq - 1) & 1
+    int* d_wait_flag = nullptr;              // set by peer_wait_kernel when it gave up
     cudaStream_t last_match_stream = nullptr;   // where the latest ewk_tick launched K3
     int join_match();
     int stage_idx = 0;

@@ -94,6 +94,12 @@ struct BankView {
     StreamResult* pub[MAX_PUB];
     int n_pub, pub_parity;
     long long pub_stride, pub_off;
+    // completion signals (optional): when the last K3 CTA of a tick call is done it stores the call's sequence number
+    // at pub_sig[p][pub_parity * MAX_PUB + pub_slot] of every destination — a put-with-signal: a consumer that sees
+    // sequence q in slot r of its own copy holds all records of rank r up to call q
+    unsigned long long* pub_sig[MAX_PUB];
+    unsigned long long pub_seq;
+    int pub_slot;
 };
 
 // One 8-byte store per destination (st.global.b64; remote destinations travel over NVLink as posted writes).
@@ -945,12 +951,40 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
         __syncthreads();
     }
     if (tid == 0) {
-        __threadfence();
+        if (B.n_pub) __threadfence_system(); else __threadfence();      // this CTA's (peer) record stores before its arrival
         if (atomicAdd(B.ev_count + 4, 1) == (int)gridDim.x - 1) {       // every other CTA has read the counters
             B.ev_count[3] = n;
             B.ev_count[2] = 0;
             B.ev_count[4] = 0;
+            if (B.n_pub && B.pub_sig[0]) {
+                // every CTA's records precede its arrival, every arrival precedes this point; K2's records were complete
+                // when this kernel started.  Release the call's sequence number to every destination.
+                __threadfence_system();
+                for (int p = 0; p < B.n_pub; p++) {
+                    unsigned long long* sg = B.pub_sig[p] + (size_t)B.pub_parity * MAX_PUB + B.pub_slot;
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(sg), "l"(B.pub_seq) : "memory");
+                }
+            }
         }
+    }
+}
+
+// Device-side consumer gate for peer publication: returns once slots [0, n_slots) of the local signal row hold a sequence
+// number >= seq (all records of those ranks up to that call have landed), or after timeout_ns (then *timed_out = 1):
+// it can never hang the device.  One warp, lane p watches slot p.
+__global__ void peer_wait_kernel(const unsigned long long* __restrict__ sig_row, int n_slots, unsigned long long seq,
+                                 unsigned long long timeout_ns, int* timed_out) {
+    const int p = threadIdx.x;
+    if (p >= n_slots) return;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(sig_row + p) : "memory");
+        if (v >= seq) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) { atomicExch(timed_out, 1); break; }
+        __nanosleep(256);
     }
 }
 

@@ -129,30 +129,39 @@ def bind_host_near_gpu(device_index: int):
 
 
 class PeerResultExchange:
-    """The result "gather" done by the producing kernels: every rank owns a symmetric buffer
-    int32 [2][world * pad][2] (two parity copies of the global record array) that all ranks of the NVLink domain map
-    (torch symmetric memory: CUDA VMM allocations whose handles are exchanged at rendezvous), and K2 / K3 of every
-    rank store each record they write straight into all of them (`ewk_set_results_peers`).  A step then needs only a
-    cross-GPU barrier — enqueued behind K3 on the stream K3 ran on, off the critical path of the next gate — instead
-    of an all-gather launch.  `view(parity)` is this rank's complete copy, global stream order when shards are equal
-    (`index` selects the valid rows otherwise, as in ResultGather)."""
+    """The result "gather" done by the producing kernels: every rank owns a symmetric buffer — two parity copies of the
+    global record array, int32 [2][world * pad][2], plus a signal row uint64 [2][16] — that all ranks of the NVLink
+    domain map (torch symmetric memory: CUDA VMM allocations whose handles are exchanged at rendezvous).  K2 / K3 of
+    every rank store each record they write straight into all copies, and the last K3 CTA of a tick call releases the
+    call's sequence number into slot `rank` of every signal row (`ewk_set_results_peers`): a put-with-signal.  No
+    all-gather and no per-step barrier: a consumer that needs call q of every rank waits for the signals
+    (`wait(ctx)` on the device, `published(ctx)` from the host).  `barrier(ctx)` is the lock-step alternative.
+    `view(parity)` is this rank's copy; `records(parity)` selects the valid rows in global stream order."""
+
+    SIG = 16                                   # ewk::MAX_PUB slots per signal row
 
     def __init__(self, n_total: int, world: int, rank: int, device, group=None):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
+        if world > self.SIG:
+            raise ValueError(f"peer publication supports up to {self.SIG} ranks")
         self.torch = torch
         self.n_total, self.world, self.rank = n_total, world, rank
         self.first, self.last = shard_range(n_total, world, rank)
         self.pad = padded_shard(n_total, world)
+        self.stride = world * self.pad
         self.device = torch.device(device)
-        self.buf = symm.empty((2, world * self.pad, 2), dtype=torch.int32, device=self.device)
-        self.buf.zero_()
+        self.raw = symm.empty((2 * self.stride + 2 * self.SIG,), dtype=torch.int64, device=self.device)
+        self.raw.zero_()
         torch.cuda.synchronize(self.device)
-        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.hdl = symm.rendezvous(self.raw, group if group is not None else dist.group.WORLD)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         if len(self.ptrs) != world or not all(self.ptrs):
             raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+        self.sig_ptrs = [p + 2 * self.stride * 8 for p in self.ptrs]
+        self.buf = self.raw[:2 * self.stride].view(torch.int32).view(2, self.stride, 2)
+        self.sig = self.raw[2 * self.stride:].view(2, self.SIG)
         idx = []
         for r in range(world):
             a, b = shard_range(n_total, world, r)
@@ -162,12 +171,27 @@ class PeerResultExchange:
         self.last_stream = None
 
     def install(self, ctx):
-        """Point the context's kernels at every rank's copy (this rank's included)."""
-        ctx.set_results_peers(self.ptrs, stride_records=self.world * self.pad, offset_records=self.rank * self.pad)
+        """Point the context's kernels at every rank's copy (this rank's included) and start a new sequence."""
+        self.raw[2 * self.stride:].zero_()
+        self.torch.cuda.synchronize(self.device)
+        self.hdl.barrier()                     # nobody publishes into a signal row that is still being cleared
+        self.torch.cuda.synchronize(self.device)
+        ctx.set_results_peers(self.ptrs, stride_records=self.stride, offset_records=self.rank * self.pad,
+                              signals=self.sig_ptrs, slot=self.rank)
+
+    def wait(self, ctx, seq=None, timeout_ms=2000):
+        """Enqueue on the context's stream a (bounded) wait until every rank's records of call `seq` (default: this
+        rank's latest) are in this rank's copy."""
+        ctx.wait_published(self.world, ctx.publish_seq() if seq is None else seq, timeout_ms)
+
+    def published(self, ctx, parity=None):
+        """Host read: sequence number each rank has completed in the given parity copy (default: the latest)."""
+        par = ctx.publish_parity() if parity is None else parity
+        return ctx.published_seq(par, self.world)
 
     def barrier(self, ctx):
-        """All ranks' records of the latest tick are in every copy once this barrier has passed.  It is enqueued on the
-        stream the tick launched K3 on (the match stream in overlap mode), so the next push and gate do not wait for it."""
+        """Lock-step alternative to the signals: a symmetric-memory barrier enqueued on the stream the tick launched K3
+        on (the match stream in overlap mode), so the next push and gate do not wait for it."""
         torch = self.torch
         h = ctx.match_stream()
         cur = torch.cuda.current_stream(self.device)

@@ -239,12 +239,26 @@ int ewk_set_results_buffer(ewk_ctx* ctx, void* device_ptr);
  * torch symmetric memory) — to arrays of 2 * stride_records ewk_stream_result.  After this call every record that
  * K2 / K3 write into the results array is also stored, by the same kernel, at
  *     bases[p][parity * stride_records + offset_records + stream]      for every p,
- * where parity alternates 0, 1, 0, ... per ewk_tick call (ewk_publish_parity returns the one the latest call used),
- * so a consumer reads a complete, stable copy of call i while call i + 1 is being produced.  The records are
- * globally visible once the kernels of the call have completed on ewk_match_stream(); a cross-GPU barrier enqueued
- * there (not an all-gather) is all a step needs.  n_bases = 0 switches publication off. */
-int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bases, int64_t stride_records, int64_t offset_records);
+ * where the k-th ewk_tick call after this one (k = 1, 2, ...; ewk_publish_seq returns the latest k) uses
+ * parity = (k - 1) & 1 (ewk_publish_parity), so a consumer reads a complete, stable copy of call k while call k + 1
+ * is being produced.
+ * signals (optional, may be NULL): signals[p] points to uint64_t[2][16] at destination p.  When K3 of call k has
+ * finished, its last CTA stores k at signals[p][parity][slot] for every p with release semantics at system scope
+ * (a put-with-signal): whoever reads k in slot r of its own copy holds every record rank r published up to call k.
+ * bases[slot] / signals[slot] must be this context's own copy (ewk_wait_published / ewk_published_seq read it).
+ * Without signals the records are globally visible once the kernels of the call have completed on ewk_match_stream()
+ * and a cross-GPU barrier enqueued there does the job.  n_bases = 0 switches publication off. */
+int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bases, int64_t stride_records, int64_t offset_records,
+                          void* const* signals, int slot);
 int ewk_publish_parity(const ewk_ctx* ctx);
+int64_t ewk_publish_seq(const ewk_ctx* ctx);
+/* Enqueue, on the context's stream, a wait until slots [0, n_slots) of the local signal row of call `seq` hold a
+ * value >= seq — everything enqueued afterwards sees all those ranks' records of that call.  The wait gives up after
+ * timeout_ms (it never hangs the device); ewk_published_seq then shows which slot is behind. */
+int ewk_wait_published(ewk_ctx* ctx, int n_slots, int64_t seq, int timeout_ms);
+/* Synchronous read of the local signal row of `parity`: out[0 .. n_slots).  Returns 1 if an earlier
+ * ewk_wait_published timed out since the last call of this function, else 0 (negative: error). */
+int ewk_published_seq(ewk_ctx* ctx, int parity, uint64_t* out, int n_slots);
 /* The cudaStream_t the latest ewk_tick launched K3 on: the match stream in overlap mode, else the context's stream. */
 int ewk_match_stream(ewk_ctx* ctx, void** out);
 /* Pinned host memory for asynchronous pushes. */

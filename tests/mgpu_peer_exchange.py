@@ -30,7 +30,7 @@ def main():
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     checked = 0
-    for overlap in (False, True):
+    for overlap, lockstep in ((False, False), (True, False), (True, True)):
         bank = WakeWordBank(ex.last - ex.first, [word], device=local, buffer_seconds=5, speech_duration_min=0.5,
                             speech_duration_max=1.6, cuda_stream=stream.cuda_stream)
         ctx = bank.ctx
@@ -39,13 +39,18 @@ def main():
         ex.install(ctx)
         for b in range(0, mine.shape[1], 16000):
             bank.step(np.ascontiguousarray(mine[:, b:b + 16000]))
-            ex.barrier(ctx)
-            ex.finish(stream)
+            if lockstep:                                      # symmetric-memory barrier behind K3
+                ex.barrier(ctx)
+                ex.finish(stream)
+            else:                                             # put-with-signal: wait for every rank's sequence number
+                ex.wait(ctx)
+                seqs, timed_out = ex.published(ctx)
+                assert not timed_out and (seqs == ctx.publish_seq()).all(), (seqs, ctx.publish_seq())
             ctx.join()
             ref = ga.gather()                                 # NCCL all-gather of the local records
             got = ex.records(ctx.publish_parity())
             torch.cuda.synchronize(dev)
-            assert torch.equal(got, ref), f"rank {rank} overlap {overlap} step {b // 16000}"
+            assert torch.equal(got, ref), f"rank {rank} overlap {overlap} lockstep {lockstep} step {b // 16000}"
             checked += 1
         scored = int(((ref[:, 1] >> 8) > 0).sum())
         assert scored > 5, scored

@@ -20,17 +20,25 @@ def test_published_copies_equal_results(word, overlap):
     n, stride, off = 24, 64, 17
     pcm16 = stream_batch(5100, n, 20.0, word, distractor_prob=0.3)
     dests = [torch.full((2, stride, 2), -7, dtype=torch.int32, device="cuda:0") for _ in range(2)]
+    sigs = [torch.zeros(2, 16, dtype=torch.int64, device="cuda:0") for _ in range(2)]
     bank = WakeWordBank(n, [word], device=0, buffer_seconds=5, speech_duration_min=0.5, speech_duration_max=1.6)
     ctx = bank.ctx
     try:
         ctx.set_overlap(overlap)
         assert ctx.publish_parity() == -1
-        ctx.set_results_peers([d.data_ptr() for d in dests], stride_records=stride, offset_records=off)
+        ctx.set_results_peers([d.data_ptr() for d in dests], stride_records=stride, offset_records=off,
+                              signals=[g.data_ptr() for g in sigs], slot=0)
+        assert ctx.publish_parity() == -1 and ctx.publish_seq() == 0
         prev, n_scored = None, 0
         for i, b in enumerate(range(0, pcm16.shape[1], 16000)):
             bank.step(np.ascontiguousarray(pcm16[:, b:b + 16000]))
             par = ctx.publish_parity()
-            assert par == i % 2
+            assert par == i % 2 and ctx.publish_seq() == i + 1
+            ctx.wait_published(1, i + 1)                       # device-side gate on the own slot: K3's completion signal
+            seqs, timed_out = ctx.published_seq(par, 2)
+            assert not timed_out and seqs.tolist() == [i + 1, 0]
+            for g in sigs:                                     # both destinations got the signal, in this call's row only
+                assert g.cpu().numpy()[par].tolist() == [i + 1] + [0] * 15
             res = ctx.results()                                # joins K3 and synchronises
             raw = res.view(np.int32).reshape(n, 2)
             for d in dests:
@@ -42,6 +50,12 @@ def test_published_copies_equal_results(word, overlap):
             prev = raw.copy()
             n_scored += int((res["flags"] & 16 != 0).sum())
         assert n_scored > 5                                    # K3 published scored records, not only K2 flags
+        # nobody ever writes slot 1: a wait that includes it gives up after its timeout instead of hanging the device
+        ctx.wait_published(2, ctx.publish_seq(), timeout_ms=30)
+        _, timed_out = ctx.published_seq(ctx.publish_parity(), 2)
+        assert timed_out
+        _, timed_out = ctx.published_seq(ctx.publish_parity(), 2)
+        assert not timed_out                                   # the flag is cleared by the read
         # switching it off stops the stores
         ctx.set_results_peers([])
         for d in dests:
@@ -66,7 +80,11 @@ def test_publish_argument_errors(word):
         ctx.set_results_peers([buf.data_ptr() + 4], stride_records=8, offset_records=0)  # misaligned
     with pytest.raises(Exception):
         ctx.set_results_peers([buf.data_ptr()] * 17, stride_records=8, offset_records=0)
+    with pytest.raises(Exception):
+        ctx.set_results_peers([buf.data_ptr()], stride_records=8, offset_records=0, signals=[buf.data_ptr()], slot=1)
     ctx.set_results_peers([buf.data_ptr()], stride_records=8, offset_records=4)
+    with pytest.raises(Exception):
+        ctx.wait_published(1, 1)                               # no signal rows installed
     ctx.close()
 
 
