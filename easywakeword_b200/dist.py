@@ -74,21 +74,52 @@ class ResultGather:
 
 
 class ShardedBank:
-    """A WakeWordBank over the rank's shard of `n_total` streams plus the result gather."""
+    """A WakeWordBank over the rank's shard of `n_total` streams plus the result exchange.
 
-    def __init__(self, n_total: int, templates, *, world: int, rank: int, device: int, **bank_kwargs):
+    exchange="peer": K2 / K3 store the records and a completion signal into every rank's copy over NVLink
+    (PeerResultExchange; needs torch symmetric memory); "nccl": one all-gather per gather() call; "auto": peer when
+    available.  gather() returns int32 [n_total, 2] in global stream order either way."""
+
+    def __init__(self, n_total: int, templates, *, world: int, rank: int, device: int, exchange: str = "auto", **bank_kwargs):
         import torch
         from .bank import WakeWordBank
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
         self.first, self.last = shard_range(n_total, world, rank)
+        self.world = world
         self.bank = WakeWordBank(self.last - self.first, templates, device=device, **bank_kwargs)
-        self.gatherer = ResultGather(n_total, world, rank, device=torch.device("cuda", device))
+        dev = torch.device("cuda", device)
+        self.gatherer = ResultGather(n_total, world, rank, device=dev)
         self.bank.ctx.set_results_buffer(self.gatherer.local.data_ptr())
+        self.peer = None
+        if exchange != "nccl" and world > 1:
+            import torch.distributed as dist
+            try:
+                self.peer = PeerResultExchange(n_total, world, rank, dev)
+            except Exception:
+                if exchange == "peer":
+                    raise
+            ok = torch.tensor([1 if self.peer is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)           # every rank takes the same path
+            if int(ok.item()) == 0:
+                if exchange == "peer":
+                    raise RuntimeError("peer exchange unavailable on at least one rank")
+                self.peer = None
+            else:
+                self.peer.install(self.bank.ctx)
 
     def step(self, pcm_local, where=0):
         self.bank.step(pcm_local, where)
 
     def gather(self):
-        self.bank.ctx.join()              # overlap mode: the records are complete once K3 has been joined
+        ctx = self.bank.ctx
+        if self.peer is not None and ctx.publish_seq() > 0:
+            self.peer.wait(ctx)                                  # every rank's records of the latest call have landed
+            seqs, timed_out = self.peer.published(ctx)           # (synchronises the context's stream)
+            if timed_out:
+                raise TimeoutError(f"peer publication: ranks are at calls {seqs.tolist()}, expected {ctx.publish_seq()}")
+            return self.peer.records(ctx.publish_parity())
+        ctx.join()                        # overlap mode: the records are complete once K3 has been joined
         return self.gatherer.gather()
 
     def poll_global(self):
@@ -98,6 +129,8 @@ class ShardedBank:
         return ev
 
     def close(self):
+        if self.peer is not None:
+            self.bank.ctx.set_results_peers([])
         self.bank.close()
 
 

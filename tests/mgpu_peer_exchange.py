@@ -56,6 +56,21 @@ def main():
         assert scored > 5, scored
         ctx.set_results_peers([])
         bank.close()
+    # the packaged form: ShardedBank with either exchange returns the same global record array
+    from easywakeword_b200.dist import ShardedBank
+    outs = {}
+    for mode in ("nccl", "peer"):
+        sb = ShardedBank(n_total, [word], world=world, rank=rank, device=local, exchange=mode, buffer_seconds=5,
+                         speech_duration_min=0.5, speech_duration_max=1.6, cuda_stream=stream.cuda_stream, overlap=True)
+        assert (sb.peer is not None) == (mode == "peer")
+        got = []
+        for b in range(0, mine.shape[1], 16000):
+            sb.step(np.ascontiguousarray(mine[:, b:b + 16000]))
+            got.append(sb.gather().clone())
+            dist.barrier()                                    # a consumer that lags must not be overrun by two calls
+        outs[mode] = torch.stack(got)
+        sb.close()
+    assert torch.equal(outs["nccl"], outs["peer"])
     dist.barrier()
     if rank == 0:
         print(f"peer exchange ok: {checked} steps x {world} ranks identical to the all-gather")
