@@ -294,6 +294,8 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    by_rank = []                                                    # per timed() call: every rank's own device time and enqueue time
+
     def timed(where, read_back, steps):
         for _ in range(W):
             step(where, True)
@@ -302,10 +304,12 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_ev = 0
         e0.record(stream)
+        c0 = time.perf_counter()
         for _ in range(steps):
             ev = step(where, read_back)
             if ev is not None:
                 n_ev += int((ev["kind"] == 2).sum())
+        cpu_issue_ms = (time.perf_counter() - c0) * 1e3             # host time to enqueue the steps (not a result: a diagnostic)
         ctx.join()                                                  # the last step's K3 belongs to the timed region
         if exchange is not None:
             if args.gather == "peer-barrier":
@@ -315,7 +319,12 @@ def run_ours(args):
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
+        by_rank.append({"ms_per_step": [ms / steps], "host_enqueue_ms_per_step": [cpu_issue_ms / steps]})
         if world > 1:
+            allr = torch.zeros(world, 2, device=dev)
+            dist.all_gather_into_tensor(allr, torch.tensor([[ms / steps, cpu_issue_ms / steps]], device=dev))
+            by_rank[-1] = {"ms_per_step": [round(float(v), 5) for v in allr[:, 0]],
+                           "host_enqueue_ms_per_step": [round(float(v), 5) for v in allr[:, 1]]}
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
@@ -382,6 +391,16 @@ def run_ours(args):
     prof = ctx.profile_read()
     ctx.profile(False)
     bank.poll()
+    prof_nopub = None
+    if exchange is not None:
+        # what the peer stores cost the kernels: the same loop (the pool repeats every 10 steps) with publication off
+        ctx.set_results_peers([])
+        ctx.profile(True)
+        for _ in range(K):
+            step(_lib.DEVICE, False)
+        prof_nopub = ctx.profile_read()
+        ctx.profile(False)
+        bank.poll()
 
     # dense mode (A9): per-hop scoring of every stream, same push, K4 instead of K2/K3
     dense_out = torch.empty(n * 100, dtype=torch.float32, device=dev)
@@ -428,7 +447,7 @@ def run_ours(args):
         kern = {k: v for k, v in prof.items() if v["launches"]}
         tot_ms = sum(v["ms"] for v in kern.values()) or 1.0
         dom = max(kern, key=lambda k: kern[k]["ms"])
-        ev_per_step = n_events / max(1, K) / world
+        ev_per_step = n_events / max(1, K)                          # rank 0's own events (its 4096 streams)
         # ALGORITHMIC bytes per launch, one launch = one step of one rank:
         #  ring_push   (K1 fused): step PCM read once + written once into the rings + one 8-byte block sum per tick
         #  tick_gate   (K2): with K1's block sums it reads no PCM: 10 block sums + state in/out per stream;
@@ -509,6 +528,7 @@ def run_ours(args):
                     "bound": "host->device copy (PCIe): the PCM of a step is 131 MB per GPU and every step pays its own "
                              "copy; kernels take ~10 % of the step and overlap the next copy"},
             "gpu_launches": int(launches),
+            "by_rank": {"device_resident": by_rank[0], "e2e": by_rank[1]},
             "gather": gather_info,
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -522,6 +542,8 @@ def run_ours(args):
                       "cpu_baseline": dense_cpu},
             "level2_events_per_step": ev_per_step,
             "kernel_ms_per_step": {k: v["ms"] / max(1, K) for k, v in kern.items()},
+            "kernel_ms_per_step_without_publication": ({k: v["ms"] / max(1, K) for k, v in prof_nopub.items() if v["launches"]}
+                                                       if prof_nopub else None),
         }
         print(json.dumps(line), flush=True)
     bank.close()

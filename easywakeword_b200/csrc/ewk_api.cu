@@ -1161,6 +1161,7 @@ extern "C" int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bas
     B.pub_slot = n_bases && signals ? slot : 0;
     B.pub_seq = 0;
     B.pub_parity = 0;
+    { const char* e = getenv("EWK_PUB_CTA_FENCE"); B.pub_cta_fence_gpu = (e && !strcmp(e, "gpu")) ? 1 : 0; }
     ctx->publish_seq = 0;
     if (n_bases && signals && !ctx->d_wait_flag) {
         CK(cudaMalloc(&ctx->d_wait_flag, sizeof(int)));

@@ -100,14 +100,19 @@ struct BankView {
     unsigned long long* pub_sig[MAX_PUB];
     unsigned long long pub_seq;
     int pub_slot;
+    int pub_cta_fence_gpu;  // diagnostics (EWK_PUB_CTA_FENCE=gpu): per-CTA fence at device scope, only the signalling CTA at system scope
 };
 
-// One 8-byte store per destination (st.global.b64; remote destinations travel over NVLink as posted writes).
+// One 8-byte store per destination.  Plain (weak) stores on purpose: remote destinations travel over NVLink as posted
+// writes that pipeline behind each other — `volatile` stores are kept in order, each waiting ~1.5 us for the previous
+// one's acknowledgement, which cost K3 12-22 us per launch at 2-8 GPUs while the CTA waited for its thread 0.  What orders
+// them before the completion signal is the system-scope fence at the end of the CTA (segment_queue_kernel); kernel
+// completion does the same for K2.
 __device__ __forceinline__ void publish_result(const BankView& B, int s, StreamResult r) {
     const size_t at = (size_t)B.pub_parity * (size_t)B.pub_stride + (size_t)B.pub_off + (size_t)s;
     const unsigned long long bits = ((unsigned long long)r.flags << 32) | (unsigned long long)__float_as_uint(r.score);
     for (int p = 0; p < B.n_pub; p++)
-        *reinterpret_cast<volatile unsigned long long*>(B.pub[p] + at) = bits;
+        asm volatile("st.weak.global.b64 [%0], %1;" :: "l"(B.pub[p] + at), "l"(bits) : "memory");
 }
 
 struct TraceView {          // optional per-tick trace for parity tests: [n_streams][n_ticks]
@@ -951,7 +956,7 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
         __syncthreads();
     }
     if (tid == 0) {
-        if (B.n_pub) __threadfence_system(); else __threadfence();      // this CTA's (peer) record stores before its arrival
+        if (B.n_pub && !B.pub_cta_fence_gpu) __threadfence_system(); else __threadfence();   // this CTA's (peer) record stores before its arrival
         if (atomicAdd(B.ev_count + 4, 1) == (int)gridDim.x - 1) {       // every other CTA has read the counters
             B.ev_count[3] = n;
             B.ev_count[2] = 0;
