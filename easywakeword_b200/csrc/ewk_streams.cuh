@@ -604,7 +604,7 @@ __device__ __forceinline__ unsigned gate_state_step(const BankView& B, int s, St
 // phase 1: the warp sums every planned range (the only HBM traffic: each new sample is read once,
 // 16-byte loads, eight in flight per lane); phase 2: the ticks are replayed in order — chunk updates
 // into an incrementally maintained sorted array, percentile, threshold, is_silent, state machine.
-__global__ void __launch_bounds__(GATE_THREADS, 8)
+__global__ void __launch_bounds__(GATE_THREADS, 7)
 tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int trace_off, int smem_chunks, int stage_bytes) {
     extern __shared__ __align__(16) double sm_d[];
     __shared__ GatePlan plans[GATE_WARPS];
