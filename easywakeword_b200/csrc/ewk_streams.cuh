@@ -520,6 +520,7 @@ struct GatePlan {                                   // one per warp (= per strea
     unsigned char np[GATE_MAX_TICKS];               // chunk pieces; 255: heavy tick (all chunks, done in phase 2)
     unsigned char alias[GATE_MAX_TICKS];            // recent window == piece 0 (frame_size 1600, aligned)
     unsigned char full[GATE_MAX_TICKS];
+    double rms[GATE_MAX_TICKS];                     // is_silent's RMS per tick, formed by lane j ahead of the replay (not staged ticks)
 };
 
 // The 4-state timing machine + segment cut of WakeWord._detect_word for one tick (lane 0 only).
@@ -698,6 +699,7 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
     long long key_lo = -1, key_hi = -1;            // bit patterns of the order statistics behind st.thr (lane 0)
 
     // ---- one tick of phase 2: chunk updates into the sorted array, percentile, threshold, is_silent, state machine
+    bool rms_ahead = false;                        // plan.rms[] holds every tick's RMS (set below once the sums are known)
     auto replay_tick = [&](int j) {
         const long long k = tick0 + j + 1;
         const long long V = plan.V[j];
@@ -739,10 +741,13 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
             int silent = 1;
             double rms = 0.0;
             if (fs > 0) {
-                double ss;
-                if (plan.alias[j]) ss = plan.pv[j][0] * (double)fs;     // same 1600 samples as the chunk
-                else { ss = plan.pv[j][GATE_MAXP]; if (B.fmt == 1) ss *= (1.0 / 1073741824.0); }
-                rms = sqrt(ss / (double)nrec);
+                if (rms_ahead) rms = plan.rms[j];
+                else {
+                    double ss;
+                    if (plan.alias[j]) ss = plan.pv[j][0] * (double)fs;     // same 1600 samples as the chunk
+                    else { ss = plan.pv[j][GATE_MAXP]; if (B.fmt == 1) ss *= (1.0 / 1073741824.0); }
+                    rms = sqrt(ss / (double)nrec);
+                }
                 silent = rms < st.thr;
             }
             st.last_rms = rms;
@@ -811,6 +816,18 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
                 if (lane == 0) plan.pv[j][GATE_MAXP] = ss;
             }
         }
+        __syncwarp();
+    }
+    if (!pipelined) {
+        // every tick's sum of squares is known: lane j forms tick j's RMS (a double division and square root, ~35
+        // instructions) once, instead of lane 0 doing it tick after tick inside the serial replay; same operations
+        if (lane < n_ticks && fs > 0) {
+            double ss;
+            if (plan.alias[lane]) ss = plan.pv[lane][0] * (double)fs;
+            else { ss = plan.pv[lane][GATE_MAXP]; if (B.fmt == 1) ss *= (1.0 / 1073741824.0); }
+            plan.rms[lane] = sqrt(ss / (double)nrec);
+        }
+        rms_ahead = true;
         __syncwarp();
     }
     // ---- phase 2: replay the ticks in order (pipelined: tick j's sum first, copies of j+1, j+2 in flight)
