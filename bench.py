@@ -215,7 +215,7 @@ def run_ours(args):
     K, W = args.steps, max(3, args.warmup)
     word, word_name = load_word()
 
-    n = N_STREAMS
+    n = args.streams
     pool_pin = _lib.PinnedArray((POOL_SECONDS, n, STEP_SAMPLES), np.int16)
     make_pool(rank * n, n, word, pool_pin.array)
     pool_host = torch.from_numpy(pool_pin.array)
@@ -505,12 +505,14 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[2]: 4096 streams per B200, 10 s int16 rings, 1.0 s of new audio per stream "
+            "config": {"workload": ("configs[2]" if n == N_STREAMS else "configs[3] shard size" if n == 8192 else "custom") +
+                                   f": {n} streams per B200, 10 s int16 rings, 1.0 s of new audio per stream "
                                    "per step = 10 ticks of the gated level-1+2 path (K1 ring_push, K2 tick_gate, "
                                    "K3 fused MFCC+match on every candidate segment)",
                        "streams_per_gpu": n, "ring_seconds": RING_SECONDS, "step_seconds": STEP_SECONDS,
                        "template": word_name, "pcm": "int16", "params": PARAMS,
-                       "l2": "inputs larger than L2: 131 MB of new PCM per step, 1.44 GB of rings per GPU",
+                       "l2": f"inputs larger than L2: {n * STEP_SAMPLES * 2 / 1e6:.0f} MB of new PCM per step, "
+                             f"{n * 179200 * 2 / 1e9:.2f} GB of rings per GPU",
                        "overlap": ("K3 of step i runs on a second stream beside K1 of step i+1 (ewk_set_overlap; K1 in its "
                                    "cp.async.bulk form); the timed region ends after the last K3 (ewk_join); per-kernel "
                                    "times are taken in sequential order, each kernel alone")
@@ -525,14 +527,14 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(8 + ev_per_step * 40), "ms_per_step": ms_e2e / K,
                     "h2d_gbs_per_gpu": n * STEP_SAMPLES * 2 / (ms_e2e / K * 1e-3) / 1e9,
                     "host_cpus_rank0": (f"{host_cpus[0]}-{host_cpus[-1]} ({len(host_cpus)})" if host_cpus else None),
-                    "bound": "host->device copy (PCIe): the PCM of a step is 131 MB per GPU and every step pays its own "
+                    "bound": f"host->device copy (PCIe): the PCM of a step is {n * STEP_SAMPLES * 2 / 1e6:.0f} MB per GPU and every step pays its own "
                              "copy; kernels take ~10 % of the step and overlap the next copy"},
             "gpu_launches": int(launches),
             "by_rank": {"device_resident": by_rank[0], "e2e": by_rank[1]},
             "gather": gather_info,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "dense": {"what": "A9 per-hop scoring: 100 hops x 4096 streams per step, 4 FFT frames per hop (1 stream-grid + 3 "
+            "dense": {"what": f"A9 per-hop scoring: 100 hops x {n} streams per step, 4 FFT frames per hop (1 stream-grid + 3 "
                               "window-edge), K1 ring_push + K4 dense_score, scores left on the device",
                       "value": audio_per_step * dense_steps / (ms_dense * 1e-3), "unit": UNIT,
                       "ms_per_step": ms_dense / dense_steps,
@@ -559,6 +561,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--streams", type=int, default=N_STREAMS,
+                    help="streams per GPU (default 4096 = BASELINE configs[2]; 8192 = the per-GPU shard of configs[3], 65536 / 8)")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "peer-barrier", "nccl"],
                     help="multi-GPU result exchange: peer = K2/K3 store records and a completion signal into every rank's "
                          "copy over NVLink (no collective, no per-step barrier); peer-barrier = same stores, one "
