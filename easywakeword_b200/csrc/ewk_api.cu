@@ -142,8 +142,13 @@ int ewk_ctx::init() {
     DeviceTables* h = new DeviceTables();
     int nnz = build_tables(*h);
     if (nnz < 0) { delete h; fail("mel table overflow"); return EWK_ERR_STATE; }
-    CK(cudaMalloc(&d_tables, sizeof(DeviceTables)));
+    // flat tables, then the per-CTA layout of them (FrameTables image) that K3 / K4 copy into shared memory
+    FrameTables* img = new FrameTables();
+    load_frame_tables(*img, h, 0, 1);
+    CK(cudaMalloc((void**)&d_tables, FRAME_IMAGE_OFFSET + sizeof(FrameTables)));
     CK(cudaMemcpy(d_tables, h, sizeof(DeviceTables), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(reinterpret_cast<char*>(d_tables) + FRAME_IMAGE_OFFSET, img, sizeof(FrameTables), cudaMemcpyHostToDevice));
+    delete img;
     delete h;
     h_tmpl.assign(cfg.max_templates, TemplateFeat{});
     CK(cudaMalloc(&d_tmpl, sizeof(TemplateFeat) * cfg.max_templates));

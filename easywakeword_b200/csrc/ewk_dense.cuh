@@ -113,7 +113,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = blockIdx.x;
-    load_frame_tables(*ft, T, tid, DENSE_THREADS);
+    copy_frame_tables(*ft, T, tid, DENSE_THREADS);
     float* scr = scratch + warp * SCR_WARP;
     init_warp_scratch(scr, lane);
     for (int i = tid; i < A.DG; i += DENSE_THREADS) g2tag[i] = 0x7fc00001;     // matches no floor

@@ -69,7 +69,10 @@ struct FrameTables {
     float4 dct[32 * DCT_LANE4];        // per lane: [band slot s < 4][m < 10] = dct(k = 2 m + (lane >> 4), band_s), see warp_dct20
 };
 
-__device__ __forceinline__ void load_frame_tables(FrameTables& ft, const DeviceTables* __restrict__ T, int tid, int nthr) {
+// Lays the per-CTA tables out from the flat ones.  Run ONCE, on the host, at context creation (tid 0 of 1): the result is
+// appended to the DeviceTables allocation and every CTA copies that image (copy_frame_tables) instead of rebuilding it
+// with scattered loads and integer divisions at the start of every launch.
+__host__ __device__ inline void load_frame_tables(FrameTables& ft, const DeviceTables* __restrict__ T, int tid, int nthr) {
     for (int i = tid; i < 256; i += nthr) {
         const int a = i >> 5, lane = i & 31;
         ft.hw[i] = make_float2(T->hann[2 * lane + 64 * a], T->hann[2 * lane + 64 * a + 1]);
@@ -92,6 +95,15 @@ __device__ __forceinline__ void load_frame_tables(FrameTables& ft, const DeviceT
         const int within = w == 0 ? 0 : w == 1 ? 1 : w == 2 ? 2 : w == 4 ? 3 : w == 5 ? 4 : -1;
         ft.coef_of_lane[i] = within < 0 ? -1 : 2 * (5 * ((i >> 3) & 1) + within) + ((i >> 4) & 1);
     }
+}
+
+static_assert(sizeof(FrameTables) % 16 == 0, "the image is copied as 16-byte words");
+constexpr size_t FRAME_IMAGE_OFFSET = (sizeof(DeviceTables) + 15) & ~(size_t)15;   // FrameTables image behind the flat tables
+
+__device__ __forceinline__ void copy_frame_tables(FrameTables& ft, const DeviceTables* __restrict__ T, int tid, int nthr) {
+    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const char*>(T) + FRAME_IMAGE_OFFSET);
+    int4* dst = reinterpret_cast<int4*>(&ft);
+    for (int i = tid; i < (int)(sizeof(FrameTables) / 16); i += nthr) dst[i] = __ldg(src + i);
 }
 
 // packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for both halves of a complex value)

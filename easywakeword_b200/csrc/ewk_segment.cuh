@@ -162,7 +162,7 @@ __device__ __forceinline__ SegSmem seg_carve(float* smem, int cap_frames) {
 
 // once per CTA: tables into shared memory, the lane's mel band descriptors into registers
 __device__ __forceinline__ void seg_prologue(const DeviceTables* __restrict__ T, const SegSmem& m) {
-    load_frame_tables(*m.ft, T, threadIdx.x, SEG_THREADS);
+    copy_frame_tables(*m.ft, T, threadIdx.x, SEG_THREADS);
     init_warp_scratch(m.scratch + (threadIdx.x >> 5) * SCR_WARP, threadIdx.x & 31);
     __syncthreads();
 }
