@@ -192,6 +192,33 @@ def test_full_mfcc_front_end_against_torchaudio(word):
         assert err.max() < 2e-5, (name, float(err.max()))
 
 
+def test_full_mfcc_front_end_against_transformers_spectrogram(word):
+    """A third code base for the same chain: transformers.audio_utils (the Whisper / CLAP feature-extractor numerics) —
+    `spectrogram(power=2, center, constant padding, periodic Hann, Slaney filter bank, log_mel="dB", db_range=80)` in
+    float64, then scipy's ortho DCT-II.  The restated librosa layer agrees with it to ~1e-7 per-frame relative L2,
+    floor path included (a digital-silence gap inside the word), which bounds what the float32 rounding points of the
+    restatement can be worth: three independent implementations, one answer."""
+    au = pytest.importorskip("transformers.audio_utils")
+    import scipy.fft
+    fb = au.mel_filter_bank(257, 128, 0.0, 8000.0, 16000, norm="slaney", mel_scale="slaney")
+    win = au.window_function(512, "hann", periodic=True)
+    cases = {
+        "word": word,
+        "noise": (np.random.default_rng(3).standard_normal(16000) * 0.05).astype(np.float32),
+        "word_gap_word": np.concatenate([word[:6000], np.zeros(4000, np.float32), word[6000:]]),
+        "sine440": synth.sine(440),
+    }
+    for name, x in cases.items():
+        db = au.spectrogram(x.astype(np.float64), win, 512, 160, fft_length=512, power=2.0, center=True, pad_mode="constant",
+                            mel_filters=fb, mel_floor=1e-10, log_mel="dB", reference=1.0, min_value=1e-10, db_range=80.0,
+                            dtype=np.float64)
+        got = scipy.fft.dct(db, axis=0, type=2, norm="ortho")[:20]
+        ref = L.mfcc(x)
+        assert got.shape == ref.shape, name
+        err = np.linalg.norm(got - ref, axis=0) / np.linalg.norm(ref, axis=0)
+        assert err.max() < 2e-6, (name, float(err.max()))
+
+
 def test_vad_duration_matches_reference_goldens(golden_vad):
     """oracle.analyze_reference_audio_duration / librosa_restated.rms and the package's host rule against the
     values WakeWord._analyze_reference_audio_duration (wakeword.py:854-898) returned for the same WAVs."""
