@@ -115,3 +115,49 @@ def test_full_size_dense_properties(big, word):
         u = int(rng.integers(0, UNIQUE)); h = int(rng.integers(hop0, hop0 + nh))
         ref = O.dense_scores(synth.from_int16(uniq[u, :secs * 16000]), [word], [h])[0, 0]
         assert abs(float(sc[first[u], h - hop0]) - float(ref)) <= 0.01
+
+
+def test_config4_shard_size_overlap_equals_sequential(big, word):
+    """8192 streams on one GPU — the per-GPU shard of BASELINE configs[3] (65 536 streams / 8 GPUs) — pushed from device
+    memory in overlap mode (K3 beside the next bulk push) and in sequential order: identical event lists and result
+    records, and every replica of a distinct stream reports the same events."""
+    import torch
+    from easywakeword_b200 import _lib
+    from easywakeword_b200.bank import WakeWordBank
+    uniq, _ = big
+    n8, secs = 8192, 14
+    which8 = np.random.default_rng(2).permutation(n8) % UNIQUE
+    dev_pcm = torch.from_numpy(np.ascontiguousarray(
+        uniq[which8, :secs * 16000].reshape(n8, secs, 16000).transpose(1, 0, 2))).to("cuda:0")       # [secs][n8][16000]
+    out = []
+    for overlap in (False, True):
+        bank = WakeWordBank(n8, [word], frame_size=1600, similarity_threshold=95.0, speech_duration_min=0.69,
+                            speech_duration_max=1.38, timeout=4.0, max_events=1 << 17, max_push_seconds=2.0)
+        bank.ctx.set_overlap(overlap)
+        try:
+            evs = []
+            for j in range(secs):
+                bank.push((dev_pcm[j].data_ptr(), n8, 16000, 16000), where=_lib.DEVICE)
+                bank.tick(10)
+                if j % 4 == 3:
+                    evs.append(bank.poll().copy())
+                    assert bank.ctx.dropped == 0
+            evs.append(bank.poll().copy())
+            out.append((np.concatenate(evs), bank.results()))
+        finally:
+            bank.close()
+    (e0, r0), (e1, r1) = out
+    assert len(e0) == len(e1) and (e0["kind"] == 2).sum() > 2 * UNIQUE
+    for f in e0.dtype.names:
+        assert np.array_equal(e0[f], e1[f], equal_nan=e0[f].dtype.kind == "f"), f
+    for f in r0.dtype.names:
+        assert np.array_equal(r0[f], r1[f], equal_nan=r0[f].dtype.kind == "f"), f
+    order = np.lexsort((e1["kind"], e1["tick"], e1["stream"]))
+    ev = e1[order]
+    starts = np.searchsorted(ev["stream"], np.arange(n8 + 1))
+    canon = {}
+    for s in range(n8):
+        mine = ev[starts[s]:starts[s + 1]]
+        key = tuple(mine[f].tobytes() for f in ("kind", "tick", "seg_start", "seg_len", "score", "matched"))
+        u = int(which8[s])
+        assert canon.setdefault(u, key) == key, f"stream {s} (copy of {u}) differs"
