@@ -54,7 +54,7 @@ def load_word():
     return synth.synthetic_word(), "synthetic word"
 
 
-def make_pool(stream0, n_streams, word, out):
+def make_pool(stream0, n_streams, word, out, as_f32=False):
     """out[POOL_SECONDS, n_streams, 16000] int16 <- synthetic streams (seed = SEED0 + global stream id), laid out
     so that one step (1.0 s of every stream) is one contiguous block, the layout a caller pushing [streams, n]
     arrays has."""
@@ -63,7 +63,8 @@ def make_pool(stream0, n_streams, word, out):
 
     def one(s):
         x, _ = synth.stream(SEED0 + stream0 + s, POOL_SECONDS, word, noise_sigma=0.002, gain=(1.0, 4.0))
-        out[:, s, :] = synth.to_int16(x).reshape(POOL_SECONDS, STEP_SAMPLES)
+        q = synth.to_int16(x)                                       # the same 16-bit sample values in either format
+        out[:, s, :] = (synth.from_int16(q) if as_f32 else q).reshape(POOL_SECONDS, STEP_SAMPLES)
 
     with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 8)) as ex:
         list(ex.map(one, range(n_streams)))
@@ -216,15 +217,18 @@ def run_ours(args):
     word, word_name = load_word()
 
     n = args.streams
-    pool_pin = _lib.PinnedArray((POOL_SECONDS, n, STEP_SAMPLES), np.int16)
-    make_pool(rank * n, n, word, pool_pin.array)
+    f32 = args.pcm == "f32"                                         # the reference's native PortAudio dtype (wakeword.py:438-444)
+    esz = 4 if f32 else 2
+    pcm_name = "float32" if f32 else "int16"
+    pool_pin = _lib.PinnedArray((POOL_SECONDS, n, STEP_SAMPLES), np.float32 if f32 else np.int16)
+    make_pool(rank * n, n, word, pool_pin.array, as_f32=f32)
     pool_host = torch.from_numpy(pool_pin.array)
     pool_dev = pool_host.to(dev, non_blocking=False)
 
     # a real (non-legacy) stream: libewk launches on it and torch.cuda.Event times it
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
-    bank = WakeWordBank(n, [word], device=local_rank, buffer_seconds=RING_SECONDS, pcm_dtype=np.int16,
+    bank = WakeWordBank(n, [word], device=local_rank, buffer_seconds=RING_SECONDS, pcm_dtype=np.float32 if f32 else np.int16,
                         max_push_seconds=2 * STEP_SECONDS, cuda_stream=stream.cuda_stream, max_events=1 << 17, **PARAMS)
     ctx = bank.ctx
     results = torch.zeros(n, 2, dtype=torch.int32, device=dev)          # ewk_stream_result[n]: NCCL send buffer
@@ -250,7 +254,7 @@ def run_ours(args):
         else:
             exchange.install(ctx)
 
-    def slice_ptr(t, j, esz=2):
+    def slice_ptr(t, j):
         return (t.data_ptr() + j * n * STEP_SAMPLES * esz, n, STEP_SAMPLES, STEP_SAMPLES)
 
     step_no = [0]
@@ -453,9 +457,9 @@ def run_ours(args):
         #  tick_gate   (K2): with K1's block sums it reads no PCM: 10 block sums + state in/out per stream;
         #              (host pushes: it reads the step's PCM once itself)
         #  segment_queue (K3): the PCM of every candidate segment once (mean 17.6 k samples) + its 40-byte event
-        alg_bytes = {"ring_push": n * (STEP_SAMPLES * 2 * 2 + TICKS_PER_STEP * 8),
+        alg_bytes = {"ring_push": n * (STEP_SAMPLES * esz * 2 + TICKS_PER_STEP * 8),
                      "tick_gate": n * (TICKS_PER_STEP * 8 + 2 * 104 + 72 + 2 * 1600),
-                     "segment_queue": ev_per_step * (17600 * 2 + 40)}
+                     "segment_queue": ev_per_step * (17600 * esz + 40)}
         share = {k: v["ms"] / tot_ms for k, v in kern.items()}
 
         def kroof(name):
@@ -486,7 +490,7 @@ def run_ours(args):
                                 "fp32_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12},
                     "hbm_bound_kernel": dict(kernel="ring_push", **(kroof("ring_push") or {})),
                     "tick_gate": kroof("tick_gate"),
-                    "whole_step_frac": (n * STEP_SAMPLES * 2) * K / (ms_dev * 1e-3) / 1e9 / hbm_peak}
+                    "whole_step_frac": (n * STEP_SAMPLES * esz) * K / (ms_dev * 1e-3) / 1e9 / hbm_peak}
         cpu = None
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
@@ -506,13 +510,13 @@ def run_ours(args):
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": ("configs[2]" if n == N_STREAMS else "configs[3] shard size" if n == 8192 else "custom") +
-                                   f": {n} streams per B200, 10 s int16 rings, 1.0 s of new audio per stream "
+                                   f": {n} streams per B200, 10 s {pcm_name} rings, 1.0 s of new audio per stream "
                                    "per step = 10 ticks of the gated level-1+2 path (K1 ring_push, K2 tick_gate, "
                                    "K3 fused MFCC+match on every candidate segment)",
                        "streams_per_gpu": n, "ring_seconds": RING_SECONDS, "step_seconds": STEP_SECONDS,
-                       "template": word_name, "pcm": "int16", "params": PARAMS,
-                       "l2": f"inputs larger than L2: {n * STEP_SAMPLES * 2 / 1e6:.0f} MB of new PCM per step, "
-                             f"{n * 179200 * 2 / 1e9:.2f} GB of rings per GPU",
+                       "template": word_name, "pcm": pcm_name, "params": PARAMS,
+                       "l2": f"inputs larger than L2: {n * STEP_SAMPLES * esz / 1e6:.0f} MB of new PCM per step, "
+                             f"{n * 179200 * esz / 1e9:.2f} GB of rings per GPU",
                        "overlap": ("K3 of step i runs on a second stream beside K1 of step i+1 (ewk_set_overlap; K1 in its "
                                    "cp.async.bulk form); the timed region ends after the last K3 (ewk_join); per-kernel "
                                    "times are taken in sequential order, each kernel alone")
@@ -523,11 +527,11 @@ def run_ours(args):
                                                          " (put-with-signal, no collective)") if exchange is not None else
                                         "all_gather of 8 B/stream results per step")) if world > 1 else "1 GPU"},
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * STEP_SAMPLES * 2,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * STEP_SAMPLES * esz,
                     "d2h_bytes_per_step": int(8 + ev_per_step * 40), "ms_per_step": ms_e2e / K,
-                    "h2d_gbs_per_gpu": n * STEP_SAMPLES * 2 / (ms_e2e / K * 1e-3) / 1e9,
+                    "h2d_gbs_per_gpu": n * STEP_SAMPLES * esz / (ms_e2e / K * 1e-3) / 1e9,
                     "host_cpus_rank0": (f"{host_cpus[0]}-{host_cpus[-1]} ({len(host_cpus)})" if host_cpus else None),
-                    "bound": f"host->device copy (PCIe): the PCM of a step is {n * STEP_SAMPLES * 2 / 1e6:.0f} MB per GPU and every step pays its own "
+                    "bound": f"host->device copy (PCIe): the PCM of a step is {n * STEP_SAMPLES * esz / 1e6:.0f} MB per GPU and every step pays its own "
                              "copy; kernels take ~10 % of the step and overlap the next copy"},
             "gpu_launches": int(launches),
             "by_rank": {"device_resident": by_rank[0], "e2e": by_rank[1]},
@@ -540,7 +544,7 @@ def run_ours(args):
                       "ms_per_step": ms_dense / dense_steps,
                       "kernel_ms": prof_dense["dense_score"]["ms"] / max(1, prof_dense["dense_score"]["launches"]),
                       "windows_per_s": n * 100 * world * dense_steps / (ms_dense * 1e-3),
-                      "hbm_frac": (n * STEP_SAMPLES * 2 + n * 400) * dense_steps / (ms_dense * 1e-3) / 1e9 / hbm_peak,
+                      "hbm_frac": (n * STEP_SAMPLES * esz + n * 400) * dense_steps / (ms_dense * 1e-3) / 1e9 / hbm_peak,
                       "cpu_baseline": dense_cpu},
             "level2_events_per_step": ev_per_step,
             "kernel_ms_per_step": {k: v["ms"] / max(1, K) for k, v in kern.items()},
@@ -563,6 +567,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--streams", type=int, default=N_STREAMS,
                     help="streams per GPU (default 4096 = BASELINE configs[2]; 8192 = the per-GPU shard of configs[3], 65536 / 8)")
+    ap.add_argument("--pcm", default="int16", choices=["int16", "f32"],
+                    help="ring / push sample format (int16: the wire format, default; f32: what PortAudio hands the reference)")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "peer-barrier", "nccl"],
                     help="multi-GPU result exchange: peer = K2/K3 store records and a completion signal into every rank's "
                          "copy over NVLink (no collective, no per-step barrier); peer-barrier = same stores, one "
