@@ -1,5 +1,7 @@
 """CPU: pin oracle/ (the checker) against the reference-generated goldens and the reference's
 own known-answer tests for this path."""
+import os
+
 import numpy as np
 import pytest
 
@@ -7,6 +9,8 @@ from oracle import ewk_oracle as O
 from oracle import librosa_restated as L
 from easywakeword_b200 import synth
 from helpers import detect_stream_for, sha
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 # ---- Appendix A anchors of the restated front-end ---------------------------------------
@@ -192,31 +196,54 @@ def test_full_mfcc_front_end_against_torchaudio(word):
         assert err.max() < 2e-5, (name, float(err.max()))
 
 
-def test_full_mfcc_front_end_against_transformers_spectrogram(word):
+_TRANSFORMERS_CHECK = r"""
+import json, sys
+import numpy as np, scipy.fft
+sys.path.insert(0, sys.argv[1])
+import transformers.audio_utils as au
+from oracle import librosa_restated as L
+from easywakeword_b200 import synth
+word = np.load(sys.argv[1] + "/tests/golden/reference_word.npz")["pcm_i16"].astype(np.float32) / np.float32(32768)
+fb = au.mel_filter_bank(257, 128, 0.0, 8000.0, 16000, norm="slaney", mel_scale="slaney")
+win = au.window_function(512, "hann", periodic=True)
+cases = {
+    "word": word,
+    "noise": (np.random.default_rng(3).standard_normal(16000) * 0.05).astype(np.float32),
+    "word_gap_word": np.concatenate([word[:6000], np.zeros(4000, np.float32), word[6000:]]),
+    "sine440": synth.sine(440),
+}
+out = {}
+for name, x in cases.items():
+    db = au.spectrogram(x.astype(np.float64), win, 512, 160, fft_length=512, power=2.0, center=True, pad_mode="constant",
+                        mel_filters=fb, mel_floor=1e-10, log_mel="dB", reference=1.0, min_value=1e-10, db_range=80.0,
+                        dtype=np.float64)
+    got = scipy.fft.dct(db, axis=0, type=2, norm="ortho")[:20]
+    ref = L.mfcc(x)
+    out[name] = [list(got.shape) == list(ref.shape), float((np.linalg.norm(got - ref, axis=0) / np.linalg.norm(ref, axis=0)).max())]
+print("RESULT " + json.dumps(out))
+"""
+
+
+def test_full_mfcc_front_end_against_transformers_spectrogram():
     """A third code base for the same chain: transformers.audio_utils (the Whisper / CLAP feature-extractor numerics) —
     `spectrogram(power=2, center, constant padding, periodic Hann, Slaney filter bank, log_mel="dB", db_range=80)` in
     float64, then scipy's ortho DCT-II.  The restated librosa layer agrees with it to ~1e-7 per-frame relative L2,
-    floor path included (a digital-silence gap inside the word), which bounds what the float32 rounding points of the
-    restatement can be worth: three independent implementations, one answer."""
-    au = pytest.importorskip("transformers.audio_utils")
-    import scipy.fft
-    fb = au.mel_filter_bank(257, 128, 0.0, 8000.0, 16000, norm="slaney", mel_scale="slaney")
-    win = au.window_function(512, "hann", periodic=True)
-    cases = {
-        "word": word,
-        "noise": (np.random.default_rng(3).standard_normal(16000) * 0.05).astype(np.float32),
-        "word_gap_word": np.concatenate([word[:6000], np.zeros(4000, np.float32), word[6000:]]),
-        "sine440": synth.sine(440),
-    }
-    for name, x in cases.items():
-        db = au.spectrogram(x.astype(np.float64), win, 512, 160, fft_length=512, power=2.0, center=True, pad_mode="constant",
-                            mel_filters=fb, mel_floor=1e-10, log_mel="dB", reference=1.0, min_value=1e-10, db_range=80.0,
-                            dtype=np.float64)
-        got = scipy.fft.dct(db, axis=0, type=2, norm="ortho")[:20]
-        ref = L.mfcc(x)
-        assert got.shape == ref.shape, name
-        err = np.linalg.norm(got - ref, axis=0) / np.linalg.norm(ref, axis=0)
-        assert err.max() < 2e-6, (name, float(err.max()))
+    floor path included (a digital-silence gap inside the word): three independent implementations, one answer.
+    Runs in a fresh interpreter: with oracle/shim's stand-in `librosa` on sys.path (the needs_reference tests put it
+    there) transformers would take its librosa/soxr branch at import."""
+    import json
+    import subprocess
+    import sys
+    pytest.importorskip("transformers")
+    r = subprocess.run([sys.executable, "-c", _TRANSFORMERS_CHECK, REPO], capture_output=True, text=True, timeout=600)
+    if r.returncode != 0 and "No module named" in r.stderr:
+        pytest.skip(r.stderr.strip().splitlines()[-1])
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(next(l for l in r.stdout.splitlines() if l.startswith("RESULT "))[7:])
+    assert len(res) == 4
+    for name, (same_shape, err) in res.items():
+        assert same_shape, name
+        assert err < 2e-6, (name, err)
 
 
 def test_vad_duration_matches_reference_goldens(golden_vad):
