@@ -210,6 +210,16 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": total_wall, "level2_events": ev,
     }
+    # context, not the arm's value: what a tuned C + OpenMP statement of the same semantics reaches on these cores
+    try:
+        word, _ = load_word()
+        pool = np.empty((POOL_SECONDS, 256, STEP_SAMPLES), np.int16)
+        make_pool(0, 256, word, pool)
+        vc, evc, audio_c = cpu_best_effort_c(pool, word, cores, streams=256, repeats=3, rounds=4)
+        line["best_effort_c"] = {"value": vc, "unit": UNIT, "cores": cores, "kind": "port (C, OpenMP over streams)",
+                                 "sample": f"4 x 256 streams x 30 s = {audio_c:.0f} audio-s, {evc} level-2 evaluations"}
+    except Exception as e:
+        line["best_effort_c"] = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
     print(json.dumps(line), flush=True)
 
 
