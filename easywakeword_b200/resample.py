@@ -85,10 +85,27 @@ class StreamResampler:
 
 
 # ------------------------------------------------------------------------------------------------ WAV
+def _g711_tables():
+    """ITU-T G.711 expansion tables, code -> 16-bit linear sample (what libsndfile's ulaw / alaw readers produce)."""
+    c = np.arange(256, dtype=np.int32)
+    u = ~c & 0xFF
+    mu = ((((u & 0x0F) << 3) + 0x84) << ((u >> 4) & 7)) - 0x84
+    mu = np.where(u & 0x80, -mu, mu)
+    a = c ^ 0x55
+    e, m = (a >> 4) & 7, a & 0x0F
+    al = np.where(e == 0, (m << 4) + 8, ((m << 4) + 0x108) << np.maximum(e - 1, 0))
+    al = np.where(a & 0x80, al, -al)
+    return mu.astype(np.int16), al.astype(np.int16)
+
+
+ULAW_TABLE, ALAW_TABLE = _g711_tables()
+
+
 def read_wav(path) -> tuple[np.ndarray, int]:
     """RIFF/WAVE reader with libsndfile's float conversion (what ``soundfile.read(dtype='float32')`` under
     ``librosa.load`` yields): PCM 8 (unsigned) / 16 / 24 / 32 bit -> x / full scale, IEEE float 32 / 64 as is,
-    WAVE_FORMAT_EXTENSIBLE.  -> (float32 [n] or [n, channels], sample_rate)."""
+    G.711 A-law / mu-law (format tags 6 / 7) expanded to 16 bit then / 32768, WAVE_FORMAT_EXTENSIBLE.
+    -> (float32 [n] or [n, channels], sample_rate)."""
     with open(path, "rb") as f:
         data = f.read()
     if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
@@ -120,6 +137,8 @@ def read_wav(path) -> tuple[np.ndarray, int]:
         y = (v.astype(np.float64) / 8388608.0).astype(np.float32)
     elif tag == 1 and bits == 32:
         y = (np.frombuffer(pcm[:len(pcm) // 4 * 4], "<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
+    elif tag in (6, 7) and bits == 8:
+        y = (ALAW_TABLE if tag == 6 else ULAW_TABLE)[np.frombuffer(pcm, np.uint8)].astype(np.float32) / np.float32(32768.0)
     elif tag == 3 and bits == 32:
         y = np.frombuffer(pcm[:len(pcm) // 4 * 4], "<f4").astype(np.float32)
     elif tag == 3 and bits == 64:

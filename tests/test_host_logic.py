@@ -72,6 +72,50 @@ def test_load_wav(wav, word):
     assert np.array_equal(load_wav_16k(wav), word)
 
 
+def test_read_wav_formats_host_side(tmp_path, word_i16):
+    """The RIFF reader behind load_16k (librosa.load's decoding step: libsndfile float conversion) on the encodings
+    libsndfile reads from WAV: PCM 8/16/32, IEEE float, and G.711 mu-law / A-law (format tags 7 / 6), whose expansion
+    tables are pinned against CPython's audioop where it still exists (< 3.13)."""
+    import struct
+    import warnings
+    from easywakeword_b200.resample import ALAW_TABLE, ULAW_TABLE, read_wav
+
+    def write(name, tag, bits, ch, sr, payload):
+        block = ch * bits // 8
+        hdr = struct.pack("<4sI4s4sIHHIIHH4sI", b"RIFF", 36 + len(payload), b"WAVE", b"fmt ", 16, tag, ch, sr, sr * block, block,
+                          bits, b"data", len(payload))
+        p = tmp_path / name
+        p.write_bytes(hdr + payload + (b"\0" if len(payload) & 1 else b""))
+        return p
+
+    q = word_i16[:4001]
+    y, sr = read_wav(write("p16.wav", 1, 16, 1, 16000, q.astype("<i2").tobytes()))
+    assert sr == 16000 and np.array_equal(y, q.astype(np.float32) / np.float32(32768))
+    y, _ = read_wav(write("p8.wav", 1, 8, 1, 8000, bytes(range(256))))
+    assert np.array_equal(y, (np.arange(256, dtype=np.float32) - 128) / 128)
+    y, _ = read_wav(write("p32.wav", 1, 32, 2, 44100, (q[:4000].astype(np.int32) << 16).astype("<i4").tobytes()))
+    assert y.shape == (2000, 2) and np.array_equal(y.reshape(-1), q[:4000].astype(np.float32) / np.float32(32768))
+    y, _ = read_wav(write("f32.wav", 3, 32, 1, 48000, (q.astype(np.float32) / 32768).astype("<f4").tobytes()))
+    assert np.array_equal(y, q.astype(np.float32) / np.float32(32768))
+    codes = np.arange(256, dtype=np.uint8)
+    for tag, table in ((7, ULAW_TABLE), (6, ALAW_TABLE)):
+        y, sr = read_wav(write(f"g711_{tag}.wav", tag, 8, 1, 8000, codes.tobytes()))
+        assert sr == 8000 and np.array_equal(y, table.astype(np.float32) / np.float32(32768))
+    assert ULAW_TABLE[0] == -32124 and ULAW_TABLE[0x80] == 32124 and ULAW_TABLE[0xFF] == 0 and ULAW_TABLE[0x7F] == 0
+    assert ALAW_TABLE[0x2A] == -32256 and ALAW_TABLE[0xAA] == 32256 and ALAW_TABLE[0xD5] == 8 and ALAW_TABLE[0x55] == -8
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            import audioop
+    except ImportError:
+        audioop = None
+    if audioop is not None:
+        assert np.array_equal(np.frombuffer(audioop.ulaw2lin(codes.tobytes(), 2), "<i2"), ULAW_TABLE)
+        assert np.array_equal(np.frombuffer(audioop.alaw2lin(codes.tobytes(), 2), "<i2"), ALAW_TABLE)
+    with pytest.raises(ValueError):
+        read_wav(write("adpcm.wav", 2, 4, 1, 8000, b"\0" * 64))
+
+
 # ---- timing state machine vs goldens from the reference's _detect_word
 def test_timing_machine_reproduces_reference_events(golden_detect):
     g, cases = golden_detect
