@@ -291,6 +291,7 @@ def _declare_stream_protos(lib):
         "ewk_default_stream_params": (C.c_int, [_p(StreamParams)]),
         "ewk_set_stream_params": (C.c_int, [vp, i32, _p(StreamParams)]),
         "ewk_push": (C.c_int, [vp, i32, i32, vp, i64, i64, i32]),
+        "ewk_push_g711": (C.c_int, [vp, i32, i32, vp, i64, i64, i32, i32]),
         "ewk_tick": (C.c_int, [vp, i32]),
         "ewk_set_overlap": (C.c_int, [vp, i32]),
         "ewk_join": (C.c_int, [vp]),
@@ -393,6 +394,24 @@ def _bank_methods():
             stride = a.strides[0] // a.itemsize if ns > 1 else n
             ptr = a.ctypes.data
         self._ck(self.lib.ewk_push(self.h, stream0, ns, ptr, n, stride, where))
+
+    def push_g711(self, codes, stream0=0, where=HOST, law="ulaw"):
+        """codes: uint8 [n_streams, n] G.711 mu-law ("ulaw") / A-law ("alaw") codes, or (ptr, n_streams, n, stride):
+        expanded to 16-bit samples on the device and pushed like PCM16 (int16 rings only)."""
+        if law not in ("ulaw", "alaw"):
+            raise ValueError("law must be 'ulaw' or 'alaw'")
+        if isinstance(codes, tuple):
+            ptr, ns, n, stride = codes
+        else:
+            a = codes if codes.ndim == 2 else codes.reshape(1, -1)
+            if a.dtype != np.uint8:
+                raise TypeError(f"push_g711 expects uint8 codes, got {a.dtype}")
+            if a.strides[1] != 1:
+                a = np.ascontiguousarray(a)
+            ns, n = a.shape
+            stride = a.strides[0] if ns > 1 else n
+            ptr = a.ctypes.data
+        self._ck(self.lib.ewk_push_g711(self.h, stream0, ns, ptr, n, stride, where, 1 if law == "alaw" else 0))
 
     def tick(self, n_ticks=1, trace=False):
         if not trace:
@@ -524,7 +543,7 @@ def _bank_methods():
         names = ["ring_push", "tick_gate", "segment_queue", "segment_batch", "dense_score", "segment_prepare"]
         return {names[i]: {"ms": ms[i], "launches": int(n[i])} for i in range(len(names))}
 
-    for f in (prepare_segments, dense_scores, profile, profile_read, set_stream_params, push, tick, poll, status, read_last, read_segment, results, results_device_ptr,
+    for f in (prepare_segments, dense_scores, profile, profile_read, set_stream_params, push, push_g711, tick, poll, status, read_last, read_segment, results, results_device_ptr,
               set_results_buffer, set_results_peers, publish_parity, publish_seq, wait_published, published_seq, match_stream, set_cuda_stream, launch_count):
         setattr(Context, f.__name__, f)
 

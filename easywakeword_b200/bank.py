@@ -93,6 +93,11 @@ class WakeWordBank:
         self.ctx.push(pcm, stream0=0, where=where)
         self.samples_pushed += pcm[2] if isinstance(pcm, tuple) else pcm.shape[-1]
 
+    def push_g711(self, codes, law: str = "ulaw", where=_lib.HOST):
+        """codes[n_streams, n] uint8: a G.711 mu-law / A-law feed, expanded to PCM16 on the device (int16 banks)."""
+        self.ctx.push_g711(codes, stream0=0, where=where, law=law)
+        self.samples_pushed += codes[2] if isinstance(codes, tuple) else codes.shape[-1]
+
     def tick(self, n_ticks: int = 1, trace: bool = False):
         """n_ticks x 100 ms of the reference's poll loop for every stream (K2 + K3)."""
         self.ticks += n_ticks

@@ -180,6 +180,7 @@ void ewk_ctx::release() {
         if (ev_free[i]) cudaEventDestroy(ev_free[i]);
         ev_ready[i] = ev_free[i] = nullptr;
         b_stage2[i].free();
+        b_raw[i].free();
     }
     if (own_stream) cudaStreamDestroy(own_stream);
     d_tables = nullptr; d_tmpl = nullptr; own_stream = nullptr; copy_stream = nullptr;
@@ -761,6 +762,63 @@ extern "C" int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pc
     else
         CK(cudaMemcpy2DAsync(ctx->b_stage2[b].p, (size_t)n * esz, pcm, (size_t)stride * esz, (size_t)n * esz, n_streams,
                              cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_ready[b], ctx->copy_stream));
+    ctx->pending.valid = true; ctx->pending.slot = b; ctx->pending.stream0 = stream0; ctx->pending.n_streams = n_streams;
+    ctx->pending.n = n;
+    return EWK_OK;
+}
+
+// G.711 feed: 8-bit mu-law (law 0) / A-law (law 1) codes, expanded on the device to the 16-bit samples of the standard
+// and pushed like PCM16.  Host codes cross PCIe at one byte per sample; the expansion (K0) runs on the copy stream right
+// behind the copy, into the same double-buffered staging the PCM path uses, and lands lazily like any host push.
+extern "C" int ewk_push_g711(ewk_ctx* ctx, int stream0, int n_streams, const uint8_t* codes, int64_t n, int64_t stride, int where, int law) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = need_streams(ctx, "ewk_push_g711", false);
+    if (rc) return rc;
+    BankView& B = ctx->bank;
+    if (B.fmt != 1) { ctx->fail("ewk_push_g711: the context's rings must be int16 (pcm_format EWK_PCM_I16)"); return EWK_ERR_STATE; }
+    if (!codes || n_streams < 1 || stream0 < 0 || stream0 + n_streams > B.n_streams || n < 1 || stride < n || law < 0 || law > 1) {
+        ctx->fail("ewk_push_g711: bad arguments (stream0=%d n_streams=%d n=%lld stride=%lld law=%d)", stream0, n_streams,
+                  (long long)n, (long long)stride, law);
+        return EWK_ERR_ARG;
+    }
+    if (n > B.P - B.R && n > B.R) { ctx->fail("ewk_push_g711: %lld samples exceed the ring (%d)", (long long)n, B.R); return EWK_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    rc = ctx->flush_pending();
+    if (rc) return rc;
+    for (int s = stream0; s < stream0 + n_streams; s++) {     // same guard as ewk_push
+        if (ctx->h_prm[s].live) continue;
+        const long long ahead = ctx->h_written[s] + n - ctx->h_visible_lb[s];
+        if (ctx->h_visible_lb[s] >= B.R && ahead > (long long)(B.P - B.R)) {
+            ctx->fail("ewk_push_g711: stream %d would hold %lld un-gated samples, more than slack_samples=%d; call ewk_tick first",
+                      s, ahead, B.P - B.R);
+            return EWK_ERR_STATE;
+        }
+    }
+    const int b = ctx->stage_idx;
+    ctx->stage_idx ^= 1;
+    CK(ctx->b_stage2[b].ensure(sizeof(short) * (size_t)n * n_streams));
+    if (ctx->ev_free_valid[b]) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));
+    const unsigned char* d_codes = codes;
+    long long d_stride = stride;
+    if (where == EWK_HOST) {
+        CK(ctx->b_raw[b].ensure((size_t)n * n_streams));
+        if (stride == n)
+            CK(cudaMemcpyAsync(ctx->b_raw[b].p, codes, (size_t)n * n_streams, cudaMemcpyHostToDevice, ctx->copy_stream));
+        else
+            CK(cudaMemcpy2DAsync(ctx->b_raw[b].p, (size_t)n, codes, (size_t)stride, (size_t)n, n_streams, cudaMemcpyHostToDevice, ctx->copy_stream));
+        d_codes = (const unsigned char*)ctx->b_raw[b].p;
+        d_stride = n;
+    } else {
+        // device-resident codes were produced on the context's stream: the copy stream starts behind it
+        CK(cudaEventRecord(ctx->ev_ready[b], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[b], 0));
+    }
+    const long long work = (long long)n * n_streams / 16 + 1;
+    const int grid = (int)std::min<long long>((work + 255) / 256, 8LL * ctx->sm_count);
+    g711_decode_kernel<<<grid, 256, 0, ctx->copy_stream>>>(d_codes, (short*)ctx->b_stage2[b].p, n_streams, (long long)n, d_stride, law);
+    CK(cudaGetLastError());
+    ctx->launches++;
     CK(cudaEventRecord(ctx->ev_ready[b], ctx->copy_stream));
     ctx->pending.valid = true; ctx->pending.slot = b; ctx->pending.stream0 = stream0; ctx->pending.n_streams = n_streams;
     ctx->pending.n = n;

@@ -58,6 +58,7 @@ struct ewk_ctx {
     int land(int stream0, int n_streams, const void* d_src, long long d_stride, long long n, int stage_slot);
     int flush_pending();
     ewk::DevBuf b_stage2[2];
+    ewk::DevBuf b_raw[2];                    // G.711 codes of a host push (ewk_push_g711), decoded into b_stage2
     ewk::DeviceTables* d_tables = nullptr;
     ewk::TemplateFeat* d_tmpl = nullptr;
     std::vector<ewk::TemplateFeat> h_tmpl;

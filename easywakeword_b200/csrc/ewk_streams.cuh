@@ -122,6 +122,53 @@ struct TraceView {          // optional per-tick trace for parity tests: [n_stre
     double* rms;
 };
 
+// ------------------------------------------------------------------------------------ K0 (G.711 ingest)
+// 8-bit mu-law / A-law codes -> the 16-bit linear samples of ITU-T G.711 (what libsndfile hands librosa.load for such
+// files, and what a telephony feed carries): in[r * stride + i] -> out[r * n + i], i < n.  The 256-entry expansion table is
+// formed in shared memory from the standard's bit layout; 16 codes per thread per step (one 16-byte load, two stores).
+// HBM-bound: 1 byte read + 2 bytes written per sample.  It runs on the copy stream right behind the H2D copy of the
+// codes, so a host feed crosses PCIe at half the bytes of PCM16.
+__global__ void __launch_bounds__(256)
+g711_decode_kernel(const unsigned char* __restrict__ in, short* __restrict__ out, int n_rows, long long n, long long stride, int alaw) {
+    __shared__ short lut[256];
+    {
+        const int c = threadIdx.x;
+        int v;
+        if (alaw) {
+            const int a = c ^ 0x55, e = (a >> 4) & 7, m = a & 0x0F;
+            v = e == 0 ? (m << 4) + 8 : ((m << 4) + 0x108) << (e - 1);
+            v = (a & 0x80) ? v : -v;
+        } else {
+            const int u = ~c & 0xFF;
+            v = ((((u & 0x0F) << 3) + 0x84) << ((u >> 4) & 7)) - 0x84;
+            v = (u & 0x80) ? -v : v;
+        }
+        lut[c] = (short)v;
+    }
+    __syncthreads();
+    const bool vec = (n % 16) == 0 && (stride % 16) == 0 && ((size_t)in & 15) == 0 && ((size_t)out & 15) == 0;
+    const long long per_row = vec ? n / 16 : n;
+    const long long total = per_row * n_rows;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / per_row, j = i - r * per_row;
+        if (vec) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + r * stride) + j);
+            const unsigned w[4] = {q.x, q.y, q.z, q.w};
+            unsigned o[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                o[2 * k] = (unsigned)(unsigned short)lut[w[k] & 0xFF] | ((unsigned)(unsigned short)lut[(w[k] >> 8) & 0xFF] << 16);
+                o[2 * k + 1] = (unsigned)(unsigned short)lut[(w[k] >> 16) & 0xFF] | ((unsigned)(unsigned short)lut[w[k] >> 24] << 16);
+            }
+            uint4* d = reinterpret_cast<uint4*>(out + r * n) + 2 * j;
+            d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        } else {
+            out[r * n + j] = lut[in[r * stride + j]];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ K1
 // src[s * stride + i] (i < n) -> ring of stream stream0 + s at absolute index written + i.
 // 16-byte vector path when source and destination runs are 16-byte aligned, scalar otherwise.

@@ -156,6 +156,11 @@ int ewk_set_stream_params(ewk_ctx* ctx, int stream, const ewk_stream_params* p);
  * the next push, a tick that reaches into it, or a read of stream state; a PINNED host buffer must therefore
  * stay unchanged until one of those calls (or ewk_synchronize) returns.  Pageable buffers are safe on return. */
 int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pcm, int64_t n, int64_t stride, int where);
+/* The same for a G.711 feed: 8-bit mu-law (law = 0) / A-law (law = 1) codes — the telephony wire format, and WAV format
+ * tags 7 / 6 that libsndfile decodes under librosa.load (wakeword.py:588).  The codes are expanded on the device to the
+ * standard's 16-bit linear samples and pushed like PCM16, so a host feed crosses PCIe at one byte per sample.  The
+ * context's rings must be EWK_PCM_I16.  Results equal those of pushing the expanded samples with ewk_push, bit for bit. */
+int ewk_push_g711(ewk_ctx* ctx, int stream0, int n_streams, const uint8_t* codes, int64_t n, int64_t stride, int where, int law);
 /* n_ticks polls of WakeWord._detect_word (wakeword.py:1064-1157) for every stream: adaptive threshold,
  * is_silent, timing state machine, segment cut, then the fused MFCC+match kernel on every candidate.
  * Asynchronous; results are read with ewk_poll / ewk_stream_results. */
