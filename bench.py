@@ -363,12 +363,70 @@ def run_ours(args):
             ms = float(t.item())
         return ms, ctx.launch_count() - l0, n_ev
 
+    audio_per_step_all = n * STEP_SECONDS * world
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     ms_dev, launches, _ = timed(_lib.DEVICE, False, K)          # inputs resident in HBM
     bank.poll()
     ms_e2e, _, n_events = timed(_lib.HOST, True, K)             # host PCM -> rings -> events on host
+
+    # the same end-to-end step fed with G.711 mu-law codes (ewk_push_g711: 1 byte per sample over PCIe, expanded on the
+    # device).  A secondary figure: the audio is the pool after companding, so its events differ from the PCM16 run.
+    g711 = None
+    if not f32 and not args.no_g711:
+        try:
+            from easywakeword_b200.resample import ULAW_TABLE
+            tab = torch.tensor(ULAW_TABLE.astype(np.int32), device=dev)
+            srt, order = torch.sort(tab)
+            codes_pin = _lib.PinnedArray((POOL_SECONDS, n, STEP_SAMPLES), np.uint8)
+            codes_host = torch.from_numpy(codes_pin.array)
+            for j in range(POOL_SECONDS):                           # nearest code of every pool sample, one pool second at a time
+                x = pool_dev[j].to(torch.int32)
+                i = torch.bucketize(x, srt).clamp_(1, 255)
+                pick = torch.where((srt[i] - x).abs() < (srt[i - 1] - x).abs(), i, i - 1)
+                codes_host[j].copy_(order[pick].to(torch.uint8))
+                del x, i, pick
+            torch.cuda.synchronize(dev)
+            while pushed[0] > step_no[0]:                           # consume the PCM push the e2e loop issued ahead
+                bank.tick(TICKS_PER_STEP)
+                step_no[0] += 1
+                bank.poll()
+            gp = [0]
+
+            def g_push():
+                ptr = codes_host.data_ptr() + (gp[0] % POOL_SECONDS) * n * STEP_SAMPLES
+                gp[0] += 1
+                bank.push_g711((ptr, n, STEP_SAMPLES, STEP_SAMPLES), law="ulaw", where=_lib.HOST)
+
+            def g_step():
+                g_push()                                            # the NEXT step's codes: copy + expansion beside this step's kernels
+                bank.tick(TICKS_PER_STEP)
+                return bank.poll()
+
+            g_push()
+            for _ in range(W):
+                g_step()
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record(stream)
+            for _ in range(K):
+                g_step()
+            ctx.join()
+            q1.record(stream)
+            barrier()
+            ms_g = q0.elapsed_time(q1)
+            if world > 1:
+                t = torch.tensor([ms_g], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_g = float(t.item())
+            bank.tick(TICKS_PER_STEP)                               # the push issued ahead by the last step
+            bank.poll()
+            g711 = {"value": audio_per_step_all * K / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g / K,
+                    "h2d_bytes_per_step": n * STEP_SAMPLES, "h2d_gbs_per_gpu": n * STEP_SAMPLES / (ms_g / K * 1e-3) / 1e9,
+                    "what": "e2e with the host feed as G.711 mu-law codes (pool after companding), K0 expansion on the copy stream"}
+        except Exception as e:
+            g711 = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     # the exchange on its own ("report gather latency separately"), and a self-check that the
     # peer-published copy equals an NCCL all-gather of the local records
@@ -554,7 +612,8 @@ def run_ours(args):
                        "streams_per_gpu": n, "ring_seconds": RING_SECONDS, "step_seconds": STEP_SECONDS,
                        "template": word_name, "pcm": pcm_name, "params": PARAMS,
                        "l2": f"inputs larger than L2: {n * STEP_SAMPLES * esz / 1e6:.0f} MB of new PCM per step, "
-                             f"{n * 179200 * esz / 1e9:.2f} GB of rings per GPU",
+                             f"{n * (RING_SECONDS * 16000 + int(2 * STEP_SECONDS * 16000) + 3200) * esz / 1e9:.2f} GB of rings per GPU "
+                             "(10 s + 2.2 s slack)",
                        "overlap": ("K3 of step i runs on a second stream beside K1 of step i+1 (ewk_set_overlap; K1 in its "
                                    "cp.async.bulk form); the timed region ends after the last K3 (ewk_join); per-kernel "
                                    "times are taken in sequential order, each kernel alone")
@@ -571,6 +630,7 @@ def run_ours(args):
                     "host_cpus_rank0": (f"{host_cpus[0]}-{host_cpus[-1]} ({len(host_cpus)})" if host_cpus else None),
                     "bound": f"host->device copy (PCIe): the PCM of a step is {n * STEP_SAMPLES * esz / 1e6:.0f} MB per GPU and every step pays its own "
                              "copy; kernels take ~10 % of the step and overlap the next copy"},
+            "e2e_g711": g711,
             "gpu_launches": int(launches),
             "by_rank": {"device_resident": by_rank[0], "e2e": by_rank[1]},
             "gather": gather_info,
@@ -612,6 +672,7 @@ def main():
                          "copy over NVLink (no collective, no per-step barrier); peer-barrier = same stores, one "
                          "symmetric-memory barrier per step; nccl = all_gather per step; auto = peer when symmetric "
                          "memory is available")
+    ap.add_argument("--no-g711", action="store_true", help="skip the secondary end-to-end leg fed with G.711 mu-law codes")
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU: do not pin each rank to the CPUs next to its GPU")
     ap.add_argument("--no-overlap", action="store_true",
                     help="keep K3 on the context's stream (default: ewk_set_overlap(1), K3 beside the next push)")
