@@ -374,7 +374,7 @@ def run_ours(args):
     # the same end-to-end step fed with G.711 mu-law codes (ewk_push_g711: 1 byte per sample over PCIe, expanded on the
     # device).  A secondary figure: the audio is the pool after companding, so its events differ from the PCM16 run.
     g711 = None
-    if not f32 and not args.no_g711:
+    if not f32 and not args.no_g711 and world == 1:            # single-GPU runs only (a secondary figure)
         try:
             from easywakeword_b200.resample import ULAW_TABLE
             tab = torch.tensor(ULAW_TABLE.astype(np.int32), device=dev)
