@@ -63,6 +63,36 @@ def test_no_gpu_means_loud_failure(lib):
         _lib.Context()
 
 
+@pytest.mark.gpu
+def test_plain_c_client_on_gpu(lib, tmp_path):
+    """The GPU leg of test_plain_c_client (that one runs in the CPU suite, where the client must be refused)."""
+    test_plain_c_client(lib, tmp_path)
+
+
+def test_plain_c_client(lib, tmp_path):
+    """include/ewk.h is a C header and libewk.so a C library: a C program builds against them with gcc alone and, on this
+    box, either scores the reference's self-similarity known answer (GPU) or is refused loudly (no GPU)."""
+    import shutil
+    import subprocess
+    import torch
+    from easywakeword_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "c_abi_client")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"),
+                        os.path.join(REPO, "tests", "c_abi_client.c"), "-o", exe, "-L", libdir, "-lewk", "-lm",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "self-similarity 100.0000  matched 1" in r.stdout and "No reference word set" in r.stdout
+    else:
+        assert r.returncode == 3, r.stdout + r.stderr
+        assert "no CPU fallback" in r.stdout
+
+
 def test_product_does_not_import_oracle():
     """The oracle is test infrastructure: nothing under easywakeword_b200/ may reference it."""
     pkg = os.path.join(REPO, "easywakeword_b200")
