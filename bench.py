@@ -9,12 +9,16 @@ the 10 ticks it covers: K1 ring_push (or direct H2D into the rings), K2 tick_gat
 threshold, is_silent, timing state machine), K3 segment_queue (fused MFCC + template match on every
 candidate the state machine cut).  That is the reference's WakeWord loop (wakeword.py:454-517,
 1036-1157) for 4096 rooms.  Streams shard across ranks (4096 per GPU, weak scaling); the only
-collective is the per-step all-gather of the 8-byte per-stream result records over NCCL.
+exchange is the delivery of the 8-byte per-stream result records to every rank: by peer stores from K2/K3 over NVLink
+with a completion signal (--gather peer, the default when symmetric memory is available) or by one NCCL all-gather per
+step (--gather nccl).
 
 Printed JSON (one line, rank 0): `value` = whole-job audio-s/s with inputs resident in HBM;
 `e2e` = the same through the public API with host (pinned) PCM, H2D copies and the event read-back
 inside the timed region; `roofline` for the dominant kernel from CUDA-event timings taken inside
-this run; `cpu_baseline` = the oracle port timed on this box's cores (N=1 only).
+this run; `cpu_baseline` = the oracle port timed on this box's cores (N=1 only), with a best-effort C + OpenMP
+statement of the same semantics beside it (`best_effort_c`); `e2e_g711` = the end-to-end step fed with G.711 codes;
+`dense` = the per-hop scoring mode (K4).
 `--impl reference` times the reference's CPU algorithm (oracle port, reference-exact statement
 order; librosa itself is not installable offline) on all host cores on the same workload.
 """
