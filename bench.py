@@ -119,37 +119,101 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on host cores
+# CPU arm: the reference's own classes (oracle/_ref staged by oracle/stage_ref.py, driven by oracle/ref_harness.py under
+# the fake clock) when present, else the oracle port — one stream per process on every host core
+THREAD_ENV = ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS")
+
+
+def cpu_kind():
+    """'reference' when the reference's unmodified module is importable on this box, else 'port'."""
+    from oracle import ref_harness
+    return "reference" if ref_harness.reference_available() else "port"
+
+
+def _cpu_check_threads(_):
+    """Runs in every worker right after it starts: one BLAS / OpenMP thread per process, or the arm is oversubscribed."""
+    bad = {k: os.environ.get(k) for k in THREAD_ENV if os.environ.get(k) != "1"}
+    assert not bad, f"worker started without single-thread environment: {bad}"
+    try:
+        from threadpoolctl import threadpool_info
+        import numpy as _np
+        _np.ones((64, 64)) @ _np.ones((64, 64))            # make sure the BLAS pool exists before it is inspected
+        info = threadpool_info()
+        assert all(int(i.get("num_threads", 1)) == 1 for i in info), info
+        return len(info)
+    except ImportError:
+        return -1
+
+
 def _cpu_worker(args):
-    seed, seconds, fast = args
-    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    seed, seconds, mode = args
     from easywakeword_b200 import synth
-    from oracle import ewk_oracle as O
     word, _ = load_word()
     x, _ = synth.stream(seed, RING_SECONDS + seconds + 0.2, word, noise_sigma=0.002, gain=(1.0, 4.0))
     x = synth.from_int16(synth.to_int16(x))
     timing = {}
     p = {k: v for k, v in PARAMS.items() if k != "frame_size"}
-    r = O.detect_stream(x, word, block=PARAMS["frame_size"], fast=fast, timing=timing, **p)
+    if mode == "reference":
+        import contextlib
+        from oracle import ref_harness
+        with open(os.devnull, "w") as null, contextlib.redirect_stdout(null):   # the reference print()s device warnings
+            r = ref_harness.run_reference_stream(x, word, block=PARAMS["frame_size"], timing=timing, keep_audio=False, **p)
+    else:
+        from oracle import ewk_oracle as O
+        r = O.detect_stream(x, word, block=PARAMS["frame_size"], fast=(mode == "port_fast"), timing=timing, **p)
     return timing["t_end"] - timing["t_full"], timing["steady_ticks"] * 0.1, len(r["events"])
 
 
-def cpu_throughput(seconds_per_stream, procs, fast, rounds=1):
-    """audio-s/s of `procs` processes each running the oracle over one stream (steady state only:
-    the ring fill is untimed).  Returns (value, audio_s, wall_s, events)."""
-    import multiprocessing as mp
-    ctx = mp.get_context("spawn")
+class CpuPool:
+    """`procs` spawn-context workers that inherit *_NUM_THREADS=1 from the moment they start (numpy and its BLAS pool
+    are imported while the worker re-imports this module, before any task runs: setting the variables inside a task is
+    too late and left the round-1 arm 2-5x oversubscribed)."""
+
+    def __init__(self, procs):
+        import multiprocessing as mp
+        self.procs = procs
+        saved = {k: os.environ.get(k) for k in THREAD_ENV}
+        for k in THREAD_ENV:
+            os.environ[k] = "1"
+        try:
+            self.pool = mp.get_context("spawn").Pool(procs)
+            self.blas_pools = self.pool.map(_cpu_check_threads, range(procs), chunksize=1)
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+    def run(self, seconds_per_stream, mode, seed0=SEED0):
+        """Every worker runs the CPU path over one stream (steady state timed, ring fill untimed).
+        -> (audio_s, wall_s = slowest worker, events, outer wall)"""
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, [(seed0 + i, seconds_per_stream, mode) for i in range(self.procs)], chunksize=1)
+        return sum(a for _, a, _ in res), max(w for w, _, _ in res), sum(e for _, _, e in res), time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_throughput(seconds_per_stream, procs, mode, rounds=1, pool=None):
+    """audio-s/s of `procs` processes each running the CPU path over one stream per round.  Every process works
+    concurrently, so a round's throughput is its summed audio over the slowest worker's steady-state wall time.
+    Returns (value, audio_s, wall_s, events)."""
+    own = pool is None
+    pool = pool or CpuPool(procs)
     tot_audio = tot_wall = 0.0
     events = 0
-    with ctx.Pool(procs) as pool:
+    try:
         for r in range(rounds):
-            t0 = time.perf_counter()
-            res = pool.map(_cpu_worker, [(SEED0 + r * procs + i, seconds_per_stream, fast) for i in range(procs)])
-            wall_outer = time.perf_counter() - t0
-            # every process works concurrently: throughput = sum of per-process rates
-            tot_audio += sum(a for _, a, _ in res)
-            tot_wall += max(w for w, _, _ in res)
-            events += sum(e for _, _, e in res)
+            a, w, e, _ = pool.run(seconds_per_stream, mode, SEED0 + r * procs)
+            tot_audio += a
+            tot_wall += w
+            events += e
+    finally:
+        if own:
+            pool.close()
     return tot_audio / tot_wall, tot_audio, tot_wall, events
 
 
@@ -187,39 +251,73 @@ def cpu_dense_throughput(seconds=3.0):
     return seconds / dt, len(hops) / dt
 
 
+def bench_config(n, pcm_name, world, word_name):
+    """The workload both arms run (the GPU arm whole, the CPU arm on a bounded sample of it): `config` of the line."""
+    esz = 4 if pcm_name == "float32" else 2
+    return {"workload": ("configs[2]" if n == N_STREAMS else "configs[3] shard size" if n == 8192 else "custom") +
+                        f": {n} streams per B200, 10 s {pcm_name} rings, 1.0 s of new audio per stream per step = 10 ticks of "
+                        "the gated level-1+2 path (ring write, adaptive silence threshold, is_silent, timing state machine, "
+                        "fused MFCC+match on every candidate segment)",
+            "streams_per_gpu": n, "ring_seconds": RING_SECONDS, "step_seconds": STEP_SECONDS,
+            "template": word_name, "pcm": pcm_name, "params": PARAMS,
+            "l2": f"inputs larger than L2: {n * STEP_SAMPLES * esz / 1e6:.0f} MB of new PCM per step, "
+                  f"{n * (RING_SECONDS * 16000 + int(2 * STEP_SECONDS * 16000) + 3200) * esz / 1e9:.2f} GB of rings per GPU "
+                  "(10 s + 2.2 s slack)",
+            "parallelism": f"streams sharded {n}/GPU x {world}" if world > 1 else "1 GPU"}
+
+
 def run_reference(args):
+    """The reference's CPU implementation of the path on every host core, on a bounded sample of the GPU arm's workload:
+    per step every core runs the reference over `sample_s` seconds of one of the workload's streams (the streams are
+    independent, so the 4096-stream step is this per-stream work repeated).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    K, W = args.steps, args.warmup
-    # a step = every core runs the reference algorithm over `sample_s` seconds of one stream
-    sample_s = 8.0
-    if W > 0:
-        cpu_throughput(1.0, cores, fast=False, rounds=1)
+    K, W = max(1, args.steps), args.warmup
+    kind = cpu_kind()
+    mode = "reference" if kind == "reference" else "port"
+    sample_s = 4.0
+    word, word_name = load_word()
+    pool = CpuPool(cores)
     t0 = time.perf_counter()
-    val, audio, wall, ev = cpu_throughput(sample_s, cores, fast=False, rounds=max(1, K))
+    for _ in range(W):
+        pool.run(1.0, mode)
+    audio = wall = 0.0
+    ev = 0
+    step_ms = []
+    for k in range(K):
+        a, w, e, _ = pool.run(sample_s, mode, SEED0 + k * cores)
+        audio += a
+        wall += w
+        ev += e
+        step_ms.append(1e3 * w)
+    pool.close()
     total_wall = time.perf_counter() - t0
+    val = audio / wall
+    what = ("the reference's own SoundBuffer / WordMatcher / WakeWord._detect_word (easywakeword/wakeword.py unmodified, "
+            "staged by oracle/stage_ref.py, on the restated-librosa shim; fake clock of oracle/ref_harness.py)"
+            if kind == "reference" else
+            "oracle port in the reference's statement order (the reference module is not staged on this box)")
+    pcm_name = "float32" if args.pcm == "f32" else "int16"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
-        "ms_per_step": 1e3 * wall / max(1, K), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * wall / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "gated level-1+2 path, 10 s rings, frame_size 1600, bundled-word template; "
-                               f"bounded sample: {cores} streams x {sample_s} s steady-state per step "
-                               "(the 4096-stream batch is the same per-stream work repeated)",
-                   "streams_per_step": cores, "seconds_per_stream": sample_s},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cores} processes x {sample_s} s x {max(1, K)} steps of the oracle restatement "
-                                   "(reference statement order, per-sample ring loop); librosa not installable offline"},
+        "config": bench_config(args.streams, pcm_name, max(1, args.gpus), word_name),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{cores} processes (one BLAS/OpenMP thread each, checked in every worker) x {sample_s} s "
+                                   f"steady state of one workload stream each per step x {K} steps = {audio:.0f} audio-s; {what}",
+                         "per_core": val / cores},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": total_wall, "level2_events": ev,
+        "ms_per_step_minmax": [min(step_ms), max(step_ms)],
     }
     # context, not the arm's value: what a tuned C + OpenMP statement of the same semantics reaches on these cores
     try:
-        word, _ = load_word()
-        pool = np.empty((POOL_SECONDS, 256, STEP_SAMPLES), np.int16)
-        make_pool(0, 256, word, pool)
-        vc, evc, audio_c = cpu_best_effort_c(pool, word, cores, streams=256, repeats=3, rounds=4)
+        pool_pcm = np.empty((POOL_SECONDS, 256, STEP_SAMPLES), np.int16)
+        make_pool(0, 256, word, pool_pcm)
+        vc, evc, audio_c = cpu_best_effort_c(pool_pcm, word, cores, streams=256, repeats=3, rounds=4)
         line["best_effort_c"] = {"value": vc, "unit": UNIT, "cores": cores, "kind": "port (C, OpenMP over streams)",
                                  "sample": f"4 x 256 streams x 30 s = {audio_c:.0f} audio-s, {evc} level-2 evaluations"}
     except Exception as e:
@@ -583,23 +681,31 @@ def run_ours(args):
                     "tick_gate": kroof("tick_gate"),
                     "whole_step_frac": (n * STEP_SAMPLES * esz) * K / (ms_dev * 1e-3) / 1e9 / hbm_peak}
         cpu = None
+        best_c = None
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            v, audio, wall, _ = cpu_throughput(3.0, cores, fast=False)
-            vf, _, _, _ = cpu_throughput(6.0, cores, fast=True)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{cores} processes x 3.0 s steady-state of one stream each, oracle in the reference's "
-                             f"statement order; vectorised oracle variant: {vf:.1f} audio-s/s",
+            kind = cpu_kind()
+            cpool = CpuPool(cores)
+            v, audio, wall, _ = cpu_throughput(4.0, cores, "reference" if kind == "reference" else "port", pool=cpool)
+            vf, _, _, _ = cpu_throughput(4.0, cores, "port_fast", pool=cpool)
+            cpool.close()
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "per_core": v / cores,
+                   "sample": f"{cores} processes (one BLAS/OpenMP thread each, checked in every worker) x 4.0 s steady state of "
+                             "one workload stream each; " +
+                             ("the reference's own SoundBuffer / WordMatcher / _detect_word (oracle/_ref, unmodified) under the fake clock"
+                              if kind == "reference" else "oracle port in the reference's statement order") +
+                             f"; vectorised oracle variant: {vf:.1f} audio-s/s",
                    "vectorised_port_value": vf}
             if pool_pin.array.dtype == np.int16:
                 try:
                     vc, evc, audio_c = cpu_best_effort_c(pool_pin.array, word, cores)
-                    cpu["best_effort_c"] = {"value": vc, "unit": UNIT, "cores": cores, "kind": "port (C, OpenMP over streams)",
-                                            "sample": f"3 x 1024 streams x 30 s of the bench pool = {audio_c:.0f} audio-s, "
-                                                      f"{evc} level-2 evaluations; not the reference's code path: what a "
-                                                      "tuned CPU implementation of the same semantics reaches on this host"}
+                    best_c = {"value": vc, "unit": UNIT, "cores": cores, "kind": "port (C, OpenMP over streams)",
+                              "sample": f"3 x 1024 streams x 30 s of the bench pool = {audio_c:.0f} audio-s, "
+                                        f"{evc} level-2 evaluations; not the reference's code path: what a "
+                                        "tuned CPU implementation of the same semantics reaches on this host"}
                 except Exception as e:                              # no gcc on the box: the baseline above stands alone
-                    cpu["best_effort_c"] = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
+                    best_c = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
+                cpu["best_effort_c"] = best_c
         dense_cpu = None
         if world == 1 and not args.no_cpu:
             dv, dw = cpu_dense_throughput(3.0)
@@ -609,24 +715,15 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("configs[2]" if n == N_STREAMS else "configs[3] shard size" if n == 8192 else "custom") +
-                                   f": {n} streams per B200, 10 s {pcm_name} rings, 1.0 s of new audio per stream "
-                                   "per step = 10 ticks of the gated level-1+2 path (K1 ring_push, K2 tick_gate, "
-                                   "K3 fused MFCC+match on every candidate segment)",
-                       "streams_per_gpu": n, "ring_seconds": RING_SECONDS, "step_seconds": STEP_SECONDS,
-                       "template": word_name, "pcm": pcm_name, "params": PARAMS,
-                       "l2": f"inputs larger than L2: {n * STEP_SAMPLES * esz / 1e6:.0f} MB of new PCM per step, "
-                             f"{n * (RING_SECONDS * 16000 + int(2 * STEP_SECONDS * 16000) + 3200) * esz / 1e9:.2f} GB of rings per GPU "
-                             "(10 s + 2.2 s slack)",
-                       "overlap": ("K3 of step i runs on a second stream beside K1 of step i+1 (ewk_set_overlap; K1 in its "
-                                   "cp.async.bulk form); the timed region ends after the last K3 (ewk_join); per-kernel "
-                                   "times are taken in sequential order, each kernel alone")
-                       if overlap else "off: K1, K2, K3 in sequence on one stream",
-                       "parallelism": (f"streams sharded {n}/GPU x {world}, " +
-                                       ("8 B/stream result records + completion signal stored by K2/K3 into every rank's copy "
+            "config": bench_config(n, pcm_name, world, word_name),
+            "execution": {"overlap": ("K3 of step i runs on a second stream beside K1 of step i+1 (ewk_set_overlap; K1 in its "
+                                      "cp.async.bulk form); the timed region ends after the last K3 (ewk_join); per-kernel "
+                                      "times are taken in sequential order, each kernel alone")
+                          if overlap else "off: K1, K2, K3 in sequence on one stream",
+                          "exchange": (("8 B/stream result records + completion signal stored by K2/K3 into every rank's copy "
                                         "over NVLink" + (", one barrier per step" if args.gather == "peer-barrier" else
                                                          " (put-with-signal, no collective)") if exchange is not None else
-                                        "all_gather of 8 B/stream results per step")) if world > 1 else "1 GPU"},
+                                        "all_gather of 8 B/stream results per step")) if world > 1 else None},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * STEP_SAMPLES * esz,
                     "d2h_bytes_per_step": int(8 + ev_per_step * 40), "ms_per_step": ms_e2e / K,
@@ -640,6 +737,8 @@ def run_ours(args):
             "gather": gather_info,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "best_effort_c": best_c,
+            "e2e_vs_best_effort_c": (e2e_val / best_c["value"]) if best_c and "value" in best_c else None,
             "dense": {"what": f"A9 per-hop scoring: 100 hops x {n} streams per step, 4 FFT frames per hop (1 stream-grid + 3 "
                               "window-edge), K1 ring_push + K4 dense_score, scores left on the device",
                       "value": audio_per_step * dense_steps / (ms_dense * 1e-3), "unit": UNIT,

@@ -11,10 +11,12 @@ sounddevice) and drives its classes deterministically:
     real ``SoundBuffer._add_sound_to_buffer`` in ``block``-sample callbacks.
   * level 3 (``_transcribe_audio``) is stubbed to return None (out of scope).
 
-/root/reference does not exist on the GPU box: this module is only used HERE, by
-oracle/gen_golden.py (to write tests/golden/*) and by the CPU-side tests that pin
-oracle/ewk_oracle.py against the reference.  Nothing under -m gpu, smoke() or
-bench.py imports it.
+/root/reference does not exist on the GPU box.  HERE this module is used by oracle/gen_golden.py
+(to write tests/golden/*) and by the CPU-side tests that pin oracle/ewk_oracle.py against the
+reference.  On the GPU box the only consumer is bench.py's CPU arm (`--impl reference`,
+`cpu_baseline`): when oracle/stage_ref.py has staged the reference's unmodified module under
+oracle/_ref/ (git-ignored, travels with gpurun), the arm times THESE classes (kind "reference")
+instead of the oracle port.  Nothing under -m gpu or smoke() imports it.
 """
 from __future__ import annotations
 
@@ -25,9 +27,21 @@ import threading
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("EWK_REFERENCE_ROOT", "/root/reference")
 _SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _find_root():
+    """EWK_REFERENCE_ROOT, else the read-only tree, else the copy staged by oracle/stage_ref.py."""
+    env = os.environ.get("EWK_REFERENCE_ROOT")
+    for root in ([env] if env else ["/root/reference", _STAGED]):
+        if os.path.isfile(os.path.join(root, "easywakeword", "wakeword.py")):
+            return root
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
@@ -115,7 +129,7 @@ def make_wakeword(mod, wavword, *, textword="computer", numberofwords=1, timeout
     return ww
 
 
-def run_reference_stream(stream, template, *, block=512, restart_on_timeout=True, **params):
+def run_reference_stream(stream, template, *, block=512, restart_on_timeout=True, timing=None, keep_audio=True, **params):
     """Drive the reference's SoundBuffer + WordMatcher + _detect_word over `stream`.
 
     template: float32 samples (set_reference) or a WAV path (load_reference_from_file).
@@ -156,8 +170,10 @@ def run_reference_stream(stream, template, *, block=512, restart_on_timeout=True
 
         def matches_logged(audio, threshold=75.0):
             ok, sim = real_matches(audio, threshold=threshold)
-            events.append({"tick": clock.k, "seg_len": int(len(audio)), "score": float(sim),
-                           "matched": bool(ok), "audio": np.array(audio, dtype=np.float64)})
+            ev = {"tick": clock.k, "seg_len": int(len(audio)), "score": float(sim), "matched": bool(ok)}
+            if keep_audio:
+                ev["audio"] = np.array(audio, dtype=np.float64)
+            events.append(ev)
             return ok, sim
 
         matcher.matches = matches_logged
@@ -166,6 +182,9 @@ def run_reference_stream(stream, template, *, block=512, restart_on_timeout=True
         try:
             ww._wait_for_buffer()
             full_tick = clock.k
+            if timing is not None:                     # bench.py: steady state only (the ring fill is untimed)
+                import time as _time
+                timing["t_full"] = _time.perf_counter()
             while True:
                 try:
                     ww._detect_word()
@@ -175,6 +194,10 @@ def run_reference_stream(stream, template, *, block=512, restart_on_timeout=True
                         break
         except StopIteration:
             pass
+        if timing is not None:
+            import time as _time
+            timing["t_end"] = _time.perf_counter()
+            timing["steady_ticks"] = clock.k - (full_tick if full_tick is not None else clock.k)
         return {
             "full_tick": full_tick,
             "trace_tick": np.asarray(trace["tick"], dtype=np.int64),
