@@ -21,7 +21,8 @@ class EwkError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("n_streams", C.c_int32), ("ring_samples", C.c_int32), ("slack_samples", C.c_int32),
-                ("pcm_format", C.c_int32), ("max_templates", C.c_int32), ("max_events", C.c_int32)]
+                ("pcm_format", C.c_int32), ("max_templates", C.c_int32), ("max_events", C.c_int32),
+                ("preemphasis", C.c_float), ("n_mfcc", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32)]
 
 
 _lib = None
@@ -106,10 +107,10 @@ class Context:
     """Owns one ewk_ctx (one GPU)."""
 
     def __init__(self, device=0, n_streams=0, ring_samples=160000, slack_samples=16000, pcm_format=PCM_I16,
-                 max_templates=4, max_events=0):
+                 max_templates=4, max_events=0, preemphasis=0.0, n_mfcc=0):
         self.lib = load()
         self.cfg = Config(n_streams, ring_samples, slack_samples, pcm_format, max_templates,
-                          max_events or max(1024, 4 * n_streams))
+                          max_events or max(1024, 4 * n_streams), float(preemphasis), int(n_mfcc), 0, 0)
         h = C.c_void_p()
         rc = self.lib.ewk_create(device, C.byref(self.cfg), C.byref(h))
         if rc != EWK_OK:

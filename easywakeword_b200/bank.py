@@ -34,7 +34,7 @@ class WakeWordBank:
                  pre_speech_silence: float = 0.8, speech_duration_min: Optional[float] = None,
                  speech_duration_max: Optional[float] = None, post_speech_silence: float = 0.4,
                  timeout: float = 30.0, max_push_seconds: float = 1.0, max_events: int = 0,
-                 cuda_stream: Optional[int] = None, overlap: bool = False):
+                 cuda_stream: Optional[int] = None, overlap: bool = False, preemphasis: float = 0.0, n_mfcc: int = 20):
         if n_streams < 1:
             raise ValueError("n_streams must be at least 1")
         if buffer_seconds <= 0:
@@ -49,7 +49,8 @@ class WakeWordBank:
         slack = int(max_push_seconds * 16000) + 2 * max(frame_size, TICK_SAMPLES)
         self.ctx = _lib.Context(device=device, n_streams=n_streams, ring_samples=buffer_seconds * 16000,
                                 slack_samples=slack, pcm_format=fmt, max_templates=max(1, len(templates)),
-                                max_events=max_events or max(4096, 2 * n_streams))
+                                max_events=max_events or max(4096, 2 * n_streams), preemphasis=preemphasis,
+                                n_mfcc=n_mfcc)
         if cuda_stream is not None:
             self.ctx.set_cuda_stream(cuda_stream)
         if overlap:

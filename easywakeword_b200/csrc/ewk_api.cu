@@ -70,6 +70,14 @@ extern "C" int ewk_create(int device, const ewk_config* cfg, ewk_ctx** out) {
         g_create_error = "ewk_create: invalid ewk_config";
         return EWK_ERR_ARG;
     }
+    if (!(cfg->preemphasis >= 0.f && cfg->preemphasis < 1.f)) {
+        g_create_error = "ewk_create: preemphasis must be in [0, 1)";
+        return EWK_ERR_ARG;
+    }
+    if (cfg->n_mfcc < 0 || cfg->n_mfcc > EWK_N_MFCC || cfg->reserved0 != 0 || cfg->reserved1 != 0) {
+        g_create_error = "ewk_create: n_mfcc must be 0 (= 20) or in [1, 20]; reserved fields must be 0";
+        return EWK_ERR_ARG;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -145,6 +153,9 @@ int ewk_ctx::init() {
     // flat tables, then the per-CTA layout of them (FrameTables image) that K3 / K4 copy into shared memory
     FrameTables* img = new FrameTables();
     load_frame_tables(*img, h, 0, 1);
+    img->preemph = cfg.preemphasis;
+    img->n_mfcc = cfg.n_mfcc > 0 ? cfg.n_mfcc : N_MFCC;
+    img->pad_[0] = img->pad_[1] = 0;
     CK(cudaMalloc((void**)&d_tables, FRAME_IMAGE_OFFSET + sizeof(FrameTables)));
     CK(cudaMemcpy(d_tables, h, sizeof(DeviceTables), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(reinterpret_cast<char*>(d_tables) + FRAME_IMAGE_OFFSET, img, sizeof(FrameTables), cudaMemcpyHostToDevice));
@@ -153,7 +164,9 @@ int ewk_ctx::init() {
     h_tmpl.assign(cfg.max_templates, TemplateFeat{});
     CK(cudaMalloc(&d_tmpl, sizeof(TemplateFeat) * cfg.max_templates));
     CK(cudaMemset(d_tmpl, 0, sizeof(TemplateFeat) * cfg.max_templates));
-    CK(cudaFuncSetAttribute(segment_mfcc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CK(cudaFuncSetAttribute(segment_mfcc_match_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
+    CK(cudaFuncSetAttribute(segment_mfcc_match_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
     int rc = init_streams();
     if (rc != EWK_OK) return rc;
@@ -206,7 +219,8 @@ int ewk_ctx::launch_segments(const SegDesc* d_segs, int n_seg, int max_frames, l
         lm = (float*)b_lm.p;
     }
     cudaEvent_t pe = prof_begin(3);
-    segment_mfcc_match_kernel<<<n_seg, SEG_THREADS, seg_smem_bytes(cap), stream>>>(
+    auto k3 = cfg.preemphasis != 0.f ? segment_mfcc_match_kernel<true> : segment_mfcc_match_kernel<false>;
+    k3<<<n_seg, SEG_THREADS, seg_smem_bytes(cap), stream>>>(
         d_tables, d_segs, cap, ws, lm, d_tmpl, n_tmpl, tmpl_first, threshold, d_feat, d_frames, d_scores, d_matched);
     prof_end(pe, 3);
     CK(cudaGetLastError());
@@ -543,13 +557,14 @@ int ewk_ctx::init_streams() {
     if (use_lm) CK(cudaMalloc(&bank.lm_ws, sizeof(float) * (size_t)queue_grid() * SEG_SMEM_FRAMES * LM_ROW));
     std::vector<StreamState> st(n);
     std::memset(st.data(), 0, sizeof(StreamState) * n);
-    for (auto& x : st) x.thr = 0.01;                                                // wakeword.py:431
+    for (auto& x : st) { x.thr = 0.01; x.last_ev = -1; }                            // wakeword.py:431
     CK(cudaMemcpyAsync(bank.st, st.data(), sizeof(StreamState) * n, cudaMemcpyHostToDevice, stream));
     ewk_stream_params dp;
     ewk_default_stream_params(&dp);
     StreamParams sp;
     std::memcpy(&sp, &dp, sizeof(sp));
     h_prm.assign(n, sp);
+    max_post = sp.post_speech_silence;
     CK(cudaMemcpyAsync(bank.prm, h_prm.data(), sizeof(StreamParams) * n, cudaMemcpyHostToDevice, stream));
     std::vector<StreamResult> rs(n);
     for (auto& r : rs) { r.score = std::nanf(""); r.flags = 0; }
@@ -559,7 +574,9 @@ int ewk_ctx::init_streams() {
     h_visible_lb.assign(n, 0);
     h_tick.assign(n, 0);
     h_frame_size.assign(n, 0);
-    CK(cudaFuncSetAttribute(segment_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CK(cudaFuncSetAttribute(segment_queue_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
+    CK(cudaFuncSetAttribute(segment_queue_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
     CK(cudaFuncSetAttribute(ring_push_bulk_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CK(cudaFuncSetAttribute(ring_push_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -655,6 +672,8 @@ extern "C" int ewk_set_stream_params(ewk_ctx* ctx, int stream, const ewk_stream_
     std::memcpy(&sp, p, sizeof(sp));
     const int a = stream < 0 ? 0 : stream, b = stream < 0 ? n : stream + 1;
     for (int s = a; s < b; s++) ctx->h_prm[s] = sp;
+    ctx->max_post = 0.0;
+    for (int s = 0; s < n; s++) ctx->max_post = std::max(ctx->max_post, ctx->h_prm[s].post_speech_silence);
     CK(cudaMemcpyAsync(ctx->bank.prm + a, ctx->h_prm.data() + a, sizeof(StreamParams) * (size_t)(b - a),
                        cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -748,6 +767,13 @@ extern "C" int ewk_push(ewk_ctx* ctx, int stream0, int n_streams, const void* pc
                       s, ahead, B.P - B.R);
             return EWK_ERR_STATE;
         }
+        // before the first full tick every sample from 0 upward is still needed (the first-full tick forms all chunks
+        // from samples): nothing may wrap onto them
+        if (ctx->h_visible_lb[s] < B.R && ctx->h_written[s] + n > (long long)B.P) {
+            ctx->fail("ewk_push: stream %d would hold %lld samples before its first full tick, more than the physical ring "
+                      "(%d); call ewk_tick first", s, ctx->h_written[s] + n, B.P);
+            return EWK_ERR_STATE;
+        }
     }
     const size_t esz = B.fmt == 1 ? 2 : 4;
     if (where != EWK_HOST) return ctx->land(stream0, n_streams, pcm, stride, n, -1);
@@ -792,6 +818,13 @@ extern "C" int ewk_push_g711(ewk_ctx* ctx, int stream0, int n_streams, const uin
         if (ctx->h_visible_lb[s] >= B.R && ahead > (long long)(B.P - B.R)) {
             ctx->fail("ewk_push_g711: stream %d would hold %lld un-gated samples, more than slack_samples=%d; call ewk_tick first",
                       s, ahead, B.P - B.R);
+            return EWK_ERR_STATE;
+        }
+        // before the first full tick every sample from 0 upward is still needed (the first-full tick forms all chunks
+        // from samples): nothing may wrap onto them
+        if (ctx->h_visible_lb[s] < B.R && ctx->h_written[s] + n > (long long)B.P) {
+            ctx->fail("ewk_push_g711: stream %d would hold %lld samples before its first full tick, more than the physical ring "
+                      "(%d); call ewk_tick first", s, ctx->h_written[s] + n, B.P);
             return EWK_ERR_STATE;
         }
     }
@@ -883,15 +916,17 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     // guard keeps un-gated samples within the slack, which protects [visible - R, visible); the segments of these ticks
     // start at most 3 s + n_ticks x 0.1 s before it, hence the ring-length condition.
     cudaStream_t ks = ctx->stream;
-    if (ctx->overlap && (long long)B.R >= MAX_SEG + (long long)(n_ticks + 2) * TICK && !want) {
+    // ... plus the tail a cut drops: n_back = segment + n_drop, n_drop ~ (post_speech_silence + 0.05 s) and one tick of slop
+    const long long drop_reserve = (long long)std::ceil((ctx->max_post + 0.15) * 16000.0);
+    if (ctx->overlap && (long long)B.R >= MAX_SEG + (long long)(n_ticks + 2) * TICK + drop_reserve && !want) {
         CK(cudaEventRecord(ctx->ev_gate, ctx->stream));
         CK(cudaStreamWaitEvent(ctx->match_stream, ctx->ev_gate, 0));
         ks = ctx->match_stream;
     }
     ctx->last_match_stream = ks;
     pe = ctx->prof_begin(2, ks);
-    segment_queue_kernel<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ks>>>(
-        ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
+    auto k3q = ctx->cfg.preemphasis != 0.f ? segment_queue_kernel<true> : segment_queue_kernel<false>;
+    k3q<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ks>>>(ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
     ctx->prof_end(pe, 2, ks);
     CK(cudaGetLastError());
     if (ks != ctx->stream) {
@@ -1143,9 +1178,10 @@ extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl
     A.keep_end = (long long*)ctx->b_keep_end.p;
     const size_t smem = dense_smem_bytes(A.DG, A.T);
     if (smem > 227 * 1024) { ctx->fail("ewk_dense_scores: templates too long for shared memory (%zu B)", smem); return EWK_ERR_ARG; }
-    CK(cudaFuncSetAttribute(dense_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto k4 = ctx->cfg.preemphasis != 0.f ? dense_score_kernel<true> : dense_score_kernel<false>;
+    CK(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t pe = ctx->prof_begin(4);
-    dense_score_kernel<<<B.n_streams, DENSE_THREADS, smem, ctx->stream>>>(ctx->d_tables, B, ctx->d_tmpl, A);
+    k4<<<B.n_streams, DENSE_THREADS, smem, ctx->stream>>>(ctx->d_tables, B, ctx->d_tmpl, A);
     ctx->prof_end(pe, 4);
     CK(cudaGetLastError());
     ctx->launches++;
@@ -1179,6 +1215,7 @@ extern "C" int ewk_set_results_buffer(ewk_ctx* ctx, void* device_ptr) {
     if (!ctx) return EWK_ERR_ARG;
     int rc = need_streams(ctx, "ewk_set_results_buffer");
     if (rc) return rc;
+    if ((size_t)device_ptr & 7) { ctx->fail("ewk_set_results_buffer: the buffer must be 8-byte aligned (records are stored as one 64-bit word)"); return EWK_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     StreamResult* dst = device_ptr ? (StreamResult*)device_ptr : (StreamResult*)ctx->own_results;
     if (dst != ctx->bank.results) {

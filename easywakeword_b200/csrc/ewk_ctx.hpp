@@ -76,6 +76,7 @@ struct ewk_ctx {
     int pushes_since_tick = 0;
     long long launches = 0;
     std::vector<ewk::StreamParams> h_prm;
+    double max_post = 0.4;                 // largest post_speech_silence of any stream (overlap-mode ring reserve)
     std::vector<long long> h_written;      // host mirror of StreamState.written
     std::vector<long long> h_visible_lb;   // lower bound of StreamState.visible (audio-clock overrun check)
     std::vector<long long> h_tick;

@@ -93,6 +93,7 @@ __device__ __forceinline__ void pool_item(float& n, float& mean, float& M2, floa
     n = nn;
 }
 
+template <bool PRE>
 __global__ void __launch_bounds__(DENSE_THREADS, 2)
 dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, DenseArgs A) {
     extern __shared__ __align__(16) float smem[];
@@ -115,7 +116,6 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
     const int s = blockIdx.x;
     copy_frame_tables(*ft, T, tid, DENSE_THREADS);
     float* scr = scratch + warp * SCR_WARP;
-    init_warp_scratch(scr, lane);
     for (int i = tid; i < A.DG; i += DENSE_THREADS) g2tag[i] = 0x7fc00001;     // matches no floor
     __syncthreads();
 
@@ -126,6 +126,11 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
     rd.f = B.fmt == 0 ? (const float*)((const char*)B.ring + (size_t)s * B.P * esz) : nullptr;
     rd.q = B.fmt == 1 ? (const short*)((const char*)B.ring + (size_t)s * B.P * esz) : nullptr;
     rd.ring = B.P;
+    __syncthreads();
+    rd.pre = PRE ? ft->preemph : 0.f;
+    // stream-grid frames are read through a view that starts `back` samples early, so that pre-emphasis finds x[n-1]
+    // of the frame's first sample inside the view (no window starts there); without pre-emphasis the view is the frame
+    constexpr int back = PRE ? 2 : 0;
 
     int max_n = 0, min_n = INT_MAX;
     for (int k = 0; k < A.T; k++) { max_n = max(max_n, A.t[k].n); min_n = min(min_n, A.t[k].n); }
@@ -173,10 +178,10 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
             int f0;
             if (job < n_g) {
                 // absolute first sample 160 g - 256 (unmasked frame of the stream grid)
-                int pos = hs_pos + 160 * (gfrom_rel + job) - N_FFT / 2;       // |offset| < P: one wrap
+                int pos = hs_pos + 160 * (gfrom_rel + job) - N_FFT / 2 - back;       // |offset| < P: one wrap
                 if (pos < 0) pos += B.P; else if (pos >= B.P) pos -= B.P;
-                rd.start = pos; rd.len = N_FFT;
-                f0 = 0;
+                rd.start = pos; rd.len = N_FFT + back;
+                f0 = back;
                 int r = gfrom_row + job; if (r >= A.DG) r -= A.DG;
                 row = G + r * ROW;
                 if (lane == 0) g2tag[r] = 0x7fc00001;
@@ -194,7 +199,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                 row = edge + ((k * DH + hl) * 4 + e) * ROW;
             }
             float2 x[8];
-            load_frame_pairs_at(rd, f0, lane, x);
+            load_frame_pairs_at<PRE>(rd, f0, lane, x);
             float mn, mx;
             warp_frame_mfcc(x, *ft, scr, lane, -INFINITY, row, mn, mx);
             if (lane == 0) { row[N_MFCC] = mn; row[N_MFCC + 1] = mx; }
@@ -228,11 +233,11 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                 for (int i = warp; i < span; i += DENSE_WARPS) {
                     int r = row_lo + i; if (r >= A.DG) r -= A.DG;
                     if (!(G[r * ROW + N_MFCC] < fstar) || g2tag[r] == fbits) continue;      // warp-uniform
-                    int pos = hs_pos + 160 * (glo_rel + i) - N_FFT / 2;
+                    int pos = hs_pos + 160 * (glo_rel + i) - N_FFT / 2 - back;
                     if (pos < 0) pos += B.P; else if (pos >= B.P) pos -= B.P;
-                    rd.start = pos; rd.len = N_FFT;
+                    rd.start = pos; rd.len = N_FFT + back;
                     float2 x[8];
-                    load_frame_pairs_at(rd, 0, lane, x);
+                    load_frame_pairs_at<PRE>(rd, back, lane, x);
                     float mn, mx;
                     warp_frame_mfcc(x, *ft, scr, lane, fstar, G2 + r * N_MFCC, mn, mx);
                     if (lane == 0) g2tag[r] = fbits;
@@ -306,7 +311,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                 const int e = __ffs(mm) - 1;
                 const int t = e < 2 ? e : tp.t_hi + 1 + (e - 2);
                 float2 x[8];
-                load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
+                load_frame_pairs_at<PRE>(rd, t * HOP - N_FFT / 2, lane, x);
                 float mn, mx;
                 warp_frame_mfcc(x, *ft, scr, lane, floor_db, patch + e * N_MFCC, mn, mx);
             }
@@ -316,7 +321,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                 if (cls == 0 || !(G[r * ROW + N_MFCC] < floor_db)) return lane < N_MFCC ? G[r * ROW + lane] : 0.f;
                 if (cls == 1) return lane < N_MFCC ? G2[r * N_MFCC + lane] : 0.f;
                 float2 x[8];
-                load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
+                load_frame_pairs_at<PRE>(rd, t * HOP - N_FFT / 2, lane, x);
                 float mn, mx;
                 __syncwarp();
                 warp_frame_mfcc(x, *ft, scr, lane, floor_db, patch + 4 * N_MFCC, mn, mx);
@@ -362,8 +367,9 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
             }
             for (int e = 2; e < n_edge; e++) pool_item(n, mean, M2, 1.f, edge_value(e), 0.f);
             const float sd = sqrtf(M2 / (float)tp.F);
-            const float sc = similarity_score_warp(lane < N_MFCC ? tf.mean[lane] : 0.f, lane < N_MFCC ? tf.std[lane] : 0.f,
-                                                   lane < N_MFCC ? mean : 0.f, lane < N_MFCC ? sd : 0.f);
+            const int nk = ft->n_mfcc;
+            const float sc = similarity_score_warp(lane < nk ? tf.mean[lane] : 0.f, lane < nk ? tf.std[lane] : 0.f,
+                                                   lane < nk ? mean : 0.f, lane < nk ? sd : 0.f);
             if (lane == 0) *outp = sc;
         }
         __syncthreads();

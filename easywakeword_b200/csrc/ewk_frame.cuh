@@ -67,6 +67,10 @@ struct FrameTables {
     int mfirst[4 * 32];           // first FFT bin of interval lane + 32 j + 1, [j][lane]
     int coef_of_lane[32];         // which MFCC coefficient the lane holds after warp_dct20 (-1: none)
     float4 dct[32 * DCT_LANE4];        // per lane: [band slot s < 4][m < 10] = dct(k = 2 m + (lane >> 4), band_s), see warp_dct20
+    // front-end parameters of the context (ewk_config, ABI 2), set on the host after load_frame_tables
+    float preemph;                // pre-emphasis coefficient (0: none = the reference, wakeword.py:561-563)
+    int n_mfcc;                   // coefficients kept (1..20; the reference: 20)
+    int pad_[2];
 };
 
 // Lays the per-CTA tables out from the flat ones.  Run ONCE, on the host, at context creation (tid 0 of 1): the result is
@@ -360,7 +364,5 @@ __device__ __noinline__ void warp_refloor_mfcc(const float* __restrict__ lm, con
     const int k = ft.coef_of_lane[lane];
     if (k >= 0) out[k] = cft;
 }
-
-__device__ __forceinline__ void init_warp_scratch(float*, int) {}
 
 }  // namespace ewk

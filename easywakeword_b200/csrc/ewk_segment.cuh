@@ -48,6 +48,7 @@ struct PcmReader {
     int ring;
     int len;
     long long start;
+    float pre;             // pre-emphasis coefficient (0: none)
     __device__ __forceinline__ float at(int i) const {   // i relative to the segment
         if (i < 0 || i >= len) return 0.f;
         long long p = start + i;
@@ -163,13 +164,12 @@ __device__ __forceinline__ SegSmem seg_carve(float* smem, int cap_frames) {
 // once per CTA: tables into shared memory, the lane's mel band descriptors into registers
 __device__ __forceinline__ void seg_prologue(const DeviceTables* __restrict__ T, const SegSmem& m) {
     copy_frame_tables(*m.ft, T, threadIdx.x, SEG_THREADS);
-    init_warp_scratch(m.scratch + (threadIdx.x >> 5) * SCR_WARP, threadIdx.x & 31);
     __syncthreads();
 }
 
 // The lane's eight sample pairs (2 lane + 64 a, +1) of frame t, zero outside the segment
 // (librosa center=True, pad_mode='constant').
-__device__ __forceinline__ void load_frame_pairs_at(const PcmReader& rd, int f0, int lane, float2 (&x)[8]) {
+__device__ __forceinline__ void load_frame_pairs_raw(const PcmReader& rd, int f0, int lane, float2 (&x)[8]) {
     const long long base = rd.fast_base(f0);
     if (base >= 0) {
         if (rd.q) {
@@ -259,8 +259,43 @@ __device__ __forceinline__ void load_frame_pairs_at(const PcmReader& rd, int f0,
     }
 }
 
+// Pre-emphasis of the segment, applied to the frame's pairs in registers: what librosa.effects.preemphasis(y, coef=a)
+// returns for the segment y, sampled at the frame's positions (the reference calls librosa.feature.mfcc on the raw
+// segment, wakeword.py:561-563: a = 0 and this function is never entered).  scipy.signal.lfilter([1, -a], [1], y,
+// zi = 2 y[0] - y[1]) in float32, direct form II transposed: out[n] = z + 1 * y[n], z' = -a * y[n]  =>
+//     out[0] = (2 y[0] - y[1]) + y[0],      out[n] = fl(-a y[n-1]) + y[n]   (n >= 1),      zero outside the segment
+// (centring pads AFTER the filter).  f0 is even (frames start at 160 t - 256; the dense kernel's views keep that), so
+// segment sample 0 is always the even member of its pair.
+__device__ __forceinline__ void preemph_pairs(const PcmReader& rd, int f0, int lane, float2 (&x)[8]) {
+    const float nb = -rd.pre;
+    float carry = rd.at(f0 - 1);                                 // raw sample before the frame (0 outside the segment)
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        float prev = __shfl_up_sync(FULL, x[k].y, 1);
+        const float last = __shfl_sync(FULL, x[k].y, 31);
+        if (lane == 0) prev = carry;
+        carry = last;
+        const int i = f0 + 2 * lane + 64 * k;                    // segment index of the pair's even sample
+        float ye = __fadd_rn(__fmul_rn(nb, prev), x[k].x);
+        float yo = __fadd_rn(__fmul_rn(nb, x[k].x), x[k].y);
+        if (i == 0) ye = __fadd_rn(__fsub_rn(__fmul_rn(2.0f, x[k].x), rd.len > 1 ? x[k].y : 0.f), x[k].x);
+        if (i < 0 || i >= rd.len) ye = 0.f;
+        if (i + 1 < 0 || i + 1 >= rd.len) yo = 0.f;
+        x[k] = make_float2(ye, yo);
+    }
+}
+
+// PRE selects the kernel instantiation with pre-emphasis (launched only when ewk_config.preemphasis != 0), so the
+// reference-parity build of every kernel carries none of it.
+template <bool PRE>
+__device__ __forceinline__ void load_frame_pairs_at(const PcmReader& rd, int f0, int lane, float2 (&x)[8]) {
+    load_frame_pairs_raw(rd, f0, lane, x);
+    if (PRE) preemph_pairs(rd, f0, lane, x);
+}
+
+template <bool PRE>
 __device__ __forceinline__ void load_frame_pairs(const PcmReader& rd, int t, int lane, float2 (&x)[8]) {
-    load_frame_pairs_at(rd, t * HOP - N_FFT / 2, lane, x);
+    load_frame_pairs_at<PRE>(rd, t * HOP - N_FFT / 2, lane, x);
 }
 
 // One segment by the whole CTA (all threads must call it); returns a shared-memory pointer to mean[20] ++ std[20]
@@ -273,6 +308,7 @@ __device__ __forceinline__ void load_frame_pairs(const PcmReader& rd, int t, int
 //   D  mean / std over frames (ddof 0): two-pass mean and M2 over the warp's own frames                | barrier
 //      then one warp pools the 16 partials (Chan et al.), in fixed order                               | barrier
 // lm: this segment's rows of the log-mel workspace ([F][LM_ROW] floats, L2-resident scratch) or null.
+template <bool PRE>
 __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegSmem& m,
                                                    int cap_frames, float* __restrict__ ws,
                                                    float* __restrict__ frames_out, float* __restrict__ lm) {
@@ -289,12 +325,12 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
     PcmReader rd;
     rd.f = sd.fmt == 0 ? (const float*)sd.base : nullptr;
     rd.q = sd.fmt == 1 ? (const short*)sd.base : nullptr;
-    rd.ring = sd.ring; rd.len = sd.len; rd.start = sd.start;
+    rd.ring = sd.ring; rd.len = sd.len; rd.start = sd.start; rd.pre = PRE ? m.ft->preemph : 0.f;
     float* scr = m.scratch + warp * SCR_WARP;
     // ---- A
     for (int t = warp; t < F; t += SEG_WARPS) {
         float2 x[8];
-        load_frame_pairs(rd, t, lane, x);
+        load_frame_pairs<PRE>(rd, t, lane, x);
         float mn, mx;
         warp_frame_mfcc(x, *m.ft, scr, lane, -INFINITY, mf + (size_t)t * N_MFCC, mn, mx,
                         lm ? lm + (size_t)t * LM_ROW : nullptr);
@@ -326,7 +362,7 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
             if (lm) warp_refloor_mfcc(lm + (size_t)t * LM_ROW, m.ft, floor_db, mf + (size_t)t * N_MFCC);
             else {
                 float2 x[8];
-                load_frame_pairs(rd, t, lane, x);
+                load_frame_pairs<PRE>(rd, t, lane, x);
                 float mn, mx;
                 warp_frame_mfcc(x, *m.ft, scr, lane, floor_db, mf + (size_t)t * N_MFCC, mn, mx);
             }
@@ -357,14 +393,16 @@ __device__ __forceinline__ float* segment_features(const SegDesc& sd, const SegS
             M2 += m.part[w * 2 * N_MFCC + N_MFCC + tid] + delta * delta * (n * cw / nn);
             n = nn;
         }
-        m.feat[tid] = mean;
-        m.feat[N_MFCC + tid] = sqrtf(M2 / (float)F);
+        const bool kept = tid < m.ft->n_mfcc;                  // coefficients beyond n_mfcc (ewk_config) drop out of both cosines
+        m.feat[tid] = kept ? mean : 0.f;
+        m.feat[N_MFCC + tid] = kept ? sqrtf(M2 / (float)F) : 0.f;
     }
     __syncthreads();
     return m.feat;
 }
 
 // K3, batch form: one CTA per caller-described segment (extract_mfcc / calculate_similarity / matches).
+template <bool PRE>
 __global__ void __launch_bounds__(512, 2)
 segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __restrict__ segs,
                           int cap_frames, float* __restrict__ ws,           // global spill [frames][22]
@@ -381,7 +419,7 @@ segment_mfcc_match_kernel(const DeviceTables* __restrict__ T, const SegDesc* __r
     seg_prologue(T, m);
     const int tid = threadIdx.x;
     const SegDesc sd = segs[blockIdx.x];
-    const float* feat = segment_features(sd, m, cap_frames, ws, frames_out,
+    const float* feat = segment_features<PRE>(sd, m, cap_frames, ws, frames_out,
                                          lm_ws ? lm_ws + (size_t)sd.lm_off * LM_ROW : nullptr);
     if (feat_out && tid < FEAT) feat_out[(size_t)blockIdx.x * FEAT + tid] = feat[tid];
     if (scores && tid < n_tmpl) {

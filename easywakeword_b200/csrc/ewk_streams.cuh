@@ -55,7 +55,9 @@ struct StreamState {
     int chunks_valid;       // chunk mean-squares reflect the ring at `visible`
     int n_timeouts;
     int n_events;
-    int pad;
+    int last_ev;            // queue index of the stream's newest level-2 candidate in the current queue epoch (-1: none):
+                            // K3 lets only that event write the per-stream result record, so the record always carries the
+                            // LATEST evaluation however the CTAs that score a stream's events are ordered
     long long ss_from;      // block_ss holds the sum of squares of every aligned 1600-sample block in [ss_from, written)
 };
 
@@ -113,6 +115,12 @@ __device__ __forceinline__ void publish_result(const BankView& B, int s, StreamR
     const unsigned long long bits = ((unsigned long long)r.flags << 32) | (unsigned long long)__float_as_uint(r.score);
     for (int p = 0; p < B.n_pub; p++)
         asm volatile("st.weak.global.b64 [%0], %1;" :: "l"(B.pub[p] + at), "l"(bits) : "memory");
+}
+
+// the record as ONE 8-byte store (readers — peers, an all-gather, the host — never see half of it)
+__device__ __forceinline__ void store_result(StreamResult* dst, StreamResult r) {
+    const unsigned long long bits = ((unsigned long long)r.flags << 32) | (unsigned long long)__float_as_uint(r.score);
+    *reinterpret_cast<unsigned long long*>(dst) = bits;
 }
 
 struct TraceView {          // optional per-tick trace for parity tests: [n_streams][n_ticks]
@@ -635,6 +643,7 @@ __device__ __forceinline__ unsigned gate_state_step(const BankView& B, int s, St
                             e.tmpl = -1; e.score = __int_as_float(0x7fc00000); e.matched = 0;
                             B.events[idx] = e;
                             st.n_events++;
+                            st.last_ev = idx;
                             evflag = 16u;
                         } else { atomicAdd(B.ev_count + 1, 1); atomicSub(B.ev_count, 1); }
                     }
@@ -905,7 +914,7 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
         StreamResult r = B.results[s];
         r.flags = (r.flags & 1u) | (st.last_silent ? 2u : 0u) | ((unsigned)st.state << 2) | evflag |
                   ((unsigned)st.n_events << 8);
-        B.results[s] = r;
+        store_result(B.results + s, r);
         publish_result(B, s, r);
     }
 }
@@ -965,6 +974,7 @@ segment_prepare_kernel(BankView B, const PrepDesc* __restrict__ d, float* __rest
 // tail by one segment instead of a static share.  Events below the watermark ev_count[3] were scored by earlier
 // launches and are not visited again; the last CTA to finish advances it and zeroes the counters.
 
+template <bool PRE>
 __global__ void __launch_bounds__(512, 2)
 segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, int n_tmpl_slots) {
     extern __shared__ __align__(16) float smem[];
@@ -992,7 +1002,7 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
         sd.base = (const char*)B.ring + (size_t)e.stream * B.P * esz;
         sd.start = e.seg_start % B.P; sd.ring = B.P; sd.len = e.seg_len; sd.fmt = B.fmt;
         sd.ws_frame_off = 0; sd.frames_off = 0; sd.lm_off = 0;
-        const float* feat = segment_features(sd, m, SEG_SMEM_FRAMES, nullptr, nullptr, lm);
+        const float* feat = segment_features<PRE>(sd, m, SEG_SMEM_FRAMES, nullptr, nullptr, lm);
         const StreamParams& prm = B.prm[e.stream];
         const int t0 = max(0, prm.template_first);
         const int nt = max(0, min(prm.template_count, n_tmpl_slots - t0));
@@ -1010,11 +1020,15 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
             const int ok = best >= prm.similarity_threshold ? 1 : 0;
             EventRec* o = B.events + i;
             o->score = best; o->tmpl = arg; o->matched = ok; o->kind = EV_SCORED;
-            StreamResult res = B.results[e.stream];
-            res.score = best;
-            res.flags = (res.flags & ~1u) | (unsigned)ok;
-            B.results[e.stream] = res;
-            publish_result(B, e.stream, res);
+            if (B.st[e.stream].last_ev == i) {
+                // only the stream's newest candidate of this queue epoch reaches the 8-byte record (one owner per stream:
+                // no read-modify-write race between CTAs that score two events of one stream in arbitrary order)
+                StreamResult res = B.results[e.stream];
+                res.score = best;
+                res.flags = (res.flags & ~1u) | (unsigned)ok;
+                store_result(B.results + e.stream, res);
+                publish_result(B, e.stream, res);
+            }
         }
         r = next_s;
         __syncthreads();

@@ -12,10 +12,12 @@ runs on the device.
 """
 from __future__ import annotations
 
+import inspect
 import logging
 import os
 import threading
 import time
+import warnings
 from typing import Callable, Dict, Optional, Union
 
 import numpy as np
@@ -36,19 +38,22 @@ AUTO_CALCULATE = None
 VOICE_ACTIVITY_THRESHOLD = 0.1
 MIN_DETECTED_DURATION = 0.2
 
-_shared_ctx = None
+_shared_ctx = {}
 _shared_lock = threading.Lock()
 
 
-def shared_matcher_context(device: int = 0):
-    """One stream-less context per process for WordMatcher facades (templates are per-facade slots)."""
-    global _shared_ctx
+def shared_matcher_context(device: int = 0, preemphasis: float = 0.0, n_mfcc: int = 0):
+    """One stream-less context per (CUDA device, front-end parameters) and process for WordMatcher facades
+    (templates are per-facade slots)."""
+    key = (int(device), float(preemphasis), int(n_mfcc) or 20)
     with _shared_lock:
-        if _shared_ctx is None:
-            _shared_ctx = _lib.Context(device=device, n_streams=0, max_templates=64)
-            _shared_ctx._slot_free = list(range(63, -1, -1))
-            _shared_ctx._lock = threading.Lock()
-        return _shared_ctx
+        ctx = _shared_ctx.get(key)
+        if ctx is None or not ctx.h:
+            ctx = _lib.Context(device=device, n_streams=0, max_templates=64, preemphasis=preemphasis, n_mfcc=n_mfcc)
+            ctx._slot_free = list(range(63, -1, -1))
+            ctx._lock = threading.Lock()
+            _shared_ctx[key] = ctx
+        return ctx
 
 
 def load_wav_16k(path: str, sample_rate: int = 16000, *, ctx=None) -> np.ndarray:
@@ -63,12 +68,15 @@ def load_wav_16k(path: str, sample_rate: int = 16000, *, ctx=None) -> np.ndarray
 class WordMatcher:
     """MFCC matcher (reference: wakeword.py:520-639); the arithmetic runs in the fused K3 kernel."""
 
-    def __init__(self, sample_rate: int = 16000, *, context=None, device: int = 0) -> None:
+    def __init__(self, sample_rate: int = 16000, *, context=None, device: int = 0, preemphasis: float = 0.0,
+                 n_mfcc: int = 20) -> None:
+        """preemphasis / n_mfcc: the front-end parameters the reference hard-codes (none / 20, wakeword.py:561-563) and
+        lists as "expose" on its roadmap (LEARNINGS.md:87); the defaults are the reference's."""
         self.sample_rate: int = sample_rate
         self.reference_mfcc_mean: Optional[np.ndarray] = None
         self.reference_mfcc_std: Optional[np.ndarray] = None
         self.reference_word: Optional[str] = None
-        self._ctx = context if context is not None else shared_matcher_context(device)
+        self._ctx = context if context is not None else shared_matcher_context(device, preemphasis, n_mfcc)
         self._owns_slot = hasattr(self._ctx, "_slot_free")
         self._slot = self._ctx._slot_free.pop() if self._owns_slot else 0
         self._lock = getattr(self._ctx, "_lock", threading.Lock())
@@ -126,6 +134,8 @@ class SoundBuffer:
 
     FREQUENCY = 16000
     MIN_THRESHOLD = 0.005
+    MIN_FRAME_SIZE = 160     # libewk: smallest callback block the device gate chunks by (ewk_set_stream_params)
+    MAX_CHUNKS = 2048        # libewk: storage-order chunks a gate warp holds in shared memory (ewk_tick)
 
     def __init__(self, seconds: int = DEFAULT_BUFFER_SECONDS, device: Optional[Union[int, str]] = None, *,
                  cuda_device: int = 0, source=None):
@@ -164,7 +174,15 @@ class SoundBuffer:
             return
         with self._lock:
             if self.frame_size == 0:
-                self.frame_size = len(new_data)
+                # the adaptive threshold works on ring_length // frame_size chunks of the FIRST callback's length
+                # (wakeword.py:457-458, 477-478); the device gate keeps them in shared memory
+                n = len(new_data)
+                if n < self.MIN_FRAME_SIZE or self.buffer_length // n > self.MAX_CHUNKS:
+                    raise ValueError(f"SoundBuffer: a first callback of {n} samples is not supported with a "
+                                     f"{self.buffer_seconds} s ring: the block must hold at least {self.MIN_FRAME_SIZE} samples and "
+                                     f"ring_length // block may not exceed {self.MAX_CHUNKS} (use a PortAudio blocksize "
+                                     f">= {max(self.MIN_FRAME_SIZE, -(-self.buffer_length // self.MAX_CHUNKS))})")
+                self.frame_size = n
             for p in range(0, len(new_data), self.buffer_length):
                 self._ctx.push(new_data[p:p + self.buffer_length].reshape(1, -1))
             self._written += len(new_data)
@@ -240,6 +258,44 @@ def analyze_reference_audio_duration(audio: np.ndarray) -> Optional[float]:
     return max((voiced[-1] - voiced[0]) * hop_length / SoundBuffer.FREQUENCY, MIN_DETECTED_DURATION)
 
 
+def _accepts_initial_prompt(t) -> bool:
+    try:
+        sig = inspect.signature(t.transcribe)
+    except (TypeError, ValueError):
+        return False
+    return "initial_prompt" in sig.parameters or any(p.kind == p.VAR_KEYWORD for p in sig.parameters.values())
+
+
+class _LocalWhisper:
+    """The reference's bundled level-3 backend (transcriber.py:11-140: openai-whisper "tiny", language="en",
+    fp16=False), loaded lazily.  Out of the accelerated path: this is the host-side hand-off only."""
+
+    def __init__(self, model_name: str = "tiny"):
+        self.model_name = model_name
+        self._model = None
+
+    @classmethod
+    def if_available(cls):
+        import importlib.util
+        try:
+            ok = importlib.util.find_spec("whisper") is not None
+        except (ImportError, ValueError):
+            ok = False
+        return cls() if ok else None
+
+    def load_model(self) -> bool:
+        if self._model is None:
+            import whisper
+            self._model = whisper.load_model(self.model_name)
+        return True
+
+    def transcribe(self, audio: np.ndarray, initial_prompt: Optional[str] = None) -> Optional[str]:
+        self.load_model()
+        kw = {"initial_prompt": initial_prompt} if initial_prompt else {}
+        result = self._model.transcribe(np.asarray(audio, dtype=np.float32), language="en", fp16=False, **kw)
+        return result.get("text", "").strip()
+
+
 class WakeWord:
     """Wake-word detector with the reference's public surface (wakeword.py:642-1240):
     ``WakeWord(textword, wavword, ...)``, ``waitforit()``, ``start()`` / ``stop()`` / ``callback``.
@@ -302,7 +358,24 @@ class WakeWord:
         self._listening = False
         self._listen_thread: Optional[threading.Thread] = None
         self._stop_event = threading.Event()
-        self._transcriber = transcriber
+        # Level 3 stays on the host and on its existing backend (out of the accelerated path).  The
+        # reference always builds its bundled WhisperTranscriber (wakeword.py:795); here an injected `transcriber` wins,
+        # else openai-whisper is used when importable, else the caller is told — loudly — that no confirmation exists.
+        self.external_whisper_url = external_whisper_url
+        self.stt_backend = stt_backend
+        self.session_headers = session_headers
+        ignored = [n for n, v, d in (("external_whisper_url", external_whisper_url, None), ("stt_backend", stt_backend, "bundled"),
+                                     ("session_headers", session_headers, None)) if v != d]
+        if ignored:
+            warnings.warn(f"easywakeword_b200.WakeWord ignores {', '.join(ignored)}: only the local level-3 backend "
+                          "(an injected `transcriber` or openai-whisper) is supported; levels 1-2 run on the GPU",
+                          RuntimeWarning, stacklevel=2)
+        self._transcriber = transcriber if transcriber is not None else _LocalWhisper.if_available()
+        if self._transcriber is None:
+            warnings.warn("easywakeword_b200.WakeWord: no level-3 speech-to-text backend (no `transcriber` given and "
+                          "openai-whisper is not importable): MFCC matches cannot be confirmed, so waitforit() will end "
+                          "in TimeoutError and start() will never call the callback.  Pass transcriber=<object with "
+                          "transcribe(audio) -> str> or install openai-whisper.", RuntimeWarning, stacklevel=2)
         self._log(f"Initialized WakeWord detector for '{self.textword}'")
 
     def _log(self, message: str, level: int = logging.DEBUG) -> None:
@@ -368,7 +441,11 @@ class WakeWord:
             self._log("No level-3 transcriber configured", logging.WARNING)
             return None
         try:
-            text = self._transcriber.transcribe(self.prepare_for_transcription(audio_samples))
+            audio = self.prepare_for_transcription(audio_samples)
+            if _accepts_initial_prompt(self._transcriber):      # wakeword.py:1029 passes initial_prompt=f"Wake word: ..."
+                text = self._transcriber.transcribe(audio, initial_prompt=f"Wake word: {self.textword}")
+            else:
+                text = self._transcriber.transcribe(audio)
             self._log(f"Transcription result: '{text}'")
             return text
         except Exception as e:

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define EWK_ABI_VERSION 1
+#define EWK_ABI_VERSION 2
 
 typedef struct ewk_ctx ewk_ctx;
 
@@ -47,6 +47,15 @@ typedef struct ewk_config {
     int32_t pcm_format;     /* ewk_pcm_format of the device rings                                     */
     int32_t max_templates;  /* template slots (reference: one WordMatcher holds one template)         */
     int32_t max_events;     /* capacity of the device event queue between two ewk_poll calls          */
+    /* --- ABI 2: front-end parameters the reference hard-codes (wakeword.py:561-563; exposing them is on its own
+     * wish list, LEARNINGS.md:87, README-CODE-ALIGNMENT.md:84-107).  0 selects the reference's value. */
+    float preemphasis;      /* coefficient a of y[n] = x[n] - a x[n-1], applied to every segment / dense window
+                               handed to the MFCC front-end, before centring (librosa.effects.preemphasis incl.
+                               its zi = 2 x[0] - x[1] initial state).  The reference applies none: 0 = identity
+                               is the parity default and leaves every result bit-identical                    */
+    int32_t n_mfcc;         /* MFCC coefficients kept, 1..20; 0 = 20                      wakeword.py:562     */
+    int32_t reserved0;
+    int32_t reserved1;
 } ewk_config;
 
 /* ---- library ------------------------------------------------------------------------------ */

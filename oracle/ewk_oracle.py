@@ -45,15 +45,20 @@ DEFAULTS = dict(similarity_threshold=75.0, pre_speech_silence=0.8, speech_durati
 
 
 # ------------------------------------------------------------------ A4-A7  WordMatcher
-def extract_mfcc(audio):
+def mfcc_frames(audio, preemphasis=0.0, n_mfcc=20):
+    """The [20 x (1 + n//160)] matrix extract_mfcc pools (wakeword.py:561-563).
+    preemphasis / n_mfcc are the build's exposed front-end parameters (ewk_config, ABI 2); the reference's values are
+    0 (none) and 20, and with them this is the reference's call, statement for statement."""
+    y = np.asarray(audio)
+    if preemphasis:
+        y = L.preemphasis(y, coef=preemphasis)
+    return L.mfcc(y=y, sr=FREQUENCY, n_mfcc=n_mfcc, n_fft=512, hop_length=160)
+
+
+def extract_mfcc(audio, preemphasis=0.0, n_mfcc=20):
     """WordMatcher.extract_mfcc (wakeword.py:544-567): MFCC[20 x frames] -> mean, std (ddof 0)."""
-    m = L.mfcc(y=audio, sr=FREQUENCY, n_mfcc=20, n_fft=512, hop_length=160)
+    m = mfcc_frames(audio, preemphasis, n_mfcc)
     return np.mean(m, axis=1), np.std(m, axis=1)
-
-
-def mfcc_frames(audio):
-    """The [20 x (1 + n//160)] matrix extract_mfcc pools (wakeword.py:561-563)."""
-    return L.mfcc(y=audio, sr=FREQUENCY, n_mfcc=20, n_fft=512, hop_length=160)
 
 
 def similarity_from_features(ref_mean, ref_std, cand_mean, cand_std):
@@ -68,17 +73,19 @@ def similarity_from_features(ref_mean, ref_std, cand_mean, cand_std):
 class WordMatcherOracle:
     """Restates WordMatcher (wakeword.py:520-639)."""
 
-    def __init__(self, sample_rate=16000):
+    def __init__(self, sample_rate=16000, preemphasis=0.0, n_mfcc=20):
         self.sample_rate = sample_rate
         self.reference_mfcc_mean = None
         self.reference_mfcc_std = None
         self.reference_word = None
+        self.preemphasis, self.n_mfcc = preemphasis, n_mfcc
 
-    extract_mfcc = staticmethod(extract_mfcc)
+    def extract_mfcc(self, audio):
+        return extract_mfcc(audio, self.preemphasis, self.n_mfcc)
 
     def set_reference(self, audio, word_name="target"):                # :569-578
         self.reference_word = word_name
-        self.reference_mfcc_mean, self.reference_mfcc_std = extract_mfcc(audio)
+        self.reference_mfcc_mean, self.reference_mfcc_std = self.extract_mfcc(audio)
 
     def load_reference_from_file(self, filepath, word_name="target"):  # :580-589
         audio, _ = L.load(filepath, sr=self.sample_rate)
@@ -87,7 +94,7 @@ class WordMatcherOracle:
     def calculate_similarity(self, audio):                              # :591-625
         if self.reference_mfcc_mean is None:
             raise ValueError("No reference word set. Call set_reference() first.")
-        m, s = extract_mfcc(audio)
+        m, s = self.extract_mfcc(audio)
         with np.errstate(all="ignore"):
             return similarity_from_features(self.reference_mfcc_mean, self.reference_mfcc_std, m, s)
 
@@ -358,7 +365,7 @@ def dense_window(n_template):
     return -(-int(n_template) // 160), int(n_template)
 
 
-def dense_scores(stream, templates, hops):
+def dense_scores(stream, templates, hops, preemphasis=0.0, n_mfcc=20):
     """A9: for every hop h in `hops` and template k, what
     WordMatcher.calculate_similarity (wakeword.py:591-625) returns when handed the dense
     window of dense_window(len(template_k)).  The usage shape is examples/tune_threshold.py:
@@ -367,7 +374,7 @@ def dense_scores(stream, templates, hops):
     stream = np.asarray(stream, dtype=np.float32)
     out = np.full((len(hops), len(templates)), np.nan, dtype=np.float32)
     for ki, tpl in enumerate(templates):
-        m = WordMatcherOracle()
+        m = WordMatcherOracle(preemphasis=preemphasis, n_mfcc=n_mfcc)
         m.set_reference(np.asarray(tpl, dtype=np.float32))
         nb, ln = dense_window(len(tpl))
         for hi, h in enumerate(hops):

@@ -156,6 +156,24 @@ def mfcc(y, sr=SR, n_mfcc=N_MFCC, n_fft=N_FFT, hop_length=HOP, n_mels=N_MELS):
     return scipy.fft.dct(S, axis=-2, type=2, norm="ortho")[..., :n_mfcc, :]
 
 
+def preemphasis(y, coef=0.97):
+    """librosa.effects.preemphasis(y, coef=coef, zi=None): ``scipy.signal.lfilter([1, -coef], [1], y, zi=2*y[0] - y[1])``
+    in y's dtype — i.e. out[n] = y[n] - coef*y[n-1] for n >= 1 and out[0] = y[0] + (2*y[0] - y[1]): librosa hands its
+    "linear extrapolation" value to lfilter as the filter STATE, unscaled (restated from librosa 0.11's effects.py from
+    memory; the source is not available offline).  The reference never calls it (wakeword.py:561-563 passes the raw
+    segment to librosa.feature.mfcc), so this is the definition of the build's `preemphasis` EXTENSION parameter:
+    parity for coef != 0 is unpinned by anything the reference holds."""
+    y = np.asarray(y)
+    if y.dtype not in (np.float32, np.float64):
+        y = y.astype(np.float32)
+    b = np.asarray([1.0, -coef], dtype=y.dtype)
+    a = np.asarray([1.0], dtype=y.dtype)
+    x1 = y[..., 1:2] if y.shape[-1] > 1 else np.zeros_like(y[..., 0:1])
+    zi = 2 * y[..., 0:1] - x1
+    out, _ = scipy.signal.lfilter(b, a, y, zi=np.asarray(zi, dtype=y.dtype))
+    return out.astype(y.dtype, copy=False)
+
+
 def rms(y, frame_length=2048, hop_length=512):
     """librosa.feature.rms(center=True, pad_mode='constant') -> [1, n_frames]."""
     y = np.asarray(y)

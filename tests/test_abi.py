@@ -24,13 +24,13 @@ def test_header_symbols_exported(lib):
     assert not missing, missing
     # and every symbol the binding declares is in the header
     assert set(lib._protos) <= set(names), set(lib._protos) - set(names)
-    assert lib.ewk_abi_version() == 1
+    assert lib.ewk_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     import ctypes as C
     from easywakeword_b200 import _lib
-    assert C.sizeof(_lib.Config) == 24
+    assert C.sizeof(_lib.Config) == 40      # ABI 2: + preemphasis, n_mfcc, 2 reserved words
     assert C.sizeof(_lib.StreamParams) == 72
     assert C.sizeof(_lib.Event) == 40 and _lib.EVENT_DTYPE.itemsize == 40
     assert C.sizeof(_lib.StreamStatus) == 64

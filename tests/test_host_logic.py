@@ -240,3 +240,34 @@ def test_shard_ranges_partition_streams(n, world):
         for s in range(a, b):
             assert owner_of(s, n, world) == (r, s - a)
     assert seen == list(range(n))
+
+
+# ---- level-3 hand-off of the drop-in WakeWord (round-1 advisor finding: a facade that silently never confirms)
+def test_missing_level3_backend_is_announced(wav):
+    import importlib.util
+    if importlib.util.find_spec("whisper") is not None:
+        pytest.skip("openai-whisper is installed: a backend exists")
+    with pytest.warns(RuntimeWarning, match="no level-3 speech-to-text backend"):
+        WakeWord("hello", wav)
+    with pytest.warns(RuntimeWarning, match="ignores external_whisper_url, stt_backend"):
+        WakeWord("hello", wav, external_whisper_url="http://localhost:1", stt_backend="external", transcriber=object())
+
+
+def test_initial_prompt_reaches_a_backend_that_accepts_it(wav):
+    """wakeword.py:1029 passes initial_prompt=f"Wake word: {textword}" to the level-3 call."""
+    seen = {}
+
+    class WithPrompt:
+        def transcribe(self, audio, initial_prompt=None):
+            seen["prompt"] = initial_prompt
+            return "hello"
+
+    class Plain:
+        def transcribe(self, audio):
+            seen["plain"] = True
+            return "hello"
+
+    x = np.zeros(1600, np.float32)
+    assert WakeWord("hello", wav, numberofwords=1, transcriber=WithPrompt())._confirm(x) == "hello"
+    assert seen["prompt"] == "Wake word: hello"
+    assert WakeWord("hello", wav, numberofwords=1, transcriber=Plain())._confirm(x) == "hello" and seen["plain"]

@@ -304,3 +304,36 @@ def test_resample_oracle_tones(sr):
     if sr > 2 * 9000:
         y = R.resample(np.sin(2 * np.pi * 9000.0 * t), sr)
         assert np.abs(y[700:-700]).max() < 1e-6             # < -120 dB
+
+
+def test_preemphasis_restatement_is_lfilter_with_librosa_state():
+    """oracle.librosa_restated.preemphasis == the closed form of scipy.signal.lfilter([1, -a], [1], y, zi=2 y0 - y1)
+    in float32; coefficient 0 is the identity (the reference's call, wakeword.py:561-563, applies none)."""
+    from oracle import librosa_restated as L
+    rng = np.random.default_rng(3)
+    y = (rng.standard_normal(5000) * 0.1).astype(np.float32)
+    for a in (0.97, 0.5):
+        out = L.preemphasis(y, a)
+        assert out.dtype == np.float32
+        na = np.float32(-a)
+        ref = np.empty_like(y)
+        ref[0] = (np.float32(2) * y[0] - y[1]) + y[0]
+        ref[1:] = (na * y[:-1]) + y[1:]                       # fl(fl(-a y[n-1]) + y[n]) in float32
+        assert np.abs(out - ref).max() <= 1e-7
+    assert np.array_equal(O.mfcc_frames(y, preemphasis=0.0), O.mfcc_frames(y))
+    m13 = O.mfcc_frames(y, n_mfcc=13)
+    assert m13.shape[0] == 13 and np.array_equal(m13, O.mfcc_frames(y)[:13])
+
+
+def test_staged_reference_is_the_reference(tmp_path):
+    """oracle/stage_ref.py copies the three files byte for byte (what the GPU box's CPU arm imports)."""
+    import hashlib
+    from oracle import stage_ref
+    if not os.path.isdir(stage_ref.SRC_ROOT):
+        pytest.skip("/root/reference not present")
+    man = stage_ref.stage()
+    assert man["matches_golden_manifest"] is True
+    for f in stage_ref.FILES:
+        a = open(os.path.join(stage_ref.SRC_ROOT, f), "rb").read()
+        b = open(os.path.join(stage_ref.DST_ROOT, f), "rb").read()
+        assert a == b and hashlib.sha256(b).hexdigest() == man["files"][f]
