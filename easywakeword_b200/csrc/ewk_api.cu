@@ -228,9 +228,9 @@ int ewk_ctx::launch_segments(const SegDesc* d_segs, int n_seg, int max_frames, l
     return EWK_OK;
 }
 
-extern "C" int ewk_extract_mfcc(ewk_ctx* ctx, const float* pcm, int64_t n, int where, float* mean20, float* std20,
-                                float* frames, int64_t frames_cap) {
-    if (!ctx) return EWK_ERR_ARG;
+// WordMatcher.extract_mfcc on one buffer; dense40 (nullable): the same features from K4's integer statistics of the frames.
+static int extract_impl(ewk_ctx* ctx, const float* pcm, int64_t n, int where, float* mean20, float* std20,
+                        float* frames, int64_t frames_cap, float* dense40) {
     if (!pcm || n < 1 || n > (int64_t)1 << 30 || !mean20 || !std20) {
         ctx->fail("ewk_extract_mfcc: need pcm, 1 <= n < 2^30, mean20, std20 (n=%lld)", (long long)n);
         return EWK_ERR_ARG;
@@ -249,19 +249,32 @@ extern "C" int ewk_extract_mfcc(ewk_ctx* ctx, const float* pcm, int64_t n, int w
     sd.lm_off = 0;
     CK(ctx->b_desc.ensure(sizeof(SegDesc)));
     CK(cudaMemcpyAsync(ctx->b_desc.p, &sd, sizeof(sd), cudaMemcpyHostToDevice, ctx->stream));
-    CK(ctx->b_feat.ensure(sizeof(float) * FEAT));
+    CK(ctx->b_feat.ensure(sizeof(float) * 2 * FEAT));
     float* d_frames = nullptr;
-    if (frames) { CK(ctx->b_frames.ensure(sizeof(float) * (size_t)F * N_MFCC)); d_frames = (float*)ctx->b_frames.p; }
+    if (frames || dense40) { CK(ctx->b_frames.ensure(sizeof(float) * (size_t)F * N_MFCC)); d_frames = (float*)ctx->b_frames.p; }
     int rc = ctx->launch_segments((const SegDesc*)ctx->b_desc.p, 1, (int)F, F > SEG_SMEM_FRAMES ? F : 0, F, 0, 0, 0.f,
                                   (float*)ctx->b_feat.p, d_frames, nullptr, nullptr);
     if (rc != EWK_OK) return rc;
-    float feat[FEAT];
-    CK(cudaMemcpyAsync(feat, ctx->b_feat.p, sizeof(feat), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dense40) {
+        dense_template_features_kernel<<<1, 32, 0, ctx->stream>>>(d_frames, (int)F, ctx->cfg.n_mfcc > 0 ? ctx->cfg.n_mfcc : N_MFCC,
+                                                                  (float*)ctx->b_feat.p + FEAT);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    float feat[2 * FEAT];
+    CK(cudaMemcpyAsync(feat, ctx->b_feat.p, sizeof(float) * (dense40 ? 2 * FEAT : FEAT), cudaMemcpyDeviceToHost, ctx->stream));
     if (frames) CK(cudaMemcpyAsync(frames, d_frames, sizeof(float) * (size_t)F * N_MFCC, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     std::memcpy(mean20, feat, sizeof(float) * N_MFCC);
     std::memcpy(std20, feat + N_MFCC, sizeof(float) * N_MFCC);
+    if (dense40) std::memcpy(dense40, feat + FEAT, sizeof(float) * FEAT);
     return EWK_OK;
+}
+
+extern "C" int ewk_extract_mfcc(ewk_ctx* ctx, const float* pcm, int64_t n, int where, float* mean20, float* std20,
+                                float* frames, int64_t frames_cap) {
+    if (!ctx) return EWK_ERR_ARG;
+    return extract_impl(ctx, pcm, n, where, mean20, std20, frames, frames_cap, nullptr);
 }
 
 static int check_slot(ewk_ctx* ctx, int slot, const char* who) {
@@ -272,15 +285,15 @@ static int check_slot(ewk_ctx* ctx, int slot, const char* who) {
     return EWK_OK;
 }
 
-extern "C" int ewk_set_template_features(ewk_ctx* ctx, int slot, const float* mean20, const float* std20, int64_t n_samples) {
-    if (!ctx) return EWK_ERR_ARG;
-    int rc = check_slot(ctx, slot, "ewk_set_template_features");
-    if (rc) return rc;
-    if (!mean20 || !std20 || n_samples < 1) { ctx->fail("ewk_set_template_features: null features or n_samples < 1"); return EWK_ERR_ARG; }
+static int install_template(ewk_ctx* ctx, int slot, const float* mean20, const float* std20, const float* dense40, int64_t n_samples) {
     CK(cudaSetDevice(ctx->device));
     TemplateFeat tf{};
     std::memcpy(tf.mean, mean20, sizeof(tf.mean));
     std::memcpy(tf.std, std20, sizeof(tf.std));
+    // features for the dense kernel: its own integer statistics of the template's frames when the audio is known,
+    // the given features otherwise
+    std::memcpy(tf.dmean, dense40 ? dense40 : mean20, sizeof(tf.dmean));
+    std::memcpy(tf.dstd, dense40 ? dense40 + N_MFCC : std20, sizeof(tf.dstd));
     tf.n_samples = n_samples;
     tf.valid = 1;
     ctx->h_tmpl[slot] = tf;
@@ -289,14 +302,22 @@ extern "C" int ewk_set_template_features(ewk_ctx* ctx, int slot, const float* me
     return EWK_OK;
 }
 
+extern "C" int ewk_set_template_features(ewk_ctx* ctx, int slot, const float* mean20, const float* std20, int64_t n_samples) {
+    if (!ctx) return EWK_ERR_ARG;
+    int rc = check_slot(ctx, slot, "ewk_set_template_features");
+    if (rc) return rc;
+    if (!mean20 || !std20 || n_samples < 1) { ctx->fail("ewk_set_template_features: null features or n_samples < 1"); return EWK_ERR_ARG; }
+    return install_template(ctx, slot, mean20, std20, nullptr, n_samples);
+}
+
 extern "C" int ewk_set_template(ewk_ctx* ctx, int slot, const float* pcm, int64_t n) {
     if (!ctx) return EWK_ERR_ARG;
     int rc = check_slot(ctx, slot, "ewk_set_template");
     if (rc) return rc;
-    float mean[N_MFCC], sd[N_MFCC];
-    rc = ewk_extract_mfcc(ctx, pcm, n, EWK_HOST, mean, sd, nullptr, 0);
+    float mean[N_MFCC], sd[N_MFCC], dense[FEAT];
+    rc = extract_impl(ctx, pcm, n, EWK_HOST, mean, sd, nullptr, 0, dense);
     if (rc) return rc;
-    return ewk_set_template_features(ctx, slot, mean, sd, n);
+    return install_template(ctx, slot, mean, sd, dense, n);
 }
 
 extern "C" int ewk_get_template(ewk_ctx* ctx, int slot, float* mean20, float* std20, int64_t* n_samples) {
@@ -594,7 +615,7 @@ void ewk_ctx::release_streams() {
         if (p) cudaFree(p);
     bank = BankView{};
     own_results = nullptr;
-    b_trace.free(); b_read.free(); b_dense.free(); b_keep_rows.free(); b_keep_end.free();
+    b_trace.free(); b_read.free(); b_dense.free(); b_keep_rows.free(); b_keep_end.free(); b_g2.free();
     for (auto& p : prof_pairs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : prof_free) cudaEventDestroy(e);
     prof_pairs.clear(); prof_free.clear();
@@ -1114,6 +1135,27 @@ extern "C" int ewk_prepare_segments(ewk_ctx* ctx, int n_seg, const int32_t* stre
     return EWK_OK;
 }
 
+// Launch geometry of K4 for a template set: hops per sub-chunk, threads per CTA and CTAs per SM that fit shared memory.
+struct DensePlan { int DH, threads, per_sm; size_t smem; };
+
+static bool dense_plan(const DenseArgs& A0, int n_min, int n_max, int re_per_hop, DensePlan& out) {
+    const size_t SM_TOTAL = 233472, CTA_MAX = 232448, RESERVED = 1024;     // sm_100: 228 KB per SM, 227 KB per CTA
+    auto bytes = [&](int DH, int threads) {
+        return dense_smem_bytes(threads / 32, A0.T, DH, DH + n_max + 2, DH + n_max - n_min, DH * re_per_hop);
+    };
+    for (int DH : {64, 32})
+        for (int threads : {512, 448}) {
+            const size_t b = bytes(DH, threads);
+            if (2 * (b + RESERVED) <= SM_TOTAL) { out = {DH, threads, 2, b}; return true; }
+        }
+    for (int threads : {1024, 512})
+        for (int DH : {64, 32}) {
+            const size_t b = bytes(DH, threads);
+            if (b <= CTA_MAX) { out = {DH, threads, 1, b}; return true; }
+        }
+    return false;
+}
+
 extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl_first, int tmpl_count, float* out, int where) {
     if (!ctx) return EWK_ERR_ARG;
     int rc = need_streams(ctx, "ewk_dense_scores");
@@ -1124,29 +1166,40 @@ extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl
     BankView& B = ctx->bank;
     if (!out || hop0 < 0 || n_hops < 1 || tmpl_count < 1 || tmpl_count > DENSE_MAX_T || tmpl_first < 0 ||
         tmpl_first + tmpl_count > ctx->cfg.max_templates) {
-        ctx->fail("ewk_dense_scores: bad arguments (hop0=%lld n_hops=%d templates [%d, %d))", (long long)hop0, n_hops,
-                  tmpl_first, tmpl_first + tmpl_count);
+        ctx->fail("ewk_dense_scores: bad arguments (hop0=%lld n_hops=%d templates [%d, %d), at most %d per call)", (long long)hop0,
+                  n_hops, tmpl_first, tmpl_first + tmpl_count, DENSE_MAX_T);
         return EWK_ERR_ARG;
     }
     DenseArgs A{};
     A.hop0 = hop0; A.n_hops = n_hops; A.T = tmpl_count;
-    int max_n = 0;
+    int max_n = 0, min_n = 1 << 30, g_back = 1 << 30, re_per_hop = 0;
     for (int k = 0; k < tmpl_count; k++) {
         const TemplateFeat& tf = ctx->h_tmpl[tmpl_first + k];
         if (!tf.valid) { ctx->fail("No reference word set. Call set_reference() first."); return EWK_ERR_NO_TEMPLATE; }
         const int L = (int)tf.n_samples;
-        if (tf.n_samples < DENSE_MIN_L || tf.n_samples > (long long)HOP * (DENSE_MAX_F - 1)) {
+        if (tf.n_samples < DENSE_MIN_L || tf.n_samples > DENSE_MAX_L) {
             ctx->fail("ewk_dense_scores: template %d has %lld samples; dense scoring needs %d..%d", tmpl_first + k,
-                      (long long)tf.n_samples, DENSE_MIN_L, HOP * (DENSE_MAX_F - 1));
+                      (long long)tf.n_samples, DENSE_MIN_L, DENSE_MAX_L);
             return EWK_ERR_ARG;
         }
         DenseTmplDev& t = A.t[k];
         t.L = L; t.n = (L + HOP - 1) / HOP; t.F = 1 + L / HOP; t.t_hi = (L - N_FFT / 2) / HOP; t.r = t.F - 1 - t.t_hi;
         t.slot = tmpl_first + k;
-        max_n = std::max(max_n, t.n);
+        t.inv_f = 1.0 / (double)t.F;
+        max_n = std::max(max_n, t.n); min_n = std::min(min_n, t.n);
+        g_back = std::min(g_back, t.n - t.t_hi);
+        re_per_hop += t.r;
     }
-    A.DG = DH + max_n + 2;
-    if ((long long)B.P < 160LL * (max_n + DH + 4) + N_FFT) {        // the kernel wraps ring positions once
+    DensePlan plan;
+    if (!dense_plan(A, min_n, max_n, re_per_hop, plan)) {
+        ctx->fail("ewk_dense_scores: this template set does not fit shared memory (%d templates, windows of %d..%d hops)",
+                  tmpl_count, min_n, max_n);
+        return EWK_ERR_ARG;
+    }
+    A.DH = plan.DH; A.DG = plan.DH + max_n + 2; A.DLE = plan.DH + max_n - min_n; A.n_re_rows = plan.DH * re_per_hop;
+    A.n_min = min_n; A.n_max = max_n; A.g_back = g_back; A.re_per_hop = re_per_hop;
+    for (int k = 0, row = 0; k < tmpl_count; k++) { A.t[k].re_row0 = row; row += A.t[k].r * plan.DH; }
+    if ((long long)B.P < 160LL * (max_n + plan.DH + 4) + N_FFT) {        // the kernel wraps ring positions once
         ctx->fail("ewk_dense_scores: ring of %d samples is too short for a template of %d hops", B.P, max_n);
         return EWK_ERR_ARG;
     }
@@ -1174,17 +1227,20 @@ extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl
         CK(ctx->b_keep_end.ensure(sizeof(long long) * 2 * (size_t)B.n_streams));
         CK(cudaMemsetAsync(ctx->b_keep_end.p, 0, sizeof(long long) * 2 * (size_t)B.n_streams, ctx->stream));
     }
+    CK(ctx->b_g2.ensure(sizeof(float) * (size_t)B.n_streams * A.DG * N_MFCC));
     A.keep_rows = (float*)ctx->b_keep_rows.p;
     A.keep_end = (long long*)ctx->b_keep_end.p;
-    const size_t smem = dense_smem_bytes(A.DG, A.T);
-    if (smem > 227 * 1024) { ctx->fail("ewk_dense_scores: templates too long for shared memory (%zu B)", smem); return EWK_ERR_ARG; }
+    A.g2 = (float*)ctx->b_g2.p;
     auto k4 = ctx->cfg.preemphasis != 0.f ? dense_score_kernel<true> : dense_score_kernel<false>;
-    CK(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    CK(cudaFuncSetAttribute(k4, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     cudaEvent_t pe = ctx->prof_begin(4);
-    k4<<<B.n_streams, DENSE_THREADS, smem, ctx->stream>>>(ctx->d_tables, B, ctx->d_tmpl, A);
+    k4<<<B.n_streams, plan.threads, plan.smem, ctx->stream>>>(ctx->d_tables, B, ctx->d_tmpl, A);
     ctx->prof_end(pe, 4);
     CK(cudaGetLastError());
     ctx->launches++;
+    ctx->dense_plan_info[0] = plan.DH; ctx->dense_plan_info[1] = plan.threads; ctx->dense_plan_info[2] = plan.per_sm;
+    ctx->dense_plan_info[3] = (int)plan.smem;
     if (where == EWK_HOST) {
         CK(cudaMemcpyAsync(out, d_out, sizeof(float) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));

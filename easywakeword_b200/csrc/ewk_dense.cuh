@@ -1,26 +1,39 @@
 // K4 — dense_score: the level-2 score of WordMatcher.calculate_similarity
 // (/root/reference/easywakeword/wakeword.py:591-625) for a template-length window at EVERY 10 ms hop
-// of every stream (usage shape of examples/tune_threshold.py:86-116 at hop
-// granularity).  One CTA per stream walks the requested hops in sub-chunks of DH hops and never writes
-// an intermediate to global memory.
+// of every stream and for every template of a set (usage shape of
+// examples/tune_threshold.py:86-116 at hop granularity; BASELINE configs[1], [4]).  One CTA per stream walks the
+// requested hops in sub-chunks of DH hops and never writes an intermediate to global memory.
 //
 // Window at hop h for template k (L samples, n = ceil(L/160), F = 1 + L/160 frames):
 //     x[160 (h - n) : 160 (h - n) + L]      — the latest template-length window that starts on the
 // hop grid and is complete at hop h (oracle.ewk_oracle.dense_window).  Handing that window to librosa
 // means window-local zero-pad centring and a window-local top_db floor, so per window:
 //   * frames t = 2 .. t_hi lie fully inside the window: they are frames of the STREAM grid
-//     (centre 160 g, g = h - n + t), shared by all windows and templates -> MFCC ring G[g];
-//   * frames t = 0, 1 (left edge) and t_hi+1 .. F-1 (right edge) see zeros outside the window and are
-//     computed per (hop, template) -> edge rows;
-//   * floor = (max log-mel over the window's frames) - 80.  Frames are first computed un-floored
-//     together with their log-mel min / max; a window whose min is below its floor recomputes just
-//     the affected frames with the floor ("patches"), everything else is reused.
-//   * mean / std over the F frames, cosine vs the template, p^1.5/10.  Consecutive windows share all but one of
-//     their stream-grid frames, so the statistics are pooled from blocks: (mean, M2) of every aligned block of 8
-//     stream-grid rows is computed once per sub-chunk, and a window combines, in a fixed order, its left edge
-//     frames, the loose rows before the first aligned block, the blocks, the loose rows after the last one and
-//     its right edge frames with the pairwise update of Chan et al. (n, mean, M2) — about 25 items instead of
-//     100 rows, no cancellation, and bit-identical for every way of cutting the request into calls or sub-chunks.
+//     (centre 160 g, g = j + t, j = h - n), shared by all windows and all templates          -> ring G[g];
+//   * frames t = 0, 1 (left edge) see zeros before the window start.  They depend on the START j only, not on
+//     the template: computed once per start and shared by every template                    -> rings LE0[j], LE1[j];
+//   * frames t = t_hi+1 .. F-1 (right edge, 1 or 2) see zeros after the window end           -> RE[k][e][hop];
+//   * floor = (max log-mel over the window's frames) - 80 (librosa.power_to_db(top_db=80)).  Frames are computed
+//     un-floored together with their log-mel min / max; a window none of whose frames reaches below its floor (the
+//     common case) is scored from the un-floored rows, the others take the floored path below.
+//
+// Statistics.  mean / std over the F frames of a window are formed from EXACT integer sums: every MFCC value
+// is quantised once to q = rint(x * 2^16) (|x| < 2^11: q fits 28 bits) and S1 = sum q, S2 = sum q^2 are 64-bit integers,
+// so consecutive windows are related by S(h) = S(h-1) + q(new row) - q(old row) with no drift and no dependence on
+// where a request is cut into calls or sub-chunks: the 32 hops of a half sub-chunk are the 32 lanes of a warp, which
+// forms the first window's sums directly, the others by an inclusive scan of the row differences, one coefficient at
+// a time.  mean = S1 / (F 2^16), var = (S2 - S1^2 / F) / (F 2^32) in double, rounded once to float32 (quantisation
+// error <= 7.6e-6 absolute per value: below float32 resolution of the pooled statistics the reference forms).  The
+// template's own features for this kernel (TemplateFeat.dmean / dstd) come from the same arithmetic on the template's
+// frames, so a window that IS the template scores exactly 100.0.
+//
+// Phases per sub-chunk (tasks are taken from shared-memory counters, one warp per task):
+//   A   frames: new stream-grid rows, left-edge rows of new starts, right-edge rows of every (template, hop)   | barrier
+//   B   per (template, half, quarter of the frame range): partial window max / min                    (B0)
+//       per (template, half, coefficient): window sums -> (mean, std) of that coefficient for 32 hops (B1)       | barrier
+//   S   per (template, half): floor test, cosine score of the un-floored windows, list of floored ones          | barrier
+//   C   (only if a window is floored) stream-grid rows floored by the sub-chunk's commonest floor f* -> G2       | barrier
+//   D   floored windows, one warp each: rows under the window's own floor (G2 when it is f*, else recomputed)    | barrier
 #pragma once
 #include <climits>
 
@@ -29,359 +42,492 @@
 
 namespace ewk {
 
-constexpr int DENSE_THREADS = 512;
-constexpr int DENSE_WARPS = DENSE_THREADS / 32;
-constexpr int DH = 32;                 // hops per sub-chunk
-constexpr int DENSE_MAX_T = 4;         // templates per launch
-constexpr int DENSE_MAX_F = 224;       // frames per window (templates up to ~2.2 s)
+constexpr int DENSE_MAX_T = 8;         // templates per launch
 constexpr int DENSE_MIN_L = 640;       // shorter templates would make a frame both left- and right-masked
-constexpr int ROW = N_MFCC + 2;        // mfcc[20], log-mel min, log-mel max
-constexpr int DENSE_KEEP = 224;        // stream-grid rows carried from one call to the next (>= frames of the longest window)
-constexpr int PATCH_CAP = 5;           // per-warp rows recomputed with a floor: 4 edge frames + 1 stream-grid frame
-constexpr int BLK = 8;                 // stream-grid rows per statistics block (aligned at absolute multiples of BLK)
+constexpr int DENSE_MAX_L = MAX_SEG;   // 3.0 s: the reference's own segment cap (wakeword.py:1114-1118)
+constexpr int ROW = N_MFCC + 3;        // mfcc[20], log-mel min, log-mel max, pad: odd stride, lanes that walk rows hit 32 banks
+constexpr int R_MIN = N_MFCC, R_MAX = N_MFCC + 1;
+constexpr int DENSE_KEEP = 304;        // stream-grid rows carried from one call to the next (>= frames of the longest window)
+constexpr int B0_PARTS = 4;            // the frame range of a window is scanned for its max / min in this many tasks
+constexpr int TAG_NONE = 0x7fc00001;   // matches no floor
+constexpr int DENSE_CTL = 32;          // control words: [0] phase-A tasks [1] phase-B tasks [2] phase-S tasks [3] floored windows
+                                       // [4] f* key; [8 + k] ring row of grid frame hs - n_k, [16 + k] LE slot of start hs - n_k
 
 struct DenseTmplDev {
     int L, n, F, t_hi, r, slot;        // r = F - 1 - t_hi right-edge frames
+    int re_row0;                       // first of this template's right-edge rows: RE[re_row0 + e * DH + hl]
+    int pad;
+    double inv_f;                      // 1 / F (IEEE double division: the same bits on host and device)
 };
 
 struct DenseArgs {
     long long hop0;                    // first hop scored (hop h <-> 160 h samples of the stream)
     int n_hops;
     int T;
-    int DG;                            // rows of the grid-frame ring
+    int DH;                            // hops per sub-chunk (32 or 64)
+    int DG;                            // rows of the grid-frame ring (>= DH + n_max + 2)
+    int DLE;                           // starts held by the left-edge rings (>= DH + n_max - n_min)
+    int n_re_rows;                     // sum over templates of DH * r
+    int n_min, n_max;                  // shortest / longest window in hops
+    int g_back;                        // min over templates of n - t_hi: the newest grid row a sub-chunk needs is hop - g_back
+    int re_per_hop;                    // sum over templates of r
     DenseTmplDev t[DENSE_MAX_T];
     float* out;                        // [n_streams][n_hops][T]
+    float* g2;                         // [n_streams][DG][20]: grid rows floored with one floor value (tags in shared memory)
     // carry-over between consecutive calls: the newest stream-grid rows of every stream (functions of the PCM only)
     float* keep_rows;                  // [n_streams][DENSE_KEEP][ROW], row of grid frame g at g % DENSE_KEEP
     long long* keep_end;               // [n_streams][2]: grid frames [keep_end[2s], keep_end[2s+1]) are stored (0, 0: nothing)
 };
 
-__host__ __device__ inline int dense_nblk(int DG) { return DG / BLK + 2; }     // ring of block statistics
-
-__host__ __device__ inline size_t dense_smem_bytes(int DG, int T) {
-    return sizeof(FrameTables) +
-           sizeof(float) * ((size_t)DENSE_WARPS * SCR_WARP + (size_t)DG * ROW + (size_t)T * DH * 4 * ROW +
-                            (size_t)DENSE_WARPS * PATCH_CAP * N_MFCC + (size_t)DG * (N_MFCC + 1) + 8 +
-                            (size_t)2 * dense_nblk(DG) * 2 * N_MFCC);
+__host__ __device__ inline size_t dense_smem_bytes(int nwarps, int T, int DH, int DG, int DLE, int n_re_rows) {
+    const size_t words = (size_t)nwarps * SCR_WARP + (size_t)2 * T * N_MFCC * DH + (size_t)DG * ROW + (size_t)2 * DLE * ROW +
+                         (size_t)n_re_rows * ROW + (size_t)2 * T * DH * B0_PARTS + (size_t)T * DH + (size_t)nwarps * N_MFCC +
+                         (size_t)DG + (size_t)T * DH + DENSE_CTL;
+    return sizeof(FrameTables) + 4 * words;
 }
 
-// frame `t` of the window of template `tp` starting at grid index j: pointer to its ROW
-// (jb = j mod DG, so that the ring index is one add and one conditional subtract)
-__device__ __forceinline__ const float* dense_row(const float* G, const float* edge_kh, const DenseTmplDev& tp, int DG,
-                                                  int jb, int t) {
-    if (t < 2) return edge_kh + t * ROW;
-    if (t <= tp.t_hi) { int r = jb + t; if (r >= DG) r -= DG; return G + r * ROW; }
-    return edge_kh + (2 + t - tp.t_hi - 1) * ROW;
+// ---- exact integer statistics -------------------------------------------------------------------------------
+__device__ __forceinline__ int quant16(float x) {           // rint(x * 2^16), |x| clamped below 2^11 (any real MFCC is)
+    return __float2int_rn(fminf(fmaxf(x, -2047.f), 2047.f) * 65536.0f);
 }
 
-// (mean, M2 = sum of squared deviations) of BLK values, two passes, fixed order
-__device__ __forceinline__ void block_mean_m2(const float (&v)[BLK], float& mu, float& m2) {
-    float sum = 0.f;
+// (S1, S2) over F frames -> mean, std (ddof 0) as float32; the same function serves windows and templates
+__device__ __forceinline__ void dense_stats(long long S1, long long S2, double invf, float& mean, float& sd) {
+    const double s1 = (double)S1, s2 = (double)S2;
+    mean = (float)(s1 * invf * (1.0 / 65536.0));
+    const double var = (s2 - s1 * s1 * invf) * invf * (1.0 / 4294967296.0);
+    sd = sqrtf(fmaxf((float)var, 0.f));
+}
+
+// Template features for this kernel: the integer statistics of the template's own MFCC frames (K3's frames_out).
+__global__ void dense_template_features_kernel(const float* __restrict__ frames, int F, int n_mfcc, float* __restrict__ out40) {
+    const int lane = threadIdx.x;
+    long long S1 = 0, S2 = 0;
+    if (lane < N_MFCC)
+        for (int t = 0; t < F; t++) {
+            const int q = quant16(frames[(size_t)t * N_MFCC + lane]);
+            S1 += q;
+            S2 += (long long)q * q;
+        }
+    float mean, sd;
+    dense_stats(S1, S2, 1.0 / (double)F, mean, sd);
+    if (lane < N_MFCC) {
+        out40[lane] = lane < n_mfcc ? mean : 0.f;
+        out40[N_MFCC + lane] = lane < n_mfcc ? sd : 0.f;
+    }
+}
+
+// ---- frame loaders for ring views (no pre-emphasis): frame sample m = 2 lane + 64 a, pairs from one aligned word -----
+// p0: ring position of frame sample 0 (even; may be negative by less than P).  Samples m < LO and m >= hi are zero
+// (window-local zero padding); LO is a compile-time multiple of 32 so that fully masked words are never loaded.
+template <int LO, bool RIGHT>
+__device__ __forceinline__ void dense_load_pairs(const void* ring_s, int fmt, int P, int p0, int hi, int lane, float2 (&x)[8]) {
+    if (p0 < 0) p0 += P;
+    const int w0 = (p0 >> 1) + lane, WP = P >> 1;
+    const bool wrap = p0 + N_FFT > P;                           // warp-uniform
 #pragma unroll
-    for (int q = 0; q < BLK; q++) sum += v[q];
-    mu = sum * (1.0f / BLK);
-    m2 = 0.f;
-#pragma unroll
-    for (int q = 0; q < BLK; q++) { const float d = v[q] - mu; m2 = fmaf(d, d, m2); }
+    for (int a = 0; a < 8; a++) {
+        if (64 * a + 64 <= LO) { x[a] = make_float2(0.f, 0.f); continue; }
+        int w = w0 + 32 * a;
+        if (wrap && w >= WP) w -= WP;
+        float2 v;
+        if (fmt == 1) {
+            const unsigned u = __ldg(reinterpret_cast<const unsigned*>(ring_s) + w);
+            v = make_float2((float)(short)(u & 0xffff) * (1.0f / 32768.0f), (float)((int)u >> 16) * (1.0f / 32768.0f));
+        } else v = __ldg(reinterpret_cast<const float2*>(ring_s) + w);
+        const int m = 2 * lane + 64 * a;
+        if (64 * a < LO && m < LO) v = make_float2(0.f, 0.f);   // LO is even: a pair is masked as a whole
+        if (RIGHT) { if (m >= hi) v.x = 0.f; if (m + 1 >= hi) v.y = 0.f; }
+        x[a] = v;
+    }
 }
 
-// pooled update (Chan, Golub, LeVeque): fold an item (nb values, mean mb, M2 m2b) into the running (n, mean, M2)
-__device__ __forceinline__ void pool_item(float& n, float& mean, float& M2, float nb, float mb, float m2b) {
-    const float nn = n + nb, f = __fdividef(nb, nn), delta = mb - mean;
-    mean = fmaf(delta, f, mean);
-    M2 += fmaf(delta * delta, n * f, m2b);
-    n = nn;
+enum : int { FR_GRID = 0, FR_LE0 = 1, FR_LE1 = 2, FR_RE = 3 };
+
+// One frame of the dense kernel -> row (20 MFCCs [+ min, max when stats]).  `pos` is the ring position of the frame's
+// sample 0 for grid frames, of the WINDOW's sample 0 for edge frames (t: frame index in the window, L: window length).
+template <bool PRE>
+__device__ __noinline__ void dense_frame(int kind, const void* ring_s, int fmt, int P, int pos, int t, int L, float pre,
+                                            const FrameTables& ft, float* scr, int lane, float floor_db,
+                                            float* __restrict__ row, bool stats) {
+    float2 x[8];
+    if (PRE) {
+        // generic loader through a window view (pre-emphasis needs x[n-1] and the window's own initial state)
+        PcmReader rd;
+        rd.f = fmt == 0 ? (const float*)ring_s : nullptr;
+        rd.q = fmt == 1 ? (const short*)ring_s : nullptr;
+        rd.ring = P; rd.pre = pre;
+        int f0;
+        if (kind == FR_GRID) {                                   // view starts 2 samples early: no window starts there
+            int p = pos - 2; if (p < 0) p += P;
+            rd.start = p; rd.len = N_FFT + 2; f0 = 2;
+        } else {
+            rd.start = pos; rd.len = L; f0 = t * HOP - N_FFT / 2;
+        }
+        load_frame_pairs_at<true>(rd, f0, lane, x);
+    } else {
+        if (kind == FR_GRID) dense_load_pairs<0, false>(ring_s, fmt, P, pos, N_FFT, lane, x);
+        else if (kind == FR_LE0) dense_load_pairs<256, false>(ring_s, fmt, P, pos - 256, N_FFT, lane, x);
+        else if (kind == FR_LE1) dense_load_pairs<96, false>(ring_s, fmt, P, pos - 96, N_FFT, lane, x);
+        else {
+            int p = pos + t * HOP - N_FFT / 2; if (p >= P) p -= P;
+            dense_load_pairs<0, true>(ring_s, fmt, P, p, L - (t * HOP - N_FFT / 2), lane, x);
+        }
+    }
+    float mn, mx;
+    warp_frame_mfcc(x, ft, scr, lane, floor_db, row, mn, mx);
+    if (stats && lane == 0) { row[R_MIN] = mn; row[R_MAX] = mx; }
 }
+
+__device__ __forceinline__ int next_task(int* counter, int lane) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(counter, 1);
+    return __shfl_sync(FULL, t, 0);
+}
+
+__device__ __forceinline__ int wrap1(int r, int n) { return r >= n ? r - n : r; }
 
 template <bool PRE>
-__global__ void __launch_bounds__(DENSE_THREADS, 2)
+__global__ void __launch_bounds__(1024, 1)
 dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, DenseArgs A) {
     extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, nthr = blockDim.x;
+    const int DH = A.DH, DG = A.DG, DLE = A.DLE, NT = A.T;
     FrameTables* ft = reinterpret_cast<FrameTables*>(smem);
     float* scratch = smem + sizeof(FrameTables) / sizeof(float);
-    float* G = scratch + DENSE_WARPS * SCR_WARP;                 // [DG][ROW]
-    float* edge = G + (size_t)A.DG * ROW;                        // [T][DH][4][ROW]
-    float* wbuf = edge + (size_t)A.T * DH * 4 * ROW;             // per warp: patch[PATCH_CAP][20]
-    // alternate ring: rows of G recomputed with ONE floor value (the current one of the stream), tagged per row, so
-    // that a floored stream-grid frame is recomputed once per floor value and not once per window that contains it
-    float* G2 = wbuf + (size_t)DENSE_WARPS * PATCH_CAP * N_MFCC;                        // [DG][20]
-    int* g2tag = reinterpret_cast<int*>(G2 + (size_t)A.DG * N_MFCC);                    // [DG] floor bits of the row
-    int* fstar_s = g2tag + A.DG;                                                        // [1] floor bits served by G2
-    // statistics of aligned blocks of BLK stream-grid rows, (mean[20], M2[20]) each, block g / BLK at (g / BLK) % NBLK:
-    // BS[0] over the un-floored rows G, BS[1] over the rows as floored by the stream's current floor (G2 where it applies)
-    const int NBLK = dense_nblk(A.DG);
-    float* BS = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(fstar_s + 4) + 15) & ~(uintptr_t)15);   // [2][NBLK][40]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float2* MS = reinterpret_cast<float2*>(scratch + (size_t)nwarps * SCR_WARP);   // [T][20][DH] (mean, std) of a coefficient
+    float* G = reinterpret_cast<float*>(MS + (size_t)NT * N_MFCC * DH);            // [DG][ROW], grid frame g at g % DG
+    float* LE0 = G + (size_t)DG * ROW;                           // [DLE][ROW], start j at j % DLE: frame t = 0
+    float* LE1 = LE0 + (size_t)DLE * ROW;                        //                                  frame t = 1
+    float* RE = LE1 + (size_t)DLE * ROW;                         // [n_re_rows][ROW]
+    float* PM = RE + (size_t)A.n_re_rows * ROW;                  // [T][B0_PARTS][2][DH] partial (max, min)
+    float* WFL = PM + (size_t)2 * NT * DH * B0_PARTS;            // [T][DH] floor of a floored window, +INF otherwise
+    float* patchb = WFL + (size_t)NT * DH;                       // [nwarps][20]
+    int* g2tag = reinterpret_cast<int*>(patchb + (size_t)nwarps * N_MFCC);          // [DG] floor bits of the row's G2 copy
+    int* FLIST = g2tag + DG;                                     // [T][DH] floored windows: k * DH + hl
+    int* ctl = FLIST + NT * DH;                                  // [DENSE_CTL]
     const int s = blockIdx.x;
-    copy_frame_tables(*ft, T, tid, DENSE_THREADS);
+    copy_frame_tables(*ft, T, tid, nthr);
     float* scr = scratch + warp * SCR_WARP;
-    for (int i = tid; i < A.DG; i += DENSE_THREADS) g2tag[i] = 0x7fc00001;     // matches no floor
-    __syncthreads();
-
-    float* patch = wbuf + (size_t)warp * PATCH_CAP * N_MFCC;
+    float* patch = patchb + warp * N_MFCC;
+    for (int i = tid; i < DG; i += nthr) g2tag[i] = TAG_NONE;
+    if (tid < DENSE_CTL) ctl[tid] = 0;
 
     const size_t esz = B.fmt == 1 ? 2 : 4;
-    PcmReader rd;
-    rd.f = B.fmt == 0 ? (const float*)((const char*)B.ring + (size_t)s * B.P * esz) : nullptr;
-    rd.q = B.fmt == 1 ? (const short*)((const char*)B.ring + (size_t)s * B.P * esz) : nullptr;
-    rd.ring = B.P;
+    const void* ring_s = (const char*)B.ring + (size_t)s * B.P * esz;
+    const int fmt = B.fmt, P = B.P;
+    float* G2 = A.g2 + (size_t)s * DG * N_MFCC;
     __syncthreads();
-    rd.pre = PRE ? ft->preemph : 0.f;
-    // stream-grid frames are read through a view that starts `back` samples early, so that pre-emphasis finds x[n-1]
-    // of the frame's first sample inside the view (no window starts there); without pre-emphasis the view is the frame
-    constexpr int back = PRE ? 2 : 0;
+    const float pre = PRE ? ft->preemph : 0.f;
+    const int n_mfcc = ft->n_mfcc;
 
-    int max_n = 0, min_n = INT_MAX;
-    for (int k = 0; k < A.T; k++) { max_n = max(max_n, A.t[k].n); min_n = min(min_n, A.t[k].n); }
-
-    long long g_done = LLONG_MIN, g_valid_lo = LLONG_MAX;       // ring G holds rows [max(g_valid_lo, g_done - DG), g_done)
+    long long g_done = LLONG_MIN, g_valid_lo = LLONG_MAX;        // ring G holds rows [max(g_valid_lo, g_done - DG), g_done)
+    long long le_done = LLONG_MIN;                               // left-edge rows of starts < le_done are in the LE rings
     {
         // rows computed by the previous call are reused when this call continues where it stopped: the history of
-        // the first window (up to t_hi frames) is loaded instead of recomputed
-        long long need_lo = LLONG_MAX;
-        for (int k = 0; k < A.T; k++) need_lo = min(need_lo, A.hop0 - A.t[k].n + 2);
+        // the first window (up to n_max frames) is loaded instead of recomputed
+        long long need_lo = A.hop0 - A.n_max + 1;
         if (need_lo < 2) need_lo = 2;
         const long long klo = A.keep_rows ? A.keep_end[2 * s] : 0, kend = A.keep_rows ? A.keep_end[2 * s + 1] : 0;
-        if (klo <= need_lo && need_lo < kend && kend - need_lo <= A.DG) {
+        if (klo <= need_lo && need_lo < kend && kend - need_lo <= DG) {
             const float* kr = A.keep_rows + (size_t)s * DENSE_KEEP * ROW;
             const int cnt = (int)(kend - need_lo);
-            for (int i = tid; i < cnt * ROW; i += DENSE_THREADS) {
+            for (int i = tid; i < cnt * ROW; i += nthr) {
                 const long long g = need_lo + i / ROW;
-                G[(size_t)(g % A.DG) * ROW + i % ROW] = kr[(size_t)(g % DENSE_KEEP) * ROW + i % ROW];
+                G[(size_t)(g % DG) * ROW + i % ROW] = kr[(size_t)(g % DENSE_KEEP) * ROW + i % ROW];
             }
             g_done = kend;
             g_valid_lo = need_lo;
         }
         __syncthreads();
     }
+
     for (long long hs = A.hop0; hs < A.hop0 + A.n_hops; hs += DH) {
         const int nh = (int)min((long long)DH, A.hop0 + A.n_hops - hs);
-        // ---- frames of this sub-chunk: new stream-grid frames, then the edge frames of every (hop, template)
-        long long g_lo = LLONG_MAX, g_hi = LLONG_MIN;
-        for (int k = 0; k < A.T; k++) {
-            g_lo = min(g_lo, hs - A.t[k].n + 2);
-            g_hi = max(g_hi, hs + nh - 1 - A.t[k].n + A.t[k].t_hi);
-        }
+        const int n_half = (nh + 31) >> 5;
+        // ================================================================ phase A: frames of this sub-chunk
+        // stream-grid rows [g_from, g_hi]: every template's windows of these hops reach back to hs - n + 1 (the row a
+        // sliding difference removes) and forward to hop - (n - t_hi)
+        long long g_lo = hs - A.n_max + 1;
         if (g_lo < 2) g_lo = 2;                                   // grid frame g needs samples from 160 g - 256 >= 0
+        const long long g_hi = hs + nh - 1 - A.g_back;
         const long long g_from = max(g_lo, g_done);
         if (g_valid_lo == LLONG_MAX) g_valid_lo = g_from;
         const int n_g = (int)max(0LL, g_hi - g_from + 1);
-        int n_e = 0;
-        for (int k = 0; k < A.T; k++) n_e += DH * (2 + A.t[k].r);        // job = (template, edge e, hop slot): slots >= nh are skipped
-        // 32-bit bases for this sub-chunk: ring position of sample 160*hs and ring row of grid frame g_from
-        const int hs_pos = (int)((160 * hs) % B.P);
-        const int gfrom_row = n_g > 0 ? (int)(g_from % A.DG) : 0;
-        const int gfrom_rel = (int)(g_from - hs);                  // grid index relative to hs
-        for (int job = warp; job < n_g + n_e; job += DENSE_WARPS) {
-            float* row;
-            int f0;
+        // left-edge rows of the starts these hops use: [hs - n_max, hs + nh - n_min), those not yet in the rings
+        long long le_lo = hs - A.n_max;
+        if (le_lo < 0) le_lo = 0;
+        const long long le_hi = hs + nh - A.n_min;               // exclusive
+        const long long le_from = max(le_lo, le_done);
+        const int n_le = (int)max(0LL, le_hi - le_from);
+        const int n_re = A.re_per_hop * nh;                      // enumerated as (hop slot, template, e)
+        // 32-bit bases for this sub-chunk: ring position of sample 160 * hs, ring rows / slots of the first new frames
+        const int hs_pos = (int)((160 * hs) % P);
+        const int gfrom_row = n_g > 0 ? (int)(g_from % DG) : 0;
+        const int gfrom_rel = (int)(g_from - hs), lefrom_rel = (int)(le_from - hs);
+        const int lefrom_slot = n_le > 0 ? (int)(le_from % DLE) : 0;
+        if (tid == 0) { ctl[1] = 0; ctl[2] = 0; ctl[3] = 0; ctl[4] = -1; }
+        if (tid < NT) {
+            // per template: ring row of grid frame (hs - n) and LE slot of start (hs - n), both possibly "negative" frames
+            const long long j0 = hs - A.t[tid].n;
+            ctl[8 + tid] = (int)(((j0 % DG) + DG) % DG);
+            ctl[16 + tid] = (int)(((j0 % DLE) + DLE) % DLE);
+        }
+        const int n_tasks_a = n_g + 2 * n_le + n_re;
+        for (int job = next_task(ctl + 0, lane); job < n_tasks_a; job = next_task(ctl + 0, lane)) {
             if (job < n_g) {
-                // absolute first sample 160 g - 256 (unmasked frame of the stream grid)
-                int pos = hs_pos + 160 * (gfrom_rel + job) - N_FFT / 2 - back;       // |offset| < P: one wrap
-                if (pos < 0) pos += B.P; else if (pos >= B.P) pos -= B.P;
-                rd.start = pos; rd.len = N_FFT + back;
-                f0 = back;
-                int r = gfrom_row + job; if (r >= A.DG) r -= A.DG;
-                row = G + r * ROW;
-                if (lane == 0) g2tag[r] = 0x7fc00001;
+                int pos = hs_pos + 160 * (gfrom_rel + job) - N_FFT / 2;          // |offset| < P: one wrap
+                if (pos < 0) pos += P; else if (pos >= P) pos -= P;
+                const int r = wrap1(gfrom_row + job, DG);
+                if (lane == 0) g2tag[r] = TAG_NONE;
+                dense_frame<PRE>(FR_GRID, ring_s, fmt, P, pos, 0, 0, pre, *ft, scr, lane, -INFINITY, G + r * ROW, true);
+            } else if (job < n_g + 2 * n_le) {
+                const int q = job - n_g, i = q >> 1, e = q & 1;
+                int pos = hs_pos + 160 * (lefrom_rel + i);                      // window start
+                if (pos < 0) pos += P; else if (pos >= P) pos -= P;
+                const int sl = wrap1(lefrom_slot + i, DLE);
+                // window length for the generic (pre-emphasis) view: any L >= 640 gives the same left-edge frames
+                dense_frame<PRE>(e ? FR_LE1 : FR_LE0, ring_s, fmt, P, pos, e, DENSE_MIN_L, pre, *ft, scr, lane, -INFINITY,
+                                 (e ? LE1 : LE0) + sl * ROW, true);
             } else {
-                int rem = job - n_g, k = 0;
-                while (rem >= DH * (2 + A.t[k].r)) { rem -= DH * (2 + A.t[k].r); k++; }
+                const int q = job - n_g - 2 * n_le;
+                const int hl = q / A.re_per_hop;
+                int rem = q - hl * A.re_per_hop, k = 0;
+                while (rem >= A.t[k].r) { rem -= A.t[k].r; k++; }
                 const DenseTmplDev& tp = A.t[k];
-                const int e = rem / DH, hl = rem % DH;              // DH is a power of two
-                if (hl >= nh || hs + hl - tp.n < 0) continue;       // unused slot / window starts before the stream
-                const int t = e < 2 ? e : tp.t_hi + 1 + (e - 2);
+                if (hs + hl - tp.n < 0) continue;                               // window starts before the stream
                 int pos = hs_pos + 160 * (hl - tp.n);
-                if (pos < 0) pos += B.P; else if (pos >= B.P) pos -= B.P;
-                rd.start = pos; rd.len = tp.L;                      // zeros outside the window
-                f0 = t * HOP - N_FFT / 2;
-                row = edge + ((k * DH + hl) * 4 + e) * ROW;
+                if (pos < 0) pos += P; else if (pos >= P) pos -= P;
+                dense_frame<PRE>(FR_RE, ring_s, fmt, P, pos, tp.t_hi + 1 + rem, tp.L, pre, *ft, scr, lane, -INFINITY,
+                                 RE + (tp.re_row0 + rem * DH + hl) * ROW, true);
             }
-            float2 x[8];
-            load_frame_pairs_at<PRE>(rd, f0, lane, x);
-            float mn, mx;
-            warp_frame_mfcc(x, *ft, scr, lane, -INFINITY, row, mn, mx);
-            if (lane == 0) { row[N_MFCC] = mn; row[N_MFCC + 1] = mx; }
         }
         g_done = g_hi + 1;
+        le_done = le_hi;
         __syncthreads();
 
-        // ---- the floor of the newest window of template 0 is the stream's current floor f*: stream-grid frames it
-        // changes are recomputed once into G2 (only rows not yet tagged with f*: in steady state the new rows)
-        {
-            const DenseTmplDev& tp0 = A.t[0];
-            const long long jl0 = hs + nh - 1 - tp0.n;
-            if (warp == 0) {
-                float wmax = -INFINITY;
-                if (jl0 >= 0) {
-                    const int j0 = (int)(jl0 % A.DG);
-                    const float* ek0 = edge + (nh - 1) * 4 * ROW;
-                    for (int t = lane; t < tp0.F; t += 32) wmax = fmaxf(wmax, dense_row(G, ek0, tp0, A.DG, j0, t)[N_MFCC + 1]);
+        // ================================================================ phase B: window max / min and window sums
+        if (tid == 0) ctl[0] = 0;
+        const int n_b0 = NT * n_half * B0_PARTS, n_b1 = NT * n_half * n_mfcc;
+        for (int job = next_task(ctl + 1, lane); job < n_b0 + n_b1; job = next_task(ctl + 1, lane)) {
+            if (job < n_b0) {
+                // ---- B0: partial max / min over a quarter of the window's frames, lanes = hops
+                const int p = job % B0_PARTS, kh = job / B0_PARTS, hh = kh % n_half, k = kh / n_half;
+                const DenseTmplDev& tp = A.t[k];
+                const int hl = 32 * hh + lane;
+                const bool valid = hl < nh && hs + hl - tp.n >= 0;
+                float wmax = -INFINITY, wmin = INFINITY;
+                if (valid) {
+                    const int cnt = tp.t_hi - 1;                                // grid frames t = 2 .. t_hi
+                    const int ta = 2 + (cnt * p) / B0_PARTS, tb = 2 + (cnt * (p + 1)) / B0_PARTS;
+                    int r = wrap1(ctl[8 + k] + hl + ta, DG);
+                    for (int t = ta; t < tb; t++) {
+                        wmax = fmaxf(wmax, G[r * ROW + R_MAX]);
+                        wmin = fminf(wmin, G[r * ROW + R_MIN]);
+                        if (++r == DG) r = 0;
+                    }
+                    if (p == 0) {
+                        const int sl = wrap1(ctl[16 + k] + hl, DLE);
+                        wmax = fmaxf(wmax, fmaxf(LE0[sl * ROW + R_MAX], LE1[sl * ROW + R_MAX]));
+                        wmin = fminf(wmin, fminf(LE0[sl * ROW + R_MIN], LE1[sl * ROW + R_MIN]));
+                        for (int e = 0; e < tp.r; e++) {
+                            const float* re = RE + (tp.re_row0 + e * DH + hl) * ROW;
+                            wmax = fmaxf(wmax, re[R_MAX]);
+                            wmin = fminf(wmin, re[R_MIN]);
+                        }
+                    }
+                }
+                if (hl < DH) {
+                    float* pm = PM + (size_t)((k * B0_PARTS + p) * 2) * DH + hl;
+                    pm[0] = wmax; pm[DH] = wmin;
+                }
+            } else {
+                // ---- B1: (mean, std) of one coefficient for the 32 hops of a half: exact integer window sums
+                const int q = job - n_b0;
+                const int c = q % n_mfcc, kh = q / n_mfcc, hh = kh % n_half, k = kh / n_half;
+                const DenseTmplDev& tp = A.t[k];
+                const int hl = 32 * hh + lane;
+                const bool valid = hl < nh && hs + hl - tp.n >= 0;
+                const unsigned vm = __ballot_sync(FULL, valid);
+                if (vm == 0) continue;
+                const int l0 = __ffs(vm) - 1;                                   // first valid hop; valid hops are contiguous
+                const int rb = ctl[8 + k] + 32 * hh;                            // ring row of "grid frame" j of lane 0 (< 2 DG)
+                // base: the first valid window's interior frames t = 2 .. t_hi, lanes = rows
+                long long b1 = 0, b2 = 0;
+                {
+                    int r = rb + l0 + 2 + lane;
+                    while (r >= DG) r -= DG;
+                    for (int t = 2 + lane; t <= tp.t_hi; t += 32) {
+                        const int v = quant16(G[r * ROW + c]);
+                        b1 += v; b2 += (long long)v * v;
+                        r += 32; while (r >= DG) r -= DG;
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) { b1 += __shfl_xor_sync(FULL, b1, o); b2 += __shfl_xor_sync(FULL, b2, o); }
+                }
+                // differences: window j (lane > l0) = window j - 1 + row (j + t_hi) - row (j + 1)
+                long long d1 = 0, d2 = 0;
+                if (valid && lane > l0) {
+                    int rin = rb + lane + tp.t_hi, rout = rb + lane + 1;
+                    while (rin >= DG) rin -= DG;
+                    while (rout >= DG) rout -= DG;
+                    const int vin = quant16(G[rin * ROW + c]), vout = quant16(G[rout * ROW + c]);
+                    d1 = (long long)vin - vout;
+                    d2 = (long long)vin * vin - (long long)vout * vout;
                 }
 #pragma unroll
-                for (int o = 16; o; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(FULL, wmax, o));
-                if (lane == 0) *fstar_s = jl0 >= 0 ? __float_as_int(wmax - 80.0f) : 0x7fc00002;
-            }
-            __syncthreads();
-            const int fbits = *fstar_s;
-            const float fstar = __int_as_float(fbits);
-            const int span = (int)(g_hi - g_lo + 1);
-            const int row_lo = span > 0 ? (int)(g_lo % A.DG) : 0;
-            const int glo_rel = (int)(g_lo - hs);
-            if (fbits != 0x7fc00002)
-                for (int i = warp; i < span; i += DENSE_WARPS) {
-                    int r = row_lo + i; if (r >= A.DG) r -= A.DG;
-                    if (!(G[r * ROW + N_MFCC] < fstar) || g2tag[r] == fbits) continue;      // warp-uniform
-                    int pos = hs_pos + 160 * (glo_rel + i) - N_FFT / 2 - back;
-                    if (pos < 0) pos += B.P; else if (pos >= B.P) pos -= B.P;
-                    rd.start = pos; rd.len = N_FFT + back;
-                    float2 x[8];
-                    load_frame_pairs_at<PRE>(rd, back, lane, x);
-                    float mn, mx;
-                    warp_frame_mfcc(x, *ft, scr, lane, fstar, G2 + r * N_MFCC, mn, mx);
-                    if (lane == 0) g2tag[r] = fbits;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long u1 = __shfl_up_sync(FULL, d1, o), u2 = __shfl_up_sync(FULL, d2, o);
+                    if (lane >= o) { d1 += u1; d2 += u2; }
                 }
-            __syncthreads();
-        }
-
-        // ---- statistics of the span's aligned blocks (both variants), one warp per block
-        // blocks [b_lo, b_lo + n_blk) lie inside the span; 32-bit ring positions of the first one
-        const long long b_lo = (g_lo + BLK - 1) / BLK;
-        const int n_blk = (int)max(0LL, (g_hi + 1) / BLK - b_lo);
-        const int blk_row_lo = (int)((b_lo * BLK) % A.DG), blk_idx_lo = (int)(b_lo % NBLK);
-        {
-            const int fb = *fstar_s;
-            const float fstar = __int_as_float(fb);
-            for (int i = warp; i < 2 * n_blk; i += DENSE_WARPS) {
-                const int var = i & 1;
-                int r = blk_row_lo + (i >> 1) * BLK; if (r >= A.DG) r -= A.DG;       // n_blk * BLK <= DG
-                int bi = blk_idx_lo + (i >> 1); if (bi >= NBLK) bi -= NBLK;
-                float v[BLK];
-#pragma unroll
-                for (int q = 0; q < BLK; q++) {
-                    const float* src = G + r * ROW;
-                    if (var && src[N_MFCC] < fstar && g2tag[r] == fb) src = G2 + r * N_MFCC;
-                    v[q] = lane < N_MFCC ? src[lane] : 0.f;
-                    r++; if (r >= A.DG) r -= A.DG;
+                long long S1 = b1 + d1, S2 = b2 + d2;
+                float mean = 0.f, sd = 0.f;
+                if (valid) {
+                    const int sl = wrap1(ctl[16 + k] + hl, DLE);
+                    int v = quant16(LE0[sl * ROW + c]);  S1 += v; S2 += (long long)v * v;
+                    v = quant16(LE1[sl * ROW + c]);      S1 += v; S2 += (long long)v * v;
+                    for (int e = 0; e < tp.r; e++) {
+                        v = quant16(RE[(tp.re_row0 + e * DH + hl) * ROW + c]);
+                        S1 += v; S2 += (long long)v * v;
+                    }
+                    dense_stats(S1, S2, tp.inv_f, mean, sd);
                 }
-                float mu, m2;
-                block_mean_m2(v, mu, m2);
-                float* dst = BS + ((size_t)var * NBLK + (size_t)bi) * 2 * N_MFCC;
-                if (lane < N_MFCC) { dst[lane] = mu; dst[N_MFCC + lane] = m2; }
+                if (hl < DH) MS[((size_t)k * N_MFCC + c) * DH + hl] = make_float2(mean, sd);
             }
         }
         __syncthreads();
 
-        // ---- windows of this sub-chunk, one warp per (template, hop): window max -> floor; class of the window
-        //   0: no stream-grid frame of the window is floored            -> block statistics over G
-        //   1: floored, and the floor is the stream's current one (f*)  -> block statistics over G2 | G
-        //   2: floored with another floor: blocks are formed here, floored rows recomputed on the fly
-        // All three give the same bits for the same window: same items, same order, same arithmetic.
-        for (int w = warp; w < A.T * nh; w += DENSE_WARPS) {
-            const int k = w / nh, hl = w - k * nh;
-            const DenseTmplDev tp = A.t[k];
-            const long long jl = hs + hl - tp.n;
-            float* outp = A.out + ((size_t)s * A.n_hops + (size_t)(hs - A.hop0 + hl)) * A.T + k;
+        // ================================================================ phase S: floors, scores of un-floored windows
+        for (int job = next_task(ctl + 2, lane); job < NT * n_half; job = next_task(ctl + 2, lane)) {
+            const int hh = job % n_half, k = job / n_half;
+            const DenseTmplDev& tp = A.t[k];
+            const int hl = 32 * hh + lane;
             const TemplateFeat& tf = tmpl[tp.slot];
-            if (jl < 0 || !tf.valid) { if (lane == 0) *outp = __int_as_float(0x7fc00000); continue; }
-            const int j = (int)(jl % A.DG);                            // ring row base of this window
-            const float* ekh = edge + (k * DH + hl) * 4 * ROW;
-            float wmax = -INFINITY, rmin = INFINITY;                   // max over all frames, min over the ring frames
-            for (int t = 2 + lane; t <= tp.t_hi; t += 32) {
-                int r = j + t; if (r >= A.DG) r -= A.DG;
-                rmin = fminf(rmin, G[r * ROW + N_MFCC]);
-                wmax = fmaxf(wmax, G[r * ROW + N_MFCC + 1]);
-            }
-            const int n_edge = 2 + tp.r;
-            const float emin = lane < n_edge ? ekh[lane * ROW + N_MFCC] : INFINITY;
-            if (lane < n_edge) wmax = fmaxf(wmax, ekh[lane * ROW + N_MFCC + 1]);
+            if (hl >= nh) continue;
+            float* outp = A.out + ((size_t)s * A.n_hops + (size_t)(hs - A.hop0 + hl)) * NT + k;
+            if (hs + hl - tp.n < 0 || !tf.valid) { *outp = __int_as_float(0x7fc00000); WFL[k * DH + hl] = INFINITY; continue; }
+            float wmax = -INFINITY, wmin = INFINITY;
 #pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                wmax = fmaxf(wmax, __shfl_xor_sync(FULL, wmax, o));
-                rmin = fminf(rmin, __shfl_xor_sync(FULL, rmin, o));
+            for (int p = 0; p < B0_PARTS; p++) {
+                const float* pm = PM + (size_t)((k * B0_PARTS + p) * 2) * DH + hl;
+                wmax = fmaxf(wmax, pm[0]); wmin = fminf(wmin, pm[DH]);
             }
-            const float floor_db = wmax - 80.0f;                       // librosa.power_to_db(top_db=80) on this window
-            const unsigned emask = __ballot_sync(FULL, emin < floor_db);   // floored edge frames
-            const int cls = !(rmin < floor_db) ? 0 : (__float_as_int(floor_db) == *fstar_s ? 1 : 2);
-            { int pos = hs_pos + 160 * (hl - tp.n); if (pos < 0) pos += B.P; else if (pos >= B.P) pos -= B.P; rd.start = pos; }
-            rd.len = tp.L;
-            // floored edge frames are recomputed with the floor (window-local PCM view) into patch slots 0..3
-            for (unsigned mm = emask; mm; mm &= mm - 1) {
-                const int e = __ffs(mm) - 1;
-                const int t = e < 2 ? e : tp.t_hi + 1 + (e - 2);
-                float2 x[8];
-                load_frame_pairs_at<PRE>(rd, t * HOP - N_FFT / 2, lane, x);
-                float mn, mx;
-                warp_frame_mfcc(x, *ft, scr, lane, floor_db, patch + e * N_MFCC, mn, mx);
+            const float floor_db = wmax - 80.0f;                                // librosa.power_to_db(top_db=80) on this window
+            if (wmin < floor_db) {                                              // some frame reaches below the floor
+                WFL[k * DH + hl] = floor_db;
+                FLIST[atomicAdd(ctl + 3, 1)] = k * DH + hl;
+                atomicMax(ctl + 4, ((NT - 1 - k) << 8) | hl);                   // f*: newest floored window of the first template that has one
+                continue;
             }
-            __syncwarp();
-            // value of ring frame t (row r) under this window's floor, coefficient = lane
-            auto ring_value = [&](int t, int r) -> float {
-                if (cls == 0 || !(G[r * ROW + N_MFCC] < floor_db)) return lane < N_MFCC ? G[r * ROW + lane] : 0.f;
-                if (cls == 1) return lane < N_MFCC ? G2[r * N_MFCC + lane] : 0.f;
-                float2 x[8];
-                load_frame_pairs_at<PRE>(rd, t * HOP - N_FFT / 2, lane, x);
-                float mn, mx;
-                __syncwarp();
-                warp_frame_mfcc(x, *ft, scr, lane, floor_db, patch + 4 * N_MFCC, mn, mx);
-                __syncwarp();
-                return lane < N_MFCC ? patch[4 * N_MFCC + lane] : 0.f;
-            };
-            auto edge_value = [&](int e) -> float {
-                if (lane >= N_MFCC) return 0.f;
-                return ((emask >> e) & 1u) ? patch[e * N_MFCC + lane] : ekh[e * ROW + lane];
-            };
-            // pooled statistics, fixed order: left edges, loose rows, aligned blocks, loose rows, right edges.
-            // Ring frames t = 2 .. t_hi are grid frames jl + t; t0 = first t on a block boundary.
-            float n = 1.f, mean = edge_value(0), M2 = 0.f;
-            pool_item(n, mean, M2, 1.f, edge_value(1), 0.f);
-            const int t0 = min(tp.t_hi + 1, 2 + ((BLK - (((int)(jl & (BLK - 1)) + 2) & (BLK - 1))) & (BLK - 1)));
-            int t = 2, r = j + 2; if (r >= A.DG) r -= A.DG;
-            for (; t < t0; t++) {
-                pool_item(n, mean, M2, 1.f, ring_value(t, r), 0.f);
-                r++; if (r >= A.DG) r -= A.DG;
+            WFL[k * DH + hl] = INFINITY;
+            // scipy cosine of (template mean, window mean) and (template std, window std), serial float32 dot products
+            float uvm = 0.f, uum = 0.f, vvm = 0.f, uvs = 0.f, uus = 0.f, vvs = 0.f;
+            for (int c = 0; c < n_mfcc; c++) {
+                const float2 ms = MS[((size_t)k * N_MFCC + c) * DH + hl];
+                const float tm = tf.dmean[c], ts = tf.dstd[c];
+                uvm = fmaf(tm, ms.x, uvm); uum = fmaf(tm, tm, uum); vvm = fmaf(ms.x, ms.x, vvm);
+                uvs = fmaf(ts, ms.y, uvs); uus = fmaf(ts, ts, uus); vvs = fmaf(ms.y, ms.y, vvs);
             }
-            const float* bs = BS + (size_t)(cls == 1 ? NBLK : 0) * 2 * N_MFCC;
-            int bi = blk_idx_lo + (int)(((jl + t0) >> 3) - b_lo); if (bi >= NBLK) bi -= NBLK;
-            static_assert(BLK == 8, "block index uses >> 3");
-            for (; t + BLK - 1 <= tp.t_hi; t += BLK) {
-                float mu, m2;
-                if (cls < 2) {
-                    const float* src = bs + (size_t)bi * 2 * N_MFCC;
-                    mu = lane < N_MFCC ? src[lane] : 0.f;
-                    m2 = lane < N_MFCC ? src[N_MFCC + lane] : 0.f;
-                    r += BLK; if (r >= A.DG) r -= A.DG;
-                } else {
-                    float v[BLK];
-#pragma unroll
-                    for (int q = 0; q < BLK; q++) { v[q] = ring_value(t + q, r); r++; if (r >= A.DG) r -= A.DG; }
-                    block_mean_m2(v, mu, m2);
-                }
-                pool_item(n, mean, M2, (float)BLK, mu, m2);
-                bi++; if (bi >= NBLK) bi -= NBLK;
-            }
-            for (; t <= tp.t_hi; t++) {
-                pool_item(n, mean, M2, 1.f, ring_value(t, r), 0.f);
-                r++; if (r >= A.DG) r -= A.DG;
-            }
-            for (int e = 2; e < n_edge; e++) pool_item(n, mean, M2, 1.f, edge_value(e), 0.f);
-            const float sd = sqrtf(M2 / (float)tp.F);
-            const int nk = ft->n_mfcc;
-            const float sc = similarity_score_warp(lane < nk ? tf.mean[lane] : 0.f, lane < nk ? tf.std[lane] : 0.f,
-                                                   lane < nk ? mean : 0.f, lane < nk ? sd : 0.f);
-            if (lane == 0) *outp = sc;
+            *outp = score_from_dots(uvm, uum, vvm, uvs, uus, vvs);
         }
         __syncthreads();
+
+        // ================================================================ floored windows (none in the common case)
+        const int n_fl = ctl[3];
+        if (n_fl > 0) {
+            // ---- C: the floor shared by most floored windows of a sub-chunk is that of its newest one (f*): stream-grid
+            // rows it changes are recomputed once into G2 (tagged), only rows not yet tagged with f*
+            const int key = ctl[4];
+            const int fk = NT - 1 - (key >> 8), fhl = key & 255;
+            const float fstar = WFL[fk * DH + fhl];
+            const int fbits = __float_as_int(fstar);
+            {
+                const long long span_lo = max(g_lo, g_valid_lo);
+                const int span = (int)max(0LL, g_hi - span_lo + 1);
+                const int row_lo = span > 0 ? (int)(span_lo % DG) : 0;
+                const int lo_rel = (int)(span_lo - hs);
+                for (int i = warp; i < span; i += nwarps) {
+                    const int r = wrap1(row_lo + i, DG);
+                    if (!(G[r * ROW + R_MIN] < fstar) || g2tag[r] == fbits) continue;      // warp-uniform
+                    int pos = hs_pos + 160 * (lo_rel + i) - N_FFT / 2;
+                    if (pos < 0) pos += P; else if (pos >= P) pos -= P;
+                    dense_frame<PRE>(FR_GRID, ring_s, fmt, P, pos, 0, 0, pre, *ft, scr, lane, fstar, patch, false);
+                    __syncwarp();
+                    if (lane < N_MFCC) __stcg(G2 + r * N_MFCC + lane, patch[lane]);
+                    if (lane == 0) g2tag[r] = fbits;
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            // ---- D: one warp per floored window, lanes = coefficients: every frame under the window's own floor
+            for (int job = warp; job < n_fl; job += nwarps) {
+                const int e_ = FLIST[job], k = e_ / DH, hl = e_ - k * DH;
+                const DenseTmplDev& tp = A.t[k];
+                const TemplateFeat& tf = tmpl[tp.slot];
+                const float f = WFL[k * DH + hl];
+                const int fb = __float_as_int(f);
+                int wpos = hs_pos + 160 * (hl - tp.n);                          // ring position of the window's sample 0
+                if (wpos < 0) wpos += P; else if (wpos >= P) wpos -= P;
+                long long S1 = 0, S2 = 0;
+                auto add = [&](float v) { const int q = quant16(v); S1 += q; S2 += (long long)q * q; };
+                const int sl = wrap1(ctl[16 + k] + hl, DLE);
+                for (int e = 0; e < 2; e++) {
+                    const float* le = (e ? LE1 : LE0) + sl * ROW;
+                    float v;
+                    if (le[R_MIN] < f) {
+                        dense_frame<PRE>(e ? FR_LE1 : FR_LE0, ring_s, fmt, P, wpos, e, tp.L, pre, *ft, scr, lane, f, patch, false);
+                        __syncwarp();
+                        v = lane < N_MFCC ? patch[lane] : 0.f;
+                        __syncwarp();
+                    } else v = lane < N_MFCC ? le[lane] : 0.f;
+                    add(v);
+                }
+                int r = wrap1(ctl[8 + k] + hl + 2, DG);
+                for (int t = 2; t <= tp.t_hi; t++) {
+                    float v;
+                    if (G[r * ROW + R_MIN] < f) {                               // warp-uniform
+                        if (g2tag[r] == fb) v = lane < N_MFCC ? __ldcg(G2 + r * N_MFCC + lane) : 0.f;
+                        else {
+                            int pos = wpos + t * HOP - N_FFT / 2; if (pos >= P) pos -= P;
+                            dense_frame<PRE>(FR_GRID, ring_s, fmt, P, pos, 0, 0, pre, *ft, scr, lane, f, patch, false);
+                            __syncwarp();
+                            v = lane < N_MFCC ? patch[lane] : 0.f;
+                            __syncwarp();
+                        }
+                    } else v = lane < N_MFCC ? G[r * ROW + lane] : 0.f;
+                    add(v);
+                    if (++r == DG) r = 0;
+                }
+                for (int e = 0; e < tp.r; e++) {
+                    const float* re = RE + (tp.re_row0 + e * DH + hl) * ROW;
+                    float v;
+                    if (re[R_MIN] < f) {
+                        dense_frame<PRE>(FR_RE, ring_s, fmt, P, wpos, tp.t_hi + 1 + e, tp.L, pre, *ft, scr, lane, f, patch, false);
+                        __syncwarp();
+                        v = lane < N_MFCC ? patch[lane] : 0.f;
+                        __syncwarp();
+                    } else v = lane < N_MFCC ? re[lane] : 0.f;
+                    add(v);
+                }
+                float mean, sd;
+                dense_stats(S1, S2, tp.inv_f, mean, sd);
+                const bool kept = lane < n_mfcc;
+                const float sc = similarity_score_warp(kept ? tf.dmean[lane] : 0.f, kept ? tf.dstd[lane] : 0.f,
+                                                       kept ? mean : 0.f, kept ? sd : 0.f);
+                if (lane == 0) A.out[((size_t)s * A.n_hops + (size_t)(hs - A.hop0 + hl)) * NT + k] = sc;
+            }
+            __syncthreads();
+        }
     }
     if (A.keep_rows && g_done > 2) {
         // keep the newest rows for the next call
         float* kr = A.keep_rows + (size_t)s * DENSE_KEEP * ROW;
-        const long long lo = max(g_valid_lo, g_done - min(DENSE_KEEP, A.DG));
+        // ... as many as the next call's first window reaches back
+        const long long lo = max(g_valid_lo, g_done - min(min(DENSE_KEEP, DG), A.n_max + 1));
         const int cnt = (int)max(0LL, g_done - lo);
-        for (int i = tid; i < cnt * ROW; i += DENSE_THREADS) {
+        for (int i = tid; i < cnt * ROW; i += nthr) {
             const long long g = lo + i / ROW;
-            kr[(size_t)(g % DENSE_KEEP) * ROW + i % ROW] = G[(size_t)(g % A.DG) * ROW + i % ROW];
+            kr[(size_t)(g % DENSE_KEEP) * ROW + i % ROW] = G[(size_t)(g % DG) * ROW + i % ROW];
         }
         if (tid == 0) { A.keep_end[2 * s] = lo; A.keep_end[2 * s + 1] = g_done; }
     }

@@ -40,6 +40,8 @@ struct TemplateFeat {
     long long n_samples;
     int valid;
     int pad;
+    float dmean[N_MFCC];   // the same features from the dense kernel's exact integer statistics (ewk_dense.cuh), so that a
+    float dstd[N_MFCC];    // dense window that IS the template scores exactly 100.0
 };
 
 struct PcmReader {
@@ -122,6 +124,19 @@ __device__ __forceinline__ float similarity_score_warp(float ref_mean, float ref
     const float sim_mean = one_minus_cosine_warp(ref_mean, mean);
     const float sim_std = one_minus_cosine_warp(ref_std, std);
     const float combined = __fadd_rn(__fmul_rn(sim_mean, 0.7f), __fmul_rn(sim_std, 0.3f));
+    const float p = __fmul_rn(combined, 100.0f);
+    return __fdiv_rn(__fmul_rn(p, sqrtf(p)), 10.0f);
+}
+
+// the same from the six dot products (u = template, v = candidate; mean pair, then std pair)
+__device__ __forceinline__ float score_from_dots(float uvm, float uum, float vvm, float uvs, float uus, float vvs) {
+    const float qm = (float)((double)uvm / sqrt((double)__fmul_rn(uum, vvm)));
+    float dm = __fsub_rn(1.0f, qm);
+    dm = dm < 0.f ? 0.f : (dm > 2.f ? 2.f : dm);
+    const float qs = (float)((double)uvs / sqrt((double)__fmul_rn(uus, vvs)));
+    float ds = __fsub_rn(1.0f, qs);
+    ds = ds < 0.f ? 0.f : (ds > 2.f ? 2.f : ds);
+    const float combined = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, dm), 0.7f), __fmul_rn(__fsub_rn(1.0f, ds), 0.3f));
     const float p = __fmul_rn(combined, 100.0f);
     return __fdiv_rn(__fmul_rn(p, sqrtf(p)), 10.0f);
 }

@@ -128,3 +128,86 @@ def test_dense_sweep_multi_template_two_word_phrase(word):
         nb, _ = O.dense_window(len(t))
         assert np.isnan(got[nb - 1][0, k]) and not np.isnan(got[nb][0, k])
     print(f"dense sweep, 3 templates (0.5 s / 0.97 s / 2.1 s): worst |score - oracle| = {worst:.2e}")
+
+
+def test_dense_config2_64_streams_strided_vs_oracle(word):
+    """BASELINE configs[1] / SURVEY §8(d) config 2: 64 concurrent streams (seeds 1000 + s, sigma = 0.002 background, 1-3
+    insertions per 10 s at arbitrary sample offsets, gain U(1, 4); 4 of them with exact-zero gaps so that the top_db
+    floor path runs), 10 s rolling buffers, every hop scored against 2 templates; every 7th hop of every stream is
+    compared with oracle.dense_scores (= WordMatcher.calculate_similarity on that window)."""
+    from oracle import ewk_oracle as O
+    n, seconds = 64, 10.0
+    short = synth.synthetic_word(seed=9, duration=0.5)
+    tpls = [word, short]
+    xs = []
+    for s in range(n):
+        x, _ = synth.stream(1000 + s, seconds, word, noise_sigma=0.002, gain=(1.0, 4.0), zero_gaps=3 if s % 16 == 5 else 0)
+        xs.append(synth.from_int16(synth.to_int16(x)))
+    q = np.stack([synth.to_int16(x) for x in xs])
+    ctx = make_ctx(n, "i16", tpls)
+    ctx.push(q)
+    sc = ctx.dense_scores(0, 1000, 0, 2)
+    # the same request in streaming form (100 hops per call, the carried rows path) must give the same bits
+    ctx2 = make_ctx(n, "i16", tpls)
+    parts = []
+    for p in range(0, q.shape[1], 16000):
+        ctx2.push(np.ascontiguousarray(q[:, p:p + 16000]))
+        parts.append(ctx2.dense_scores(p // 160 + 1, 100, 0, 2))
+    ctx2.close()
+    stream_form = np.concatenate(parts, axis=1)
+    assert np.array_equal(stream_form[:, :-1], sc[:, 1:], equal_nan=True)
+    hops = np.arange(3, 1000, 7)
+    worst, n_cmp, n_nan = 0.0, 0, 0
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=8) as ex:                      # numpy's FFT / einsum release the GIL
+        refs = list(ex.map(lambda x: O.dense_scores(x, tpls, hops), xs))
+    for s in range(n):
+        ref = refs[s]
+        got = sc[s, hops, :]
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), s
+        ok = ~np.isnan(ref)
+        n_nan += int((~ok).sum())
+        d = np.abs(got[ok].astype(np.float64) - ref[ok])
+        worst = max(worst, float(d.max()))
+        n_cmp += int(ok.sum())
+        assert d.max() <= SCORE_ATOL, (s, float(d.max()))
+    ctx.close()
+    print(f"config 2: {n_cmp} windows of 64 streams x 2 templates within {worst:.2e} of the oracle ({n_nan} before the first window)")
+
+
+def test_dense_five_templates_of_assorted_lengths(word):
+    """More templates than fit the two-CTAs-per-SM geometry (the kernel then runs 32-warp CTAs): 0.04 s-granular lengths
+    from the 640-sample minimum to the 3.0 s cap, scored in two calls; sampled hops against the oracle."""
+    from oracle import ewk_oracle as O
+    rng = np.random.default_rng(5)
+    long3 = np.concatenate([word, np.zeros(1600, np.float32), word[::-1], np.zeros(900, np.float32), 0.5 * word])[:48000].astype(np.float32)
+    tpls = [word, synth.synthetic_word(seed=3, duration=0.04 * 1 + 0.0), synth.sine(440.0, 1.0, 0.3), long3,
+            (rng.standard_normal(7777) * 0.05).astype(np.float32)]
+    tpls[1] = synth.synthetic_word(seed=3, duration=0.5)[:640]        # the shortest supported template
+    xs = []
+    for i in range(2):
+        x, _ = synth.stream(8800 + i, 12.0, word, gain=(1.5, 3.0), inserts_per_10s=(2, 3), zero_gaps=i)
+        xs.append(synth.from_int16(synth.to_int16(x)))
+    q = np.stack([synth.to_int16(x) for x in xs])
+    from easywakeword_b200 import _lib
+    ctx = _lib.Context(device=0, n_streams=2, ring_samples=200000, slack_samples=16000, pcm_format=_lib.PCM_I16, max_templates=8)
+    for i, t in enumerate(tpls):
+        ctx.set_template(i, t)
+    ctx.set_stream_params(-1, frame_size=1600, template_count=len(tpls))
+    ctx.push(q)
+    a = ctx.dense_scores(0, 700, 0, 5)
+    b = ctx.dense_scores(700, 500, 0, 5)
+    sc = np.concatenate([a, b], axis=1)
+    one = ctx.dense_scores(350, 300, 3, 1)                               # a single long template on its own
+    assert np.array_equal(one[:, :, 0], sc[:, 350:650, 3], equal_nan=True)
+    ctx.close()
+    hops = np.sort(rng.choice(np.arange(5, 1200), size=40, replace=False))
+    worst = 0.0
+    for s in range(2):
+        ref = O.dense_scores(xs[s], tpls, hops)
+        got = sc[s, hops, :]
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        worst = max(worst, float(np.abs(got[ok] - ref[ok]).max()))
+        assert np.abs(got[ok] - ref[ok]).max() <= SCORE_ATOL, (s, worst)
+    print(f"5 templates (640 .. 48000 samples): worst |score - oracle| = {worst:.2e}")
