@@ -326,6 +326,199 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------
+# secondary legs of the GPU arm: BASELINE configs[4] (offline multi-template sweep) and configs[3] (65 536 / 8 streams per GPU)
+SWEEP_STREAMS = 1024
+SWEEP_CHUNK_SECONDS = 10
+SWEEP_SECONDS = 600            # per stream, measured; the config's 3600 s are 6 x the same chunks (stated in the leg)
+
+
+def sweep_templates(word):
+    """the bundled word (1-word), a 2-word phrase built as word + 0.15 s gap + time-reversed word,
+    and two pitch-shifted sines under a speech-like envelope."""
+    phrase = np.concatenate([word, np.zeros(2400, np.float32), word[::-1]]).astype(np.float32)
+    out = [word, phrase]
+    for f, dur in ((440.0, 1.0), (440.0 * 2 ** (5 / 12), 0.6)):
+        t = np.arange(int(dur * 16000)) / 16000.0
+        out.append((0.3 * np.sin(2 * np.pi * f * t) * np.sin(np.pi * t / dur) ** 0.5).astype(np.float32))
+    return out, ["bundled word (0.97 s)", "word + 0.15 s + reversed word (2.09 s)", "440 Hz tone (1.0 s)", "587 Hz tone (0.6 s)"]
+
+
+def sweep_leg(torch, dist, dev, stream, local_rank, rank, world, word, hbm_peak, seconds=SWEEP_SECONDS):
+    """configs[4]: 1024 streams per GPU, every hop scored against T = 4 templates (and T = 1), streamed in 10 s chunks:
+    one ewk_push of the chunk (K1) + one ewk_dense_scores over its 1000 hops (K4; the window history of a chunk's first
+    hops is the previous chunk's audio still in the ring: the (L_k + 352)-sample halo of SURVEY §8(d))."""
+    from easywakeword_b200 import _lib, synth
+    from easywakeword_b200.bank import WakeWordBank
+    n, chunk = SWEEP_STREAMS, SWEEP_CHUNK_SECONDS * 16000
+    tpls, names = sweep_templates(word)
+    T = len(tpls)
+    n_pool = 3                                                      # distinct 10 s chunks per stream, cycled
+    pin = _lib.PinnedArray((n_pool, n, chunk), np.int16)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(s_):
+        x, _ = synth.stream(SEED0 + 100000 + rank * n + s_, n_pool * SWEEP_CHUNK_SECONDS, word, noise_sigma=0.002, gain=(1.0, 4.0))
+        pin.array[:, s_, :] = synth.to_int16(x).reshape(n_pool, chunk)
+
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 8)) as ex:
+        list(ex.map(one, range(n)))
+    host = torch.from_numpy(pin.array)
+    pool = host.to(dev)
+    bank = WakeWordBank(n, tpls, device=local_rank, buffer_seconds=SWEEP_CHUNK_SECONDS, pcm_dtype=np.int16, max_push_seconds=3.0,
+                        cuda_stream=stream.cuda_stream, **PARAMS)
+    ctx = bank.ctx
+    ctx.set_stream_params(-1, live=1, **PARAMS)                     # no ticks in this mode: pushes run free of the gate's guard
+    hops = chunk // 160
+    out_dev = torch.empty(n * hops * T, dtype=torch.float32, device=dev)
+    out_pin = _lib.PinnedArray((n, hops, T), np.float32)
+    pushed = [0]
+
+    def chunk_step(where, t_first, t_count, to_host):
+        j = pushed[0] % n_pool
+        src = pool if where == _lib.DEVICE else host
+        hop0 = pushed[0] * hops + 1
+        bank.push((src.data_ptr() + j * n * chunk * 2, n, chunk, chunk), where=where)
+        pushed[0] += 1
+        if to_host:
+            ctx._ck(ctx.lib.ewk_dense_scores(ctx.h, hop0, hops, t_first, t_count, out_pin.ptr, _lib.HOST))
+        else:
+            ctx.dense_scores(hop0, hops, t_first, t_count, out_device_ptr=out_dev.data_ptr())
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def run(where, t_count, to_host, chunks):
+        for _ in range(2):
+            chunk_step(where, 0, t_count, to_host)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(chunks):
+            chunk_step(where, 0, t_count, to_host)
+        e1.record(stream)
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    chunks = max(2, seconds // SWEEP_CHUNK_SECONDS)
+    audio = n * SWEEP_CHUNK_SECONDS * chunks * world
+    ms4 = run(_lib.DEVICE, T, False, chunks)
+    ms1 = run(_lib.DEVICE, 1, False, chunks)
+    ms4_e2e = run(_lib.HOST, T, True, max(2, chunks // 3))
+    audio_e2e = n * SWEEP_CHUNK_SECONDS * max(2, chunks // 3) * world
+    ctx.profile(True)
+    for _ in range(3):
+        chunk_step(_lib.DEVICE, 0, T, False)
+    prof4 = ctx.profile_read()
+    for _ in range(3):
+        chunk_step(_lib.DEVICE, 0, 1, False)
+    prof1 = ctx.profile_read()
+    ctx.profile(False)
+    k4_ms = prof4["dense_score"]["ms"] / max(1, prof4["dense_score"]["launches"])
+    k1_ms = prof1["dense_score"]["ms"] / max(1, prof1["dense_score"]["launches"])
+    pcm_bytes = n * chunk * 2
+    leg = {
+        "what": f"configs[4]: {n} streams per GPU, {seconds} s of audio per stream measured in {SWEEP_CHUNK_SECONDS} s chunks "
+                f"(the config's 3600 s per stream are {3600 // seconds} x the same chunk loop: throughput is per chunk), every 10 ms hop "
+                f"scored against T = {T} templates; per chunk one ewk_push (K1) + one ewk_dense_scores over {hops} hops (K4), "
+                "scores left on the device",
+        "templates": names, "streams_per_gpu": n, "seconds_per_stream": chunks * SWEEP_CHUNK_SECONDS, "chunk_seconds": SWEEP_CHUNK_SECONDS,
+        "value": audio / (ms4 * 1e-3), "unit": UNIT, "ms_per_chunk": ms4 / chunks,
+        "windows_per_s": n * hops * T * chunks * world / (ms4 * 1e-3),
+        "t1": {"value": audio / (ms1 * 1e-3), "unit": UNIT, "ms_per_chunk": ms1 / chunks, "kernel_ms": k1_ms,
+               "windows_per_s": n * hops * chunks * world / (ms1 * 1e-3)},
+        "kernel_ms": k4_ms,
+        "e2e": {"value": audio_e2e / (ms4_e2e * 1e-3), "unit": UNIT, "ms_per_chunk": ms4_e2e / max(2, chunks // 3),
+                "h2d_bytes_per_chunk": pcm_bytes, "d2h_bytes_per_chunk": n * hops * T * 4,
+                "what": "pinned host PCM -> H2D -> K1 -> K4 -> scores copied back into pinned host memory, every chunk"},
+        "algorithmic_bytes_per_chunk": pcm_bytes + n * hops * T * 4,
+        "hbm_frac": (pcm_bytes + n * hops * T * 4) / (k4_ms * 1e-3) / 1e9 / hbm_peak,
+        "geometry": "K4 chooses hops per sub-chunk / threads per CTA / CTAs per SM from shared memory (csrc/ewk_api.cu dense_plan)",
+    }
+    bank.close()
+    pin.free()
+    out_pin.free()
+    return leg
+
+
+def config3_leg(torch, dist, dev, stream, local_rank, rank, world, word, pool_dev, K, W, overlap):
+    """configs[3]: 65 536 streams over 8 GPUs = 8192 streams per GPU (the same per-GPU shard at every N: weak scaling), the
+    gated level-1+2 path, 8-byte result records gathered over NVLink with one NCCL all-gather per step."""
+    from easywakeword_b200 import _lib
+    from easywakeword_b200.bank import WakeWordBank
+    n = 8192
+    n0 = pool_dev.shape[1]
+    reps = -(-n // n0)
+    # streams beyond the pool are the pool's streams shifted by 3, 6, ... seconds (cheap stand-in for more seeds)
+    big = torch.cat([pool_dev.roll(3 * r, dims=0) for r in range(reps)], dim=1)[:, :n, :].contiguous()
+    bank = WakeWordBank(n, [word], device=local_rank, buffer_seconds=RING_SECONDS, pcm_dtype=np.int16,
+                        max_push_seconds=2 * STEP_SECONDS, cuda_stream=stream.cuda_stream, max_events=1 << 18, **PARAMS)
+    ctx = bank.ctx
+    results = torch.zeros(n, 2, dtype=torch.int32, device=dev)
+    ctx.set_results_buffer(results.data_ptr())
+    ctx.set_overlap(overlap)
+    gathered = torch.zeros(world * n, 2, dtype=torch.int32, device=dev) if world > 1 else None
+    pushed = [0]
+
+    def step():
+        j = pushed[0] % POOL_SECONDS
+        pushed[0] += 1
+        bank.push((big.data_ptr() + j * n * STEP_SAMPLES * 2, n, STEP_SAMPLES, STEP_SAMPLES), where=_lib.DEVICE)
+        bank.tick(TICKS_PER_STEP)
+        if gathered is not None:
+            ctx.join()
+            dist.all_gather_into_tensor(gathered, results)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    n_ev = 0
+    for _ in range(RING_SECONDS + W):
+        step()
+        n_ev = len(bank.poll())
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        step()
+    ctx.join()
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ev = bank.poll()
+    ctx.set_overlap(False)
+    ctx.profile(True)
+    for _ in range(K):
+        step()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    bank.poll()
+    leg = {"what": f"configs[3]: {n} streams per GPU x {world} GPU(s) = {n * world} streams (65 536 at 8 GPUs), gated level-1+2 path, "
+                   "PCM resident in HBM, one NCCL all-gather of the 8-byte result records per step" + ("" if world > 1 else " (N > 1 only)"),
+           "streams_per_gpu": n, "streams_total": n * world, "value": n * STEP_SECONDS * world * K / (ms * 1e-3), "unit": UNIT,
+           "ms_per_step": ms / K, "level2_events_per_step": int((ev["kind"] == 2).sum()) / K,
+           "kernel_ms_per_step": {k: v["ms"] / K for k, v in prof.items() if v["launches"]},
+           "rings_gb_per_gpu": n * (RING_SECONDS * 16000 + int(2 * STEP_SECONDS * 16000) + 3200) * 2 / 1e9}
+    bank.close()
+    del big
+    return leg
+
+
+# ----------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -431,47 +624,57 @@ def run_ours(args):
 
     by_rank = []                                                    # per timed() call: every rank's own device time and enqueue time
 
-    def timed(where, read_back, steps):
+    def timed(where, read_back, steps, repeats):
+        """W warm-up steps, then `repeats` blocks of exactly `steps` steps, each bracketed by barrier + synchronize and
+        timed with CUDA events on the launching stream (max over ranks).  Returns the MEDIAN block's ms plus every
+        block's ms, the launches of one block and the level-2 events of the median block."""
         for _ in range(W):
             step(where, True)
-        barrier()
-        l0 = ctx.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_ev = 0
-        e0.record(stream)
-        c0 = time.perf_counter()
-        for _ in range(steps):
-            ev = step(where, read_back)
-            if ev is not None:
-                n_ev += int((ev["kind"] == 2).sum())
-        cpu_issue_ms = (time.perf_counter() - c0) * 1e3             # host time to enqueue the steps (not a result: a diagnostic)
-        ctx.join()                                                  # the last step's K3 belongs to the timed region
-        if exchange is not None:
-            if args.gather == "peer-barrier":
-                exchange.finish(stream)                             # ... and so does its barrier
-            else:
-                exchange.wait(ctx)                                  # ... and so does the arrival of every rank's last step
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        by_rank.append({"ms_per_step": [ms / steps], "host_enqueue_ms_per_step": [cpu_issue_ms / steps]})
-        if world > 1:
-            allr = torch.zeros(world, 2, device=dev)
-            dist.all_gather_into_tensor(allr, torch.tensor([[ms / steps, cpu_issue_ms / steps]], device=dev))
-            by_rank[-1] = {"ms_per_step": [round(float(v), 5) for v in allr[:, 0]],
-                           "host_enqueue_ms_per_step": [round(float(v), 5) for v in allr[:, 1]]}
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, ctx.launch_count() - l0, n_ev
+        blocks = []
+        for _ in range(repeats):
+            barrier()
+            l0 = ctx.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_ev = 0
+            e0.record(stream)
+            c0 = time.perf_counter()
+            for _ in range(steps):
+                ev = step(where, read_back)
+                if ev is not None:
+                    n_ev += int((ev["kind"] == 2).sum())
+            cpu_issue_ms = (time.perf_counter() - c0) * 1e3         # host time to enqueue the steps (not a result: a diagnostic)
+            ctx.join()                                              # the last step's K3 belongs to the timed region
+            if exchange is not None:
+                if args.gather == "peer-barrier":
+                    exchange.finish(stream)                         # ... and so does its barrier
+                else:
+                    exchange.wait(ctx)                              # ... and so does the arrival of every rank's last step
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1)
+            br = {"ms_per_step": [ms / steps], "host_enqueue_ms_per_step": [cpu_issue_ms / steps]}
+            if world > 1:
+                allr = torch.zeros(world, 2, device=dev)
+                dist.all_gather_into_tensor(allr, torch.tensor([[ms / steps, cpu_issue_ms / steps]], device=dev))
+                br = {"ms_per_step": [round(float(v), 5) for v in allr[:, 0]],
+                      "host_enqueue_ms_per_step": [round(float(v), 5) for v in allr[:, 1]]}
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            blocks.append((ms, ctx.launch_count() - l0, n_ev, br))
+        order = sorted(range(repeats), key=lambda i: blocks[i][0])
+        med = blocks[order[repeats // 2]]
+        by_rank.append(med[3])
+        return med[0], med[1], med[2], [b[0] for b in blocks]
 
     audio_per_step_all = n * STEP_SECONDS * world
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_dev, launches, _ = timed(_lib.DEVICE, False, K)          # inputs resident in HBM
+    R = max(1, args.repeats)
+    ms_dev, launches, _, dev_blocks = timed(_lib.DEVICE, False, K, R)      # inputs resident in HBM
     bank.poll()
-    ms_e2e, _, n_events = timed(_lib.HOST, True, K)             # host PCM -> rings -> events on host
+    ms_e2e, _, n_events, e2e_blocks = timed(_lib.HOST, True, K, R)         # host PCM -> rings -> events on host
 
     # the same end-to-end step fed with G.711 mu-law codes (ewk_push_g711: 1 byte per sample over PCIe, expanded on the
     # device).  A secondary figure: the audio is the pool after companding, so its events differ from the PCM16 run.
@@ -625,17 +828,27 @@ def run_ours(args):
     prof_dense = ctx.profile_read()
     ctx.profile(False)
 
+    pk = os.path.join(REPO, "MEASURED_PEAKS.json")
+    peaks = json.load(open(pk)) if os.path.exists(pk) else {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    sweep = config3 = None
+    if not args.no_extra and not f32:
+        torch.cuda.synchronize(dev)
+        try:
+            sweep = sweep_leg(torch, dist, dev, stream, local_rank, rank, world, word, hbm_peak)
+        except Exception as e:                                      # a secondary leg never takes the headline down with it
+            sweep = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        if n != 8192:
+            try:
+                config3 = config3_leg(torch, dist, dev, stream, local_rank, rank, world, word, pool_dev, K, W, overlap)
+            except Exception as e:
+                config3 = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     clocks = sampler.finish() if sampler else None
     audio_per_step = n * STEP_SECONDS * world
     value = audio_per_step * K / (ms_dev * 1e-3)
     e2e_val = audio_per_step * K / (ms_e2e * 1e-3)
 
     if rank == 0:
-        peaks = {}
-        pk = os.path.join(REPO, "MEASURED_PEAKS.json")
-        if os.path.exists(pk):
-            peaks = json.load(open(pk))
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
         kern = {k: v for k, v in prof.items() if v["launches"]}
         tot_ms = sum(v["ms"] for v in kern.values()) or 1.0
@@ -715,6 +928,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
+            "repeats": {"blocks": R, "steps_per_block": K, "reported": "median block",
+                        "ms_per_step_blocks": [round(b / K, 5) for b in dev_blocks],
+                        "e2e_ms_per_step_blocks": [round(b / K, 5) for b in e2e_blocks]},
             "config": bench_config(n, pcm_name, world, word_name),
             "execution": {"overlap": ("K3 of step i runs on a second stream beside K1 of step i+1 (ewk_set_overlap; K1 in its "
                                       "cp.async.bulk form); the timed region ends after the last K3 (ewk_join); per-kernel "
@@ -747,6 +963,8 @@ def run_ours(args):
                       "windows_per_s": n * 100 * world * dense_steps / (ms_dense * 1e-3),
                       "hbm_frac": (n * STEP_SAMPLES * esz + n * 400) * dense_steps / (ms_dense * 1e-3) / 1e9 / hbm_peak,
                       "cpu_baseline": dense_cpu},
+            "sweep": sweep,
+            "config3": config3,
             "level2_events_per_step": ev_per_step,
             "kernel_ms_per_step": {k: v["ms"] / max(1, K) for k, v in kern.items()},
             "kernel_ms_per_step_without_publication": ({k: v["ms"] / max(1, K) for k, v in prof_nopub.items() if v["launches"]}
@@ -764,6 +982,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--repeats", type=int, default=5,
+                    help="timed blocks of exactly --steps steps; the line reports the median block (all blocks listed)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary legs (sweep = configs[4], config3, dense)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--streams", type=int, default=N_STREAMS,
