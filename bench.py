@@ -277,7 +277,7 @@ def run_reference(args):
     K, W = max(1, args.steps), args.warmup
     kind = cpu_kind()
     mode = "reference" if kind == "reference" else "port"
-    sample_s = 4.0
+    sample_s = 16.0
     word, word_name = load_word()
     pool = CpuPool(cores)
     t0 = time.perf_counter()
@@ -977,6 +977,39 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_only(args):
+    """`--only sweep|config3`: one secondary leg on its own (profiling, quick checks); prints {"<leg>": {...}}."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    word, _ = load_word()
+    pk = os.path.join(REPO, "MEASURED_PEAKS.json")
+    hbm_peak = float(json.load(open(pk)).get("hbm_gbs", 6650.0)) if os.path.exists(pk) else 6650.0
+    if args.only == "sweep":
+        leg = sweep_leg(torch, dist, dev, stream, local_rank, rank, world, word, hbm_peak, seconds=args.sweep_seconds)
+    else:
+        pool_pin = np.empty((POOL_SECONDS, N_STREAMS, STEP_SAMPLES), np.int16)
+        make_pool(rank * N_STREAMS, N_STREAMS, word, pool_pin)
+        pool_dev = torch.from_numpy(pool_pin).to(dev)
+        leg = config3_leg(torch, dist, dev, stream, local_rank, rank, world, word, pool_dev, args.steps, max(3, args.warmup),
+                          not args.no_overlap)
+    if rank == 0:
+        print(json.dumps({args.only: leg, "n_gpus": world}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -1000,9 +1033,14 @@ def main():
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU: do not pin each rank to the CPUs next to its GPU")
     ap.add_argument("--no-overlap", action="store_true",
                     help="keep K3 on the context's stream (default: ewk_set_overlap(1), K3 beside the next push)")
+    ap.add_argument("--only", default="all", choices=["all", "sweep", "config3"],
+                    help="run one secondary leg on its own instead of the whole line")
+    ap.add_argument("--sweep-seconds", type=int, default=SWEEP_SECONDS, help="audio seconds per stream the sweep leg measures")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.only != "all":
+        run_only(args)
     else:
         run_ours(args)
 

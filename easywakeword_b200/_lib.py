@@ -541,7 +541,7 @@ def _bank_methods():
         ms = (C.c_double * 8)()
         n = (C.c_int64 * 8)()
         self._ck(self.lib.ewk_profile_read(self.h, ms, n))
-        names = ["ring_push", "tick_gate", "segment_queue", "segment_batch", "dense_score", "segment_prepare"]
+        names = ["ring_push", "tick_gate", "segment_queue", "segment_batch", "dense_score", "segment_prepare", "publish"]
         return {names[i]: {"ms": ms[i], "launches": int(n[i])} for i in range(len(names))}
 
     for f in (prepare_segments, dense_scores, profile, profile_read, set_stream_params, push, push_g711, tick, poll, status, read_last, read_segment, results, results_device_ptr,

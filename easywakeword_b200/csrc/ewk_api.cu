@@ -126,6 +126,7 @@ extern "C" int ewk_synchronize(ewk_ctx* ctx) {
     int jr = ctx->join_match();
     if (jr) return jr;
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->pub_stream) CK(cudaStreamSynchronize(ctx->pub_stream));
     return EWK_OK;
 }
 
@@ -182,6 +183,10 @@ void ewk_ctx::release() {
     rs_tables.clear();
     b_rs_in.free(); b_rs_out.free();
     if (d_wait_flag) { cudaFree(d_wait_flag); d_wait_flag = nullptr; }
+    if (pub_stream) { cudaStreamSynchronize(pub_stream); cudaStreamDestroy(pub_stream); pub_stream = nullptr; }
+    if (ev_k3) { cudaEventDestroy(ev_k3); ev_k3 = nullptr; }
+    for (int i = 0; i < 2; i++) if (ev_pub[i]) { cudaEventDestroy(ev_pub[i]); ev_pub[i] = nullptr; }
+    if (d_pub_snap) { cudaFree(d_pub_snap); d_pub_snap = nullptr; }
     if (d_tables) cudaFree(d_tables);
     if (d_tmpl) cudaFree(d_tmpl);
     if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
@@ -945,6 +950,8 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         ks = ctx->match_stream;
     }
     ctx->last_match_stream = ks;
+    if (B.n_pub > 0 && ctx->ev_pub_valid[B.pub_parity])
+        CK(cudaStreamWaitEvent(ks, ctx->ev_pub[B.pub_parity], 0));       // this parity's snapshot was sent two calls ago: long done
     pe = ctx->prof_begin(2, ks);
     auto k3q = ctx->cfg.preemphasis != 0.f ? segment_queue_kernel<true> : segment_queue_kernel<false>;
     k3q<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ks>>>(ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
@@ -955,6 +962,18 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         ctx->match_inflight = true;
     }
     ctx->launches += 1;
+    if (B.n_pub > 0) {
+        // the sender: off everybody's critical path on its own stream, behind K3's snapshot of the records
+        CK(cudaEventRecord(ctx->ev_k3, ks));
+        CK(cudaStreamWaitEvent(ctx->pub_stream, ctx->ev_k3, 0));
+        cudaEvent_t pp = ctx->prof_begin(6, ctx->pub_stream);
+        publish_records_kernel<<<B.n_pub, 256, 0, ctx->pub_stream>>>(B);
+        ctx->prof_end(pp, 6, ctx->pub_stream);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev_pub[B.pub_parity], ctx->pub_stream));
+        ctx->ev_pub_valid[B.pub_parity] = true;
+        ctx->launches += 1;
+    }
     ctx->pushes_since_tick = 0;
     // host mirrors (audio clock): V after these ticks, given what has been pushed
     for (int s = 0; s < B.n_streams; s++) {
@@ -1317,8 +1336,16 @@ extern "C" int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bas
     B.pub_slot = n_bases && signals ? slot : 0;
     B.pub_seq = 0;
     B.pub_parity = 0;
-    { const char* e = getenv("EWK_PUB_CTA_FENCE"); B.pub_cta_fence_gpu = (e && !strcmp(e, "gpu")) ? 1 : 0; }
     ctx->publish_seq = 0;
+    if (ctx->pub_stream) CK(cudaStreamSynchronize(ctx->pub_stream));
+    ctx->ev_pub_valid[0] = ctx->ev_pub_valid[1] = false;
+    if (n_bases && !ctx->pub_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->pub_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_k3, cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&ctx->ev_pub[i], cudaEventDisableTiming));
+        CK(cudaMalloc(&ctx->d_pub_snap, sizeof(StreamResult) * 2 * (size_t)B.n_streams));
+    }
+    B.pub_snap = (StreamResult*)ctx->d_pub_snap;
     if (n_bases && signals && !ctx->d_wait_flag) {
         CK(cudaMalloc(&ctx->d_wait_flag, sizeof(int)));
         CK(cudaMemsetAsync(ctx->d_wait_flag, 0, sizeof(int), ctx->stream));
@@ -1337,6 +1364,8 @@ extern "C" int ewk_wait_published(ewk_ctx* ctx, int n_slots, int64_t seq, int ti
     if (!B.n_pub || !B.pub_sig[0]) { ctx->fail("ewk_wait_published: no signal rows installed (ewk_set_results_peers)"); return EWK_ERR_STATE; }
     if (n_slots < 1 || n_slots > B.n_pub || seq < 1 || timeout_ms < 1) { ctx->fail("ewk_wait_published: bad arguments"); return EWK_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
+    // this rank's own sender (side stream, same GPU) first: the wait kernel then only spins on other GPUs' signals
+    if (ctx->ev_pub_valid[(seq - 1) & 1]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_pub[(seq - 1) & 1], 0));
     const unsigned long long* row = B.pub_sig[B.pub_slot] + (size_t)((seq - 1) & 1) * MAX_PUB;
     peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(row, n_slots, (unsigned long long)seq, (unsigned long long)timeout_ms * 1000000ULL,
                                                 ctx->d_wait_flag);
@@ -1363,6 +1392,7 @@ extern "C" int ewk_published_seq(ewk_ctx* ctx, int parity, uint64_t* out, int n_
 
 extern "C" int ewk_match_stream(ewk_ctx* ctx, void** out) {
     if (!ctx || !out) return EWK_ERR_ARG;
+    if (ctx->bank.n_pub > 0 && ctx->pub_stream) { *out = (void*)ctx->pub_stream; return EWK_OK; }   // where the call's records are sent
     *out = (void*)(ctx->last_match_stream ? ctx->last_match_stream : ctx->stream);
     return EWK_OK;
 }
@@ -1403,6 +1433,7 @@ int ewk_ctx::prof_collect() {
     int jr = join_match();
     if (jr) return jr;
     CK(cudaStreamSynchronize(stream));
+    if (pub_stream) CK(cudaStreamSynchronize(pub_stream));
     for (auto& p : prof_pairs) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { prof_ms[p.cls] += ms; prof_n[p.cls]++; }

@@ -482,10 +482,30 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                     } else v = lane < N_MFCC ? le[lane] : 0.f;
                     add(v);
                 }
-                int r = wrap1(ctl[8 + k] + hl + 2, DG);
-                for (int t = 2; t <= tp.t_hi; t++) {
-                    float v;
-                    if (G[r * ROW + R_MIN] < f) {                               // warp-uniform
+                // stream-grid frames t = 2 .. t_hi: their un-floored sums in a tight loop (lane = coefficient; lanes >= 20
+                // carry don't-care values), then the floored rows — found 32 at a time with lanes = rows — replace their
+                // un-floored contribution by the floored one
+                const int r0 = wrap1(ctl[8 + k] + hl + 2, DG);
+                {
+                    const int cl = lane < N_MFCC ? lane : 0;
+                    int r = r0;
+                    for (int t = 2; t <= tp.t_hi; t++) {
+                        const int q = quant16(G[r * ROW + cl]);
+                        S1 += q; S2 += (long long)q * q;
+                        if (++r == DG) r = 0;
+                    }
+                }
+                for (int t0 = 2; t0 <= tp.t_hi; t0 += 32) {
+                    int rl = r0 + (t0 - 2) + lane;
+                    while (rl >= DG) rl -= DG;
+                    unsigned m = __ballot_sync(FULL, t0 + lane <= tp.t_hi && G[rl * ROW + R_MIN] < f);
+                    while (m) {
+                        const int b_ = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int t = t0 + b_;
+                        int r = r0 + (t - 2);
+                        while (r >= DG) r -= DG;
+                        float v;
                         if (g2tag[r] == fb) v = lane < N_MFCC ? __ldcg(G2 + r * N_MFCC + lane) : 0.f;
                         else {
                             int pos = wpos + t * HOP - N_FFT / 2; if (pos >= P) pos -= P;
@@ -494,9 +514,10 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                             v = lane < N_MFCC ? patch[lane] : 0.f;
                             __syncwarp();
                         }
-                    } else v = lane < N_MFCC ? G[r * ROW + lane] : 0.f;
-                    add(v);
-                    if (++r == DG) r = 0;
+                        const int qf = quant16(v), qu = quant16(G[r * ROW + (lane < N_MFCC ? lane : 0)]);
+                        S1 += qf - qu;
+                        S2 += (long long)qf * qf - (long long)qu * qu;
+                    }
                 }
                 for (int e = 0; e < tp.r; e++) {
                     const float* re = RE + (tp.re_row0 + e * DH + hl) * ROW;

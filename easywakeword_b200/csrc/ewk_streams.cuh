@@ -90,31 +90,38 @@ struct BankView {
     double* block_ss;       // [n_streams][NB]: sum of squares of absolute block b = a / 1600 at b % NB (written by K1)
     float* lm_ws;           // K3 log-mel workspace: [segment_queue CTAs][SEG_SMEM_FRAMES][LM_ROW]
     int n_streams, R, P, fmt, chunk_cap, max_events, NB;
-    // peer publication (ewk_set_results_peers): every record K2 / K3 write into `results` is also stored at
-    // pub[p] + pub_parity * pub_stride + pub_off + stream for each destination p — local or NVLink peer-mapped memory,
-    // so the multi-GPU "gather" is done by the producing kernels themselves.
+    // peer publication (ewk_set_results_peers): when the last K3 CTA of a tick call has seen every other CTA arrive, it
+    // snapshots `results` into pub_snap[pub_parity] (local); a small kernel on a side stream then copies the snapshot to
+    // pub[p] + pub_parity * pub_stride + pub_off for each destination p — local or NVLink peer-mapped memory — and
+    // releases the call's sequence number into every destination's signal row: a put-with-signal that is on nobody's
+    // critical path (the next push and gate depend on neither the copy nor the signal).
     StreamResult* pub[MAX_PUB];
     int n_pub, pub_parity;
     long long pub_stride, pub_off;
-    // completion signals (optional): when the last K3 CTA of a tick call is done it stores the call's sequence number
-    // at pub_sig[p][pub_parity * MAX_PUB + pub_slot] of every destination — a put-with-signal: a consumer that sees
-    // sequence q in slot r of its own copy holds all records of rank r up to call q
-    unsigned long long* pub_sig[MAX_PUB];
+    unsigned long long* pub_sig[MAX_PUB];   // per destination: uint64 [2][MAX_PUB] signal rows (optional)
     unsigned long long pub_seq;
     int pub_slot;
-    int pub_cta_fence_gpu;  // diagnostics (EWK_PUB_CTA_FENCE=gpu): per-CTA fence at device scope, only the signalling CTA at system scope
+    int pad_pub;
+    StreamResult* pub_snap;                 // [2][n_streams] local snapshots, one per parity
 };
 
-// One 8-byte store per destination.  Plain (weak) stores on purpose: remote destinations travel over NVLink as posted
-// writes that pipeline behind each other — `volatile` stores are kept in order, each waiting ~1.5 us for the previous
-// one's acknowledgement, which cost K3 12-22 us per launch at 2-8 GPUs while the CTA waited for its thread 0.  What orders
-// them before the completion signal is the system-scope fence at the end of the CTA (segment_queue_kernel); kernel
-// completion does the same for K2.
-__device__ __forceinline__ void publish_result(const BankView& B, int s, StreamResult r) {
-    const size_t at = (size_t)B.pub_parity * (size_t)B.pub_stride + (size_t)B.pub_off + (size_t)s;
-    const unsigned long long bits = ((unsigned long long)r.flags << 32) | (unsigned long long)__float_as_uint(r.score);
-    for (int p = 0; p < B.n_pub; p++)
-        asm volatile("st.weak.global.b64 [%0], %1;" :: "l"(B.pub[p] + at), "l"(bits) : "memory");
+// Peer publication, the sending side: CTA p copies the call's snapshot of this rank's records into destination p with
+// plain (weak) 8-byte stores — remote destinations travel over NVLink as posted writes that pipeline behind each other —
+// then every thread orders its stores at system scope and thread 0 releases the call's sequence number into slot
+// `pub_slot` of the destination's signal row: whoever reads that number (ld.acquire.sys) holds all records of the call.
+__global__ void __launch_bounds__(256)
+publish_records_kernel(BankView B) {
+    const int p = blockIdx.x;
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(B.pub_snap + (size_t)B.pub_parity * B.n_streams);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(B.pub[p] + (size_t)B.pub_parity * (size_t)B.pub_stride + (size_t)B.pub_off);
+    for (int i = threadIdx.x; i < B.n_streams; i += blockDim.x)
+        asm volatile("st.weak.global.b64 [%0], %1;" :: "l"(dst + i), "l"(__ldcg(src + i)) : "memory");
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && B.pub_sig[p]) {
+        unsigned long long* sg = B.pub_sig[p] + (size_t)B.pub_parity * MAX_PUB + B.pub_slot;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(sg), "l"(B.pub_seq) : "memory");
+    }
 }
 
 // the record as ONE 8-byte store (readers — peers, an all-gather, the host — never see half of it)
@@ -915,7 +922,6 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
         r.flags = (r.flags & 1u) | (st.last_silent ? 2u : 0u) | ((unsigned)st.state << 2) | evflag |
                   ((unsigned)st.n_events << 8);
         store_result(B.results + s, r);
-        publish_result(B, s, r);
     }
 }
 
@@ -1027,27 +1033,27 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
                 res.score = best;
                 res.flags = (res.flags & ~1u) | (unsigned)ok;
                 store_result(B.results + e.stream, res);
-                publish_result(B, e.stream, res);
             }
         }
         r = next_s;
         __syncthreads();
     }
+    __shared__ int last_s;
     if (tid == 0) {
-        if (B.n_pub && !B.pub_cta_fence_gpu) __threadfence_system(); else __threadfence();   // this CTA's (peer) record stores before its arrival
-        if (atomicAdd(B.ev_count + 4, 1) == (int)gridDim.x - 1) {       // every other CTA has read the counters
-            B.ev_count[3] = n;
-            B.ev_count[2] = 0;
-            B.ev_count[4] = 0;
-            if (B.n_pub && B.pub_sig[0]) {
-                // every CTA's records precede its arrival, every arrival precedes this point; K2's records were complete
-                // when this kernel started.  Release the call's sequence number to every destination.
-                __threadfence_system();
-                for (int p = 0; p < B.n_pub; p++) {
-                    unsigned long long* sg = B.pub_sig[p] + (size_t)B.pub_parity * MAX_PUB + B.pub_slot;
-                    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(sg), "l"(B.pub_seq) : "memory");
-                }
-            }
+        __threadfence();                                                 // this CTA's records before its arrival
+        last_s = atomicAdd(B.ev_count + 4, 1) == (int)gridDim.x - 1;     // every other CTA has read the counters
+        if (last_s) { B.ev_count[3] = n; B.ev_count[2] = 0; B.ev_count[4] = 0; }
+    }
+    if (B.n_pub) {                                                       // uniform over the launch
+        __syncthreads();
+        if (last_s) {
+            // every CTA's records precede its arrival, every arrival precedes this point; K2's records were complete when
+            // this kernel started: snapshot them for the sender (publish_records_kernel), so that the next gate may
+            // rewrite `results` while the snapshot is still travelling
+            __threadfence();
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(B.results);
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(B.pub_snap + (size_t)B.pub_parity * B.n_streams);
+            for (int i = tid; i < B.n_streams; i += blockDim.x) dst[i] = __ldcg(src + i);
         }
     }
 }

@@ -247,20 +247,21 @@ int ewk_stream_results(ewk_ctx* ctx, ewk_stream_result* out);
  * caller-owned device buffer instead (e.g. a registered NCCL send buffer). */
 int ewk_results_device_ptr(ewk_ctx* ctx, void** out);
 int ewk_set_results_buffer(ewk_ctx* ctx, void* device_ptr);
-/* Peer publication — the multi-GPU "gather" done by the producing kernels (the reference's multiroom
- * shape, examples/multiroom_async.py:14-35, has no exchange at all: N objects report to one host thread).
+/* Peer publication — the multi-GPU "gather" without a collective (the reference's multiroom shape,
+ * examples/multiroom_async.py:14-35, has no exchange at all: N objects report to one host thread).
  * bases[p], p < n_bases <= 16, are device pointers — local, or peer-mapped over NVLink (CUDA IPC / VMM /
- * torch symmetric memory) — to arrays of 2 * stride_records ewk_stream_result.  After this call every record that
- * K2 / K3 write into the results array is also stored, by the same kernel, at
+ * torch symmetric memory) — to arrays of 2 * stride_records ewk_stream_result.  After this call every ewk_tick ends
+ * with the last K3 CTA snapshotting the per-stream records, and a small sender kernel on a side stream of the context
+ * (nothing of the next push / gate waits for it) storing the snapshot at
  *     bases[p][parity * stride_records + offset_records + stream]      for every p,
  * where the k-th ewk_tick call after this one (k = 1, 2, ...; ewk_publish_seq returns the latest k) uses
  * parity = (k - 1) & 1 (ewk_publish_parity), so a consumer reads a complete, stable copy of call k while call k + 1
  * is being produced.
- * signals (optional, may be NULL): signals[p] points to uint64_t[2][16] at destination p.  When K3 of call k has
- * finished, its last CTA stores k at signals[p][parity][slot] for every p with release semantics at system scope
+ * signals (optional, may be NULL): signals[p] points to uint64_t[2][16] at destination p.  Behind its stores to
+ * destination p the sender stores k at signals[p][parity][slot] with release semantics at system scope
  * (a put-with-signal): whoever reads k in slot r of its own copy holds every record rank r published up to call k.
  * bases[slot] / signals[slot] must be this context's own copy (ewk_wait_published / ewk_published_seq read it).
- * Without signals the records are globally visible once the kernels of the call have completed on ewk_match_stream()
+ * Without signals the records are globally visible once the sender of the call has completed on ewk_match_stream()
  * and a cross-GPU barrier enqueued there does the job.  n_bases = 0 switches publication off. */
 int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bases, int64_t stride_records, int64_t offset_records,
                           void* const* signals, int slot);
@@ -273,7 +274,8 @@ int ewk_wait_published(ewk_ctx* ctx, int n_slots, int64_t seq, int timeout_ms);
 /* Synchronous read of the local signal row of `parity`: out[0 .. n_slots).  Returns 1 if an earlier
  * ewk_wait_published timed out since the last call of this function, else 0 (negative: error). */
 int ewk_published_seq(ewk_ctx* ctx, int parity, uint64_t* out, int n_slots);
-/* The cudaStream_t the latest ewk_tick launched K3 on: the match stream in overlap mode, else the context's stream. */
+/* The cudaStream_t on which the latest ewk_tick's results become complete: the sender's stream while peer publication is
+ * on, else the stream K3 was launched on (the match stream in overlap mode, else the context's stream). */
 int ewk_match_stream(ewk_ctx* ctx, void** out);
 /* Pinned host memory for asynchronous pushes. */
 int ewk_host_alloc(void** out, int64_t bytes);
@@ -282,7 +284,7 @@ int ewk_host_free(void* p);
 int64_t ewk_launch_count(const ewk_ctx* ctx);
 /* Per-kernel device timing with CUDA events on the context's stream.  ewk_profile(ctx, 1) starts
  * bracketing every kernel launch with an event pair; ewk_profile_read synchronises and returns, per
- * kernel class (0 ring_push, 1 tick_gate, 2 segment_queue, 3 segment_batch, 4 dense_score), the summed
+ * kernel class (0 ring_push, 1 tick_gate, 2 segment_queue, 3 segment_batch, 4 dense_score, 5 segment_prepare, 6 publish), the summed
  * milliseconds and the number of launches since profiling was enabled, then resets the sums. */
 enum { EWK_PROF_CLASSES = 8 };
 int ewk_profile(ewk_ctx* ctx, int enable);
