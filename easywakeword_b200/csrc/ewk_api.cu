@@ -1157,10 +1157,10 @@ extern "C" int ewk_prepare_segments(ewk_ctx* ctx, int n_seg, const int32_t* stre
 // Launch geometry of K4 for a template set: hops per sub-chunk, threads per CTA and CTAs per SM that fit shared memory.
 struct DensePlan { int DH, threads, per_sm; size_t smem; };
 
-static bool dense_plan(const DenseArgs& A0, int n_min, int n_max, int re_per_hop, DensePlan& out) {
+static bool dense_plan(const DenseArgs& A0, int n_min, int n_max, int n_re_u, DensePlan& out) {
     const size_t SM_TOTAL = 233472, CTA_MAX = 232448, RESERVED = 1024;     // sm_100: 228 KB per SM, 227 KB per CTA
     auto bytes = [&](int DH, int threads) {
-        return dense_smem_bytes(threads / 32, A0.T, DH, DH + n_max + 2, DH + n_max - n_min, DH * re_per_hop);
+        return dense_smem_bytes(threads / 32, A0.T, DH, DH + n_max + 2, DH + n_max - n_min, n_re_u);
     };
     for (int DH : {64, 32})
         for (int threads : {512, 448}) {
@@ -1191,7 +1191,7 @@ extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl
     }
     DenseArgs A{};
     A.hop0 = hop0; A.n_hops = n_hops; A.T = tmpl_count;
-    int max_n = 0, min_n = 1 << 30, g_back = 1 << 30, re_per_hop = 0;
+    int max_n = 0, min_n = 1 << 30, g_back = 1 << 30, n_re_u = 0;
     for (int k = 0; k < tmpl_count; k++) {
         const TemplateFeat& tf = ctx->h_tmpl[tmpl_first + k];
         if (!tf.valid) { ctx->fail("No reference word set. Call set_reference() first."); return EWK_ERR_NO_TEMPLATE; }
@@ -1207,17 +1207,28 @@ extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl
         t.inv_f = 1.0 / (double)t.F;
         max_n = std::max(max_n, t.n); min_n = std::min(min_n, t.n);
         g_back = std::min(g_back, t.n - t.t_hi);
-        re_per_hop += t.r;
+        // right-edge frame e: stream-grid frame (hop - goff) cut at sample 160 hop - delta.  Templates with the same
+        // (goff, delta) share it; the group is computed through the window of its shortest member
+        const int delta = HOP * t.n - L;
+        for (int e = 0; e < t.r; e++) {
+            const int goff = t.n - (t.t_hi + 1 + e);
+            int u = 0;
+            while (u < n_re_u && !(A.re_goff[u] == goff && A.re_delta[u] == delta)) u++;
+            if (u == n_re_u) {
+                A.re_goff[u] = goff; A.re_delta[u] = delta; A.re_rep[u] = k; A.re_rep_e[u] = e; A.re_nfirst[u] = t.n;
+                n_re_u++;
+            } else if (t.n < A.re_nfirst[u]) { A.re_rep[u] = k; A.re_rep_e[u] = e; A.re_nfirst[u] = t.n; }
+            t.re_u[e] = u;
+        }
     }
     DensePlan plan;
-    if (!dense_plan(A, min_n, max_n, re_per_hop, plan)) {
+    if (!dense_plan(A, min_n, max_n, n_re_u, plan)) {
         ctx->fail("ewk_dense_scores: this template set does not fit shared memory (%d templates, windows of %d..%d hops)",
                   tmpl_count, min_n, max_n);
         return EWK_ERR_ARG;
     }
-    A.DH = plan.DH; A.DG = plan.DH + max_n + 2; A.DLE = plan.DH + max_n - min_n; A.n_re_rows = plan.DH * re_per_hop;
-    A.n_min = min_n; A.n_max = max_n; A.g_back = g_back; A.re_per_hop = re_per_hop;
-    for (int k = 0, row = 0; k < tmpl_count; k++) { A.t[k].re_row0 = row; row += A.t[k].r * plan.DH; }
+    A.DH = plan.DH; A.DG = plan.DH + max_n + 2; A.DLE = plan.DH + max_n - min_n; A.n_re_u = n_re_u;
+    A.n_min = min_n; A.n_max = max_n; A.g_back = g_back;
     if ((long long)B.P < 160LL * (max_n + plan.DH + 4) + N_FFT) {        // the kernel wraps ring positions once
         ctx->fail("ewk_dense_scores: ring of %d samples is too short for a template of %d hops", B.P, max_n);
         return EWK_ERR_ARG;
@@ -1246,7 +1257,7 @@ extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl
         CK(ctx->b_keep_end.ensure(sizeof(long long) * 2 * (size_t)B.n_streams));
         CK(cudaMemsetAsync(ctx->b_keep_end.p, 0, sizeof(long long) * 2 * (size_t)B.n_streams, ctx->stream));
     }
-    CK(ctx->b_g2.ensure(sizeof(float) * (size_t)B.n_streams * A.DG * N_MFCC));
+    CK(ctx->b_g2.ensure(sizeof(float) * (size_t)B.n_streams * DENSE_WAYS * A.DG * N_MFCC));
     A.keep_rows = (float*)ctx->b_keep_rows.p;
     A.keep_end = (long long*)ctx->b_keep_end.p;
     A.g2 = (float*)ctx->b_g2.p;
