@@ -60,12 +60,13 @@ constexpr int ROW = N_MFCC + 3;        // mfcc[20], log-mel min, log-mel max, pa
 constexpr int R_MIN = N_MFCC, R_MAX = N_MFCC + 1;
 constexpr int DENSE_KEEP = 304;        // stream-grid rows carried from one call to the next (>= frames of the longest window)
 constexpr int B0_PARTS = 4;            // the frame range of a window is scanned for its max / min in this many tasks
-constexpr int DENSE_WAYS = 4;          // floor values with a cached copy of the rows they change
+constexpr int DENSE_WAYS = 8;          // floor values with a cached copy of the rows they change
 constexpr int TAG_NONE = 0x7fc00001;   // matches no floor
 // control words: [0] phase-A tasks [1] phase-B tasks [2] phase-S tasks [3] frame-by-frame windows [4] phase-D tasks [5] way windows
-// [6] phase-E tasks; [8 + k] ring row of grid frame hs - n_k; [16 + k] LE slot of start hs - n_k; [24 + w] floor bits of way w;
-// [28 + w] way used in this sub-chunk; [32 + 2 k + half] ways used by the windows of (template, half)
-constexpr int DENSE_CTL = 48;
+// [6] phase-E tasks [7] (template, half, way) combinations with way windows; [8 + k] ring row of grid frame hs - n_k;
+// [16 + k] LE slot of start hs - n_k; [24 + w] floor bits of way w; [32 + w] way used in this sub-chunk;
+// [40 + 2 k + half] ways used by the windows of (template, half); [56 ...] the combinations: (k * 2 + half) * DENSE_WAYS + w
+constexpr int DENSE_CTL = 56 + 2 * DENSE_MAX_T * DENSE_WAYS;
 
 struct DenseTmplDev {
     int L, n, F, t_hi, r, slot;        // r = F - 1 - t_hi right-edge frames
@@ -103,8 +104,8 @@ __host__ __device__ inline size_t dense_smem_bytes(int nwarps, int T, int DH, in
 }
 
 // ---- exact integer statistics -------------------------------------------------------------------------------
-__device__ __forceinline__ int quant16(float x) {           // rint(x * 2^16), |x| clamped below 2^11 (any real MFCC is)
-    return __float2int_rn(fminf(fmaxf(x, -2047.f), 2047.f) * 65536.0f);
+__device__ __forceinline__ int quant16(float x) {           // rint(x * 2^16) of a row value (|x| <= 2047: clamped where rows are written)
+    return __float2int_rn(x * 65536.0f);
 }
 
 // (S1, S2) over F frames -> mean, std (ddof 0) as float32; the same function serves windows and templates
@@ -121,7 +122,7 @@ __global__ void dense_template_features_kernel(const float* __restrict__ frames,
     long long S1 = 0, S2 = 0;
     if (lane < N_MFCC)
         for (int t = 0; t < F; t++) {
-            const int q = quant16(frames[(size_t)t * N_MFCC + lane]);
+            const int q = quant16(fminf(fmaxf(frames[(size_t)t * N_MFCC + lane], -2047.f), 2047.f));   // K3's rows are not clamped
             S1 += q;
             S2 += (long long)q * q;
         }
@@ -193,6 +194,9 @@ __device__ __noinline__ void dense_frame(int kind, const void* ring_s, int fmt, 
     float mn, mx;
     warp_frame_mfcc(x, ft, scr, lane, floor_db, row, mn, mx);
     if (stats && lane == 0) { row[R_MIN] = mn; row[R_MAX] = mx; }
+    // rows are clamped once here (|MFCC| < 2^11 holds for any audio below ~1e4 x full scale), so quant16 needs no clamp
+    __syncwarp();
+    if (lane < N_MFCC) row[lane] = fminf(fmaxf(row[lane], -2047.f), 2047.f);
 }
 
 __device__ __forceinline__ int next_task(int* counter, int lane) {
@@ -225,14 +229,15 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
     int* WAY = FLIST + NT * DH;                                  // [T][DH] way of a floored window (-1: none)
     int* ctl = WAY + NT * DH;                                    // [DENSE_CTL]
     int* WAYF = ctl + 24;
-    int* WAYU = ctl + 28;
-    int* WAYMASK = ctl + 32;
+    int* WAYU = ctl + 32;
+    int* WAYMASK = ctl + 40;
+    int* COMBO = ctl + 56;
     const int s = blockIdx.x;
     copy_frame_tables(*ft, T, tid, nthr);
     float* scr = scratch + warp * SCR_WARP;
     float* patch = patchb + warp * N_MFCC;
     for (int i = tid; i < DENSE_WAYS * DG; i += nthr) g2tag[i] = TAG_NONE;
-    if (tid < DENSE_CTL) ctl[tid] = (tid >= 24 && tid < 28) ? TAG_NONE : 0;
+    if (tid < DENSE_CTL) ctl[tid] = (tid >= 24 && tid < 24 + DENSE_WAYS) ? TAG_NONE : 0;
 
     const size_t esz = B.fmt == 1 ? 2 : 4;
     const void* ring_s = (const char*)B.ring + (size_t)s * B.P * esz;
@@ -358,16 +363,16 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
         const int gfrom_row = n_g > 0 ? (int)(g_from % DG) : 0;
         const int gfrom_rel = (int)(g_from - hs), lefrom_rel = (int)(le_from - hs);
         const int lefrom_slot = n_le > 0 ? (int)(le_from % DLE) : 0;
-        if (tid == 0) { ctl[1] = 0; ctl[2] = 0; ctl[3] = 0; ctl[4] = 0; ctl[5] = 0; ctl[6] = 0; }
+        if (tid == 0) { ctl[1] = 0; ctl[2] = 0; ctl[3] = 0; ctl[4] = 0; ctl[5] = 0; ctl[6] = 0; ctl[7] = 0; }
         if (tid < NT) {
             // per template: ring row of grid frame (hs - n) and LE slot of start (hs - n), both possibly "negative" frames
             const long long j0 = hs - A.t[tid].n;
             ctl[8 + tid] = (int)(((j0 % DG) + DG) % DG);
             ctl[16 + tid] = (int)(((j0 % DLE) + DLE) % DLE);
-            ctl[32 + 2 * tid] = 0; ctl[33 + 2 * tid] = 0;
+            WAYMASK[2 * tid] = 0; WAYMASK[2 * tid + 1] = 0;
         }
-        if (tid >= 32 && tid < 32 + DENSE_WAYS) {                 // a way nobody used in the previous sub-chunk is free again
-            const int w = tid - 32;
+        if (tid >= 64 && tid < 64 + DENSE_WAYS) {                 // a way nobody used in the previous sub-chunk is free again
+            const int w = tid - 64;
             if (!WAYU[w]) WAYF[w] = TAG_NONE;
             WAYU[w] = 0;
         }
@@ -470,22 +475,22 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
             const float emin = EMN[k * DH + hl];
             if (fminf(wmin, emin) < floor_db) {                                 // some frame reaches below the floor
                 WFL[k * DH + hl] = floor_db;
+                // the way that holds this floor, or a free one: its copy serves the stream-grid rows the floor changes
                 int way = -1;
-                if (!(emin < floor_db)) {
-                    // only stream-grid rows are floored: take the way that holds this floor, or a free one
-                    const int fb = __float_as_int(floor_db);
-                    for (int w = 0; w < DENSE_WAYS && way < 0; w++) {
-                        int cur = *(volatile int*)(WAYF + w);
-                        if (cur == TAG_NONE) cur = atomicCAS(WAYF + w, TAG_NONE, fb), cur = cur == TAG_NONE ? fb : cur;
-                        if (cur == fb) way = w;
-                    }
+                const int fb = __float_as_int(floor_db);
+                for (int w = 0; w < DENSE_WAYS && way < 0; w++) {
+                    int cur = *(volatile int*)(WAYF + w);
+                    if (cur == TAG_NONE) cur = atomicCAS(WAYF + w, TAG_NONE, fb), cur = cur == TAG_NONE ? fb : cur;
+                    if (cur == fb) way = w;
                 }
-                if (way >= 0) {
+                if (way >= 0) WAYU[way] = 1;
+                if (way >= 0 && !(emin < floor_db)) {
+                    // only stream-grid rows are floored: sliding sums over the way's copy
                     WAY[k * DH + hl] = way;
-                    WAYU[way] = 1;
-                    atomicOr(WAYMASK + 2 * k + hh, 1 << way);
+                    if (!((atomicOr(WAYMASK + 2 * k + hh, 1 << way) >> way) & 1))
+                        COMBO[atomicAdd(ctl + 7, 1)] = (2 * k + hh) * DENSE_WAYS + way;
                     ctl[5] = 1;
-                } else FLIST[atomicAdd(ctl + 3, 1)] = k * DH + hl;              // frame by frame
+                } else FLIST[atomicAdd(ctl + 3, 1)] = k * DH + hl;              // edge frames floored, or no way left: frame by frame
                 continue;
             }
             WFL[k * DH + hl] = INFINITY;
@@ -501,29 +506,29 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
             const int span = (int)max(0LL, g_hi - span_lo + 1);
             const int row_lo = span > 0 ? (int)(span_lo % DG) : 0;
             const int lo_rel = (int)(span_lo - hs);
-            for (int job = warp; job < DENSE_WAYS * span; job += nwarps) {
-                const int w = job / span, i = job - w * span;
+            for (int w = 0; w < DENSE_WAYS; w++) {
                 if (!WAYU[w]) continue;
                 const int fbits = WAYF[w];
                 const float f = __int_as_float(fbits);
-                const int r = wrap1(row_lo + i, DG);
-                if (!(G[r * ROW + R_MIN] < f) || g2tag[w * DG + r] == fbits) continue;      // warp-uniform
-                int pos = hs_pos + 160 * (lo_rel + i) - N_FFT / 2;
-                if (pos < 0) pos += P; else if (pos >= P) pos -= P;
-                dense_frame<PRE>(FR_GRID, ring_s, fmt, P, pos, 0, 0, pre, *ft, scr, lane, f, patch, false);
-                __syncwarp();
-                if (lane < N_MFCC) __stcg(G2 + ((size_t)w * DG + r) * N_MFCC + lane, patch[lane]);
-                if (lane == 0) g2tag[w * DG + r] = fbits;
-                __syncwarp();
+                for (int i = warp; i < span; i += nwarps) {
+                    const int r = wrap1(row_lo + i, DG);
+                    if (!(G[r * ROW + R_MIN] < f) || g2tag[w * DG + r] == fbits) continue;      // warp-uniform
+                    int pos = hs_pos + 160 * (lo_rel + i) - N_FFT / 2;
+                    if (pos < 0) pos += P; else if (pos >= P) pos -= P;
+                    dense_frame<PRE>(FR_GRID, ring_s, fmt, P, pos, 0, 0, pre, *ft, scr, lane, f, patch, false);
+                    __syncwarp();
+                    if (lane < N_MFCC) __stcg(G2 + ((size_t)w * DG + r) * N_MFCC + lane, patch[lane]);
+                    if (lane == 0) g2tag[w * DG + r] = fbits;
+                    __syncwarp();
+                }
             }
             __syncthreads();
             // ---- D: frame-by-frame windows first (long tasks), then the way windows' sums per (template, half, way, coefficient)
-            const int n_d1 = NT * n_half * DENSE_WAYS * n_mfcc;
+            const int n_d1 = ctl[7] * n_mfcc;
             for (int job = next_task(ctl + 4, lane); job < n_slow + n_d1; job = next_task(ctl + 4, lane)) {
                 if (job >= n_slow) {
                     const int q = job - n_slow;
-                    const int c = q % n_mfcc, q1 = q / n_mfcc, w = q1 % DENSE_WAYS, kh = q1 / DENSE_WAYS, hh = kh % n_half, k = kh / n_half;
-                    if (!((WAYMASK[2 * k + hh] >> w) & 1)) continue;
+                    const int c = q % n_mfcc, cb = COMBO[q / n_mfcc], w = cb % DENSE_WAYS, kh = cb / DENSE_WAYS, hh = kh & 1, k = kh >> 1;
                     bool valid; float mean, sd;
                     window_sums(k, c, hh, nh, hs, w, __int_as_float(WAYF[w]), valid, mean, sd);
                     const int hl = 32 * hh + lane;
@@ -534,7 +539,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
                 const DenseTmplDev& tp = A.t[k];
                 const float f = WFL[k * DH + hl];
                 const int fb = __float_as_int(f);
-                int way = -1;                                                   // a way that happens to hold this floor
+                int way = -1;                                                   // the way that holds this floor, if any
                 for (int w = 0; w < DENSE_WAYS; w++) if (WAYF[w] == fb) way = w;
                 int wpos = hs_pos + 160 * (hl - tp.n);                          // ring position of the window's sample 0
                 if (wpos < 0) wpos += P; else if (wpos >= P) wpos -= P;
