@@ -679,7 +679,7 @@ def run_ours(args):
     # the same end-to-end step fed with G.711 mu-law codes (ewk_push_g711: 1 byte per sample over PCIe, expanded on the
     # device).  A secondary figure: the audio is the pool after companding, so its events differ from the PCM16 run.
     g711 = None
-    if not f32 and not args.no_g711 and world == 1:            # single-GPU runs only (a secondary figure)
+    if not f32 and not args.no_g711:
         try:
             from easywakeword_b200.resample import ULAW_TABLE
             tab = torch.tensor(ULAW_TABLE.astype(np.int32), device=dev)
@@ -707,6 +707,9 @@ def run_ours(args):
             def g_step():
                 g_push()                                            # the NEXT step's codes: copy + expansion beside this step's kernels
                 bank.tick(TICKS_PER_STEP)
+                if gathered is not None and exchange is None:       # (peer publication needs no call: the tick sends the records)
+                    ctx.join()
+                    dist.all_gather_into_tensor(gathered, results)
                 return bank.poll()
 
             g_push()

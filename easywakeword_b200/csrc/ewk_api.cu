@@ -185,6 +185,7 @@ void ewk_ctx::release() {
     if (d_wait_flag) { cudaFree(d_wait_flag); d_wait_flag = nullptr; }
     if (pub_stream) { cudaStreamSynchronize(pub_stream); cudaStreamDestroy(pub_stream); pub_stream = nullptr; }
     if (ev_k3) { cudaEventDestroy(ev_k3); ev_k3 = nullptr; }
+    if (ev_snap) { cudaEventDestroy(ev_snap); ev_snap = nullptr; }
     for (int i = 0; i < 2; i++) if (ev_pub[i]) { cudaEventDestroy(ev_pub[i]); ev_pub[i] = nullptr; }
     if (d_pub_snap) { cudaFree(d_pub_snap); d_pub_snap = nullptr; }
     if (d_tables) cudaFree(d_tables);
@@ -926,6 +927,10 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         B.pub_seq = (unsigned long long)ctx->publish_seq;
         B.pub_parity = (int)((ctx->publish_seq - 1) & 1);
     }
+    if (ctx->snap_pending) {                              // the previous call's records must be snapshotted before K2 rewrites them
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_snap, 0));
+        ctx->snap_pending = false;
+    }
     cudaEvent_t pe = ctx->prof_begin(1);
     for (int done = 0; done < n_ticks; done += GATE_MAX_TICKS) {
         const int nt = std::min(GATE_MAX_TICKS, n_ticks - done);
@@ -966,10 +971,14 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         // the sender: off everybody's critical path on its own stream, behind K3's snapshot of the records
         CK(cudaEventRecord(ctx->ev_k3, ks));
         CK(cudaStreamWaitEvent(ctx->pub_stream, ctx->ev_k3, 0));
+        snapshot_records_kernel<<<std::min(32, (B.n_streams + 255) / 256), 256, 0, ctx->pub_stream>>>(B);
+        CK(cudaEventRecord(ctx->ev_snap, ctx->pub_stream));                 // the next gate rewrites `results`: it waits for this
+        ctx->snap_pending = true;
         cudaEvent_t pp = ctx->prof_begin(6, ctx->pub_stream);
         publish_records_kernel<<<B.n_pub, 256, 0, ctx->pub_stream>>>(B);
         ctx->prof_end(pp, 6, ctx->pub_stream);
         CK(cudaGetLastError());
+        ctx->launches += 1;
         CK(cudaEventRecord(ctx->ev_pub[B.pub_parity], ctx->pub_stream));
         ctx->ev_pub_valid[B.pub_parity] = true;
         ctx->launches += 1;
@@ -1353,6 +1362,7 @@ extern "C" int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bas
     if (n_bases && !ctx->pub_stream) {
         CK(cudaStreamCreateWithFlags(&ctx->pub_stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ctx->ev_k3, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_snap, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&ctx->ev_pub[i], cudaEventDisableTiming));
         CK(cudaMalloc(&ctx->d_pub_snap, sizeof(StreamResult) * 2 * (size_t)B.n_streams));
     }

@@ -90,11 +90,11 @@ struct BankView {
     double* block_ss;       // [n_streams][NB]: sum of squares of absolute block b = a / 1600 at b % NB (written by K1)
     float* lm_ws;           // K3 log-mel workspace: [segment_queue CTAs][SEG_SMEM_FRAMES][LM_ROW]
     int n_streams, R, P, fmt, chunk_cap, max_events, NB;
-    // peer publication (ewk_set_results_peers): when the last K3 CTA of a tick call has seen every other CTA arrive, it
-    // snapshots `results` into pub_snap[pub_parity] (local); a small kernel on a side stream then copies the snapshot to
-    // pub[p] + pub_parity * pub_stride + pub_off for each destination p — local or NVLink peer-mapped memory — and
-    // releases the call's sequence number into every destination's signal row: a put-with-signal that is on nobody's
-    // critical path (the next push and gate depend on neither the copy nor the signal).
+    // peer publication (ewk_set_results_peers): behind K3 of a tick call, on a side stream, one small kernel snapshots
+    // `results` into pub_snap[pub_parity] (local: the next gate may rewrite `results` as soon as that is done) and a second
+    // one copies the snapshot to pub[p] + pub_parity * pub_stride + pub_off for each destination p — local or NVLink
+    // peer-mapped memory — and releases the call's sequence number into every destination's signal row: a put-with-signal
+    // that is on nobody's critical path (the next push depends on nothing of it, the next gate on the snapshot only).
     StreamResult* pub[MAX_PUB];
     int n_pub, pub_parity;
     long long pub_stride, pub_off;
@@ -110,12 +110,27 @@ struct BankView {
 // then every thread orders its stores at system scope and thread 0 releases the call's sequence number into slot
 // `pub_slot` of the destination's signal row: whoever reads that number (ld.acquire.sys) holds all records of the call.
 __global__ void __launch_bounds__(256)
+snapshot_records_kernel(BankView B) {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(B.results);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(B.pub_snap + (size_t)B.pub_parity * B.n_streams);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.n_streams; i += gridDim.x * blockDim.x) dst[i] = __ldcg(src + i);
+}
+
+__global__ void __launch_bounds__(256)
 publish_records_kernel(BankView B) {
     const int p = blockIdx.x;
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(B.pub_snap + (size_t)B.pub_parity * B.n_streams);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(B.pub[p] + (size_t)B.pub_parity * (size_t)B.pub_stride + (size_t)B.pub_off);
-    for (int i = threadIdx.x; i < B.n_streams; i += blockDim.x)
-        asm volatile("st.weak.global.b64 [%0], %1;" :: "l"(dst + i), "l"(__ldcg(src + i)) : "memory");
+    for (int i0 = threadIdx.x; i0 < B.n_streams; i0 += 8 * blockDim.x) {
+        unsigned long long v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int i = i0 + u * blockDim.x; v[u] = i < B.n_streams ? __ldcg(src + i) : 0ull; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = i0 + u * blockDim.x;
+            if (i < B.n_streams) asm volatile("st.weak.global.b64 [%0], %1;" :: "l"(dst + i), "l"(v[u]) : "memory");
+        }
+    }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0 && B.pub_sig[p]) {
@@ -1038,22 +1053,12 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
         r = next_s;
         __syncthreads();
     }
-    __shared__ int last_s;
     if (tid == 0) {
-        __threadfence();                                                 // this CTA's records before its arrival
-        last_s = atomicAdd(B.ev_count + 4, 1) == (int)gridDim.x - 1;     // every other CTA has read the counters
-        if (last_s) { B.ev_count[3] = n; B.ev_count[2] = 0; B.ev_count[4] = 0; }
-    }
-    if (B.n_pub) {                                                       // uniform over the launch
-        __syncthreads();
-        if (last_s) {
-            // every CTA's records precede its arrival, every arrival precedes this point; K2's records were complete when
-            // this kernel started: snapshot them for the sender (publish_records_kernel), so that the next gate may
-            // rewrite `results` while the snapshot is still travelling
-            __threadfence();
-            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(B.results);
-            unsigned long long* dst = reinterpret_cast<unsigned long long*>(B.pub_snap + (size_t)B.pub_parity * B.n_streams);
-            for (int i = tid; i < B.n_streams; i += blockDim.x) dst[i] = __ldcg(src + i);
+        __threadfence();
+        if (atomicAdd(B.ev_count + 4, 1) == (int)gridDim.x - 1) {       // every other CTA has read the counters
+            B.ev_count[3] = n;
+            B.ev_count[2] = 0;
+            B.ev_count[4] = 0;
         }
     }
 }
