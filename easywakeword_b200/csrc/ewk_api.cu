@@ -581,7 +581,17 @@ int ewk_ctx::init_streams() {
     CK(cudaMalloc(&bank.block_ss, sizeof(double) * (size_t)n * std::max(1, bank.NB)));
     CK(cudaMalloc(&own_results, sizeof(StreamResult) * (size_t)n));
     bank.results = (StreamResult*)own_results;
-    if (use_lm) CK(cudaMalloc(&bank.lm_ws, sizeof(float) * (size_t)queue_grid() * SEG_SMEM_FRAMES * LM_ROW));
+    if (const char* e = getenv("EWK_K3")) k3_frames = atoi(e) != 1;      // EWK_K3=1: one CTA per segment (the round-1 form)
+    if (!k3_frames) {
+        if (use_lm) CK(cudaMalloc(&bank.lm_ws, sizeof(float) * (size_t)queue_grid() * SEG_SMEM_FRAMES * LM_ROW));
+    } else {
+        // frame-parallel K3: a frame table for the candidates of ONE ewk_tick call (it restarts after every K3 launch)
+        const size_t cap = std::min<size_t>((size_t)bank.max_events * SEG_SMEM_FRAMES, ((size_t)2 << 30) / (FROW * sizeof(float)));
+        bank.frow_cap = (int)cap;
+        CK(cudaMalloc(&bank.frow, sizeof(float) * FROW * cap));
+        CK(cudaMalloc(&bank.frame_ev, sizeof(int) * cap));
+        CK(cudaMalloc(&bank.ev_done, sizeof(int) * (size_t)bank.max_events));
+    }
     std::vector<StreamState> st(n);
     std::memset(st.data(), 0, sizeof(StreamState) * n);
     for (auto& x : st) { x.thr = 0.01; x.last_ev = -1; }                            // wakeword.py:431
@@ -605,6 +615,8 @@ int ewk_ctx::init_streams() {
                             (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
     CK(cudaFuncSetAttribute(segment_queue_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)seg_smem_bytes(SEG_SMEM_FRAMES)));
+    CK(cudaFuncSetAttribute(segment_frames_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fq_smem_bytes()));
+    CK(cudaFuncSetAttribute(segment_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fq_smem_bytes()));
     CK(cudaFuncSetAttribute(ring_push_bulk_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CK(cudaFuncSetAttribute(ring_push_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     {
@@ -617,7 +629,8 @@ int ewk_ctx::init_streams() {
 
 void ewk_ctx::release_streams() {
     for (void* p : {bank.ring, (void*)bank.st, (void*)bank.prm, (void*)bank.chunk_ms, (void*)bank.events,
-                    (void*)bank.ev_count, (void*)bank.block_ss, (void*)bank.lm_ws, own_results})
+                    (void*)bank.ev_count, (void*)bank.block_ss, (void*)bank.lm_ws, own_results, (void*)bank.frow,
+                    (void*)bank.frame_ev, (void*)bank.ev_done})
         if (p) cudaFree(p);
     bank = BankView{};
     own_results = nullptr;
@@ -958,8 +971,13 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
     if (B.n_pub > 0 && ctx->ev_pub_valid[B.pub_parity])
         CK(cudaStreamWaitEvent(ks, ctx->ev_pub[B.pub_parity], 0));       // this parity's snapshot was sent two calls ago: long done
     pe = ctx->prof_begin(2, ks);
-    auto k3q = ctx->cfg.preemphasis != 0.f ? segment_queue_kernel<true> : segment_queue_kernel<false>;
-    k3q<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ks>>>(ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
+    if (ctx->k3_frames) {
+        auto k3f = ctx->cfg.preemphasis != 0.f ? segment_frames_kernel<true> : segment_frames_kernel<false>;
+        k3f<<<grid, SEG_THREADS, fq_smem_bytes(), ks>>>(ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
+    } else {
+        auto k3q = ctx->cfg.preemphasis != 0.f ? segment_queue_kernel<true> : segment_queue_kernel<false>;
+        k3q<<<grid, SEG_THREADS, seg_smem_bytes(SEG_SMEM_FRAMES), ks>>>(ctx->d_tables, B, ctx->d_tmpl, ctx->cfg.max_templates);
+    }
     ctx->prof_end(pe, 2, ks);
     CK(cudaGetLastError());
     if (ks != ctx->stream) {
@@ -1031,7 +1049,7 @@ extern "C" int ewk_poll(ewk_ctx* ctx, ewk_event* out, int cap, int* dropped) {
     if (n > 0) {
         CK(cudaMemcpyAsync(out, B.events, sizeof(EventRec) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    CK(cudaMemsetAsync(B.ev_count, 0, sizeof(int) * 4, ctx->stream));     // count, dropped, K3 work counter, scored watermark
+    CK(cudaMemsetAsync(B.ev_count, 0, sizeof(int) * 7, ctx->stream));     // count, dropped, K3 work counter, scored watermark, frame table
     CK(cudaStreamSynchronize(ctx->stream));
     std::sort(out, out + n, [](const ewk_event& a, const ewk_event& b) {
         if (a.tick != b.tick) return a.tick < b.tick;

@@ -78,6 +78,7 @@ struct StreamResult {       // dense per-stream record (what multi-GPU runs gath
 };
 
 constexpr int MAX_PUB = 16;  // destinations of a peer publication (GPUs of one NVLink domain)
+constexpr int FROW = 24;     // floats per frame row of the frame-parallel K3: mfcc[20], log-mel min, log-mel max, pad (96 B)
 
 struct BankView {
     void* ring;             // [n_streams][P]
@@ -85,7 +86,12 @@ struct BankView {
     StreamParams* prm;
     double* chunk_ms;       // [n_streams][chunk_cap] mean square per storage-order chunk
     EventRec* events;
-    int* ev_count;          // [0] count, [1] dropped, [2] K3 work counter, [3] events below this index are scored, [4] K3 CTAs done
+    int* ev_count;          // [0] count, [1] dropped, [2] K3 work counter, [3] events below this index are scored, [4] K3 CTAs done,
+                            // [5] frames below this index are done, [6] frames allocated to queued candidates (frame-parallel K3)
+    int* frame_ev;          // [frow_cap] event index of every allocated frame (-1: a hole left by a dropped candidate)
+    int* ev_done;           // [max_events] frames of the event computed so far: whoever completes the last one scores the event
+    float* frow;            // [frow_cap][FROW] un-floored MFCC rows (+ log-mel min / max) of the queued candidates' frames
+    int frow_cap;
     StreamResult* results;
     double* block_ss;       // [n_streams][NB]: sum of squares of absolute block b = a / 1600 at b % NB (written by K1)
     float* lm_ws;           // K3 log-mel workspace: [segment_queue CTAs][SEG_SMEM_FRAMES][LM_ROW]
@@ -658,16 +664,29 @@ __device__ __forceinline__ unsigned gate_state_step(const BankView& B, int s, St
                     const long long len = n_back - n_drop;
                     if (len >= 1 && len <= MAX_SEG) {                                    // :1114-1118
                         const int idx = atomicAdd(B.ev_count, 1);
-                        if (idx < B.max_events) {
+                        // frame-parallel K3: the candidate's 1 + len/160 frames get a contiguous range of the frame table
+                        const int nf = 1 + (int)len / HOP;
+                        const int f0 = B.frame_ev ? atomicAdd(B.ev_count + 6, nf) : 0;
+                        const bool fits = !B.frame_ev || (f0 >= 0 && f0 + nf <= B.frow_cap);
+                        if (idx < B.max_events && fits) {
                             EventRec e{};
                             e.stream = s; e.kind = EV_PENDING; e.tick = k;
                             e.seg_start = V - n_back; e.seg_len = (int)len;
-                            e.tmpl = -1; e.score = __int_as_float(0x7fc00000); e.matched = 0;
+                            e.tmpl = f0;                                 // first frame of the range until K3 writes the best template
+                            e.score = __int_as_float(0x7fc00000); e.matched = 0;
                             B.events[idx] = e;
+                            if (B.frame_ev) {
+                                B.ev_done[idx] = 0;
+                                for (int t = 0; t < nf; t++) B.frame_ev[f0 + t] = idx;
+                            }
                             st.n_events++;
                             st.last_ev = idx;
                             evflag = 16u;
-                        } else { atomicAdd(B.ev_count + 1, 1); atomicSub(B.ev_count, 1); }
+                        } else {
+                            atomicAdd(B.ev_count + 1, 1); atomicSub(B.ev_count, 1);
+                            if (B.frame_ev && f0 >= 0)                   // the range stays allocated: mark what exists of it as a hole
+                                for (int t = 0; t < nf && f0 + t < B.frow_cap; t++) B.frame_ev[f0 + t] = -1;
+                        }
                     }
                     st.state = ST_WAITING;                      // :1117, 1155
                 }
@@ -1057,6 +1076,191 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
         __threadfence();
         if (atomicAdd(B.ev_count + 4, 1) == (int)gridDim.x - 1) {       // every other CTA has read the counters
             B.ev_count[3] = n;
+            B.ev_count[2] = 0;
+            B.ev_count[4] = 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ K3 (frame-parallel queue form)
+// The same result as segment_queue_kernel, with FRAMES as the unit of work instead of segments: the queued candidates'
+// frames (K2 gave every candidate a contiguous range of a frame table) are taken in small chunks by any warp of the
+// grid, so the kernel has no block barrier and no tail of whole segments.  A warp turns its frames into un-floored MFCC
+// rows (+ log-mel min / max) in a global row table that stays L2-resident (96 B per frame), counts them on the
+// candidate's completion counter, and the warp that delivers a candidate's LAST frame runs its epilogue alone:
+// max over frames -> power_to_db floor, frames below it recomputed with the floor, mean / std over frames with the very
+// operation order of segment_features (14 strided partials, Chan pooling — so the features are bit-identical to the
+// one-CTA form and to what ewk_extract_mfcc / ewk_set_template produce), cosine scores, event and result records.
+constexpr int FQ_CHUNK = 2;                    // frames a warp takes per visit of the work counter
+__host__ __device__ inline size_t fq_smem_bytes() { return sizeof(FrameTables) + sizeof(float) * (size_t)SEG_WARPS * (SCR_WARP + FEAT); }
+
+struct FqView {                                // what the epilogue needs of the bank, by value (the kernel's BankView stays in
+    const void* ring;                          // parameter space: a non-inlined callee must not take its address)
+    EventRec* events;
+    float* frow;
+    const StreamParams* prm;
+    const StreamState* st;
+    StreamResult* results;
+    int P, fmt;
+};
+
+template <bool PRE>
+__device__ __forceinline__ void fq_reader(const void* ring, int P, int fmt, int stream, long long seg_start, int seg_len, float pre,
+                                          PcmReader& rd) {
+    const size_t esz = fmt == 1 ? 2 : 4;
+    const char* base = (const char*)ring + (size_t)stream * P * esz;
+    rd.f = fmt == 0 ? (const float*)base : nullptr;
+    rd.q = fmt == 1 ? (const short*)base : nullptr;
+    rd.ring = P; rd.len = seg_len; rd.start = seg_start % P; rd.pre = PRE ? pre : 0.f;
+}
+
+// epilogue of one candidate by one warp: rows -> features -> scores -> records
+template <bool PRE>
+__device__ __noinline__ void fq_finish(const FqView B, int idx, const FrameTables* ft, float* scr, float* feat,
+                                       const TemplateFeat* __restrict__ tmpl, int n_tmpl_slots) {
+    const int lane = threadIdx.x & 31;
+    const EventRec e = B.events[idx];
+    const int F = 1 + e.seg_len / HOP;
+    float* rows = B.frow + (size_t)e.tmpl * FROW;              // e.tmpl still holds the candidate's first frame
+    // floor = (max over frames of the log-mel max) - 80
+    float vmax = -INFINITY;
+    for (int t = lane; t < F; t += 32) vmax = fmaxf(vmax, __ldcg(rows + (size_t)t * FROW + N_MFCC + 1));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
+    const float floor_db = vmax - 80.0f;                        // librosa.power_to_db(top_db=80)
+    // frames that reach below the floor are recomputed with it (same function, same bits as the one-CTA form's re-floor)
+    PcmReader rd;
+    fq_reader<PRE>(B.ring, B.P, B.fmt, e.stream, e.seg_start, e.seg_len, ft->preemph, rd);
+    for (int t0 = 0; t0 < F; t0 += 32) {
+        const int t = t0 + lane;
+        unsigned m = __ballot_sync(FULL, t < F && __ldcg(rows + (size_t)t * FROW + N_MFCC) < floor_db);
+        while (m) {
+            const int tt = t0 + __ffs(m) - 1;
+            m &= m - 1;
+            float2 x[8];
+            load_frame_pairs<PRE>(rd, tt, lane, x);
+            float mn, mx;
+            warp_frame_mfcc(x, *ft, scr, lane, floor_db, rows + (size_t)tt * FROW, mn, mx);
+        }
+    }
+    __syncwarp();
+    // mean / std over frames, operation for operation as segment_features: partial w owns frames w, w + 14, ...
+    if (lane < N_MFCC) {
+        float n = 0.f, mean = 0.f, M2 = 0.f;
+        for (int w = 0; w < SEG_WARPS && w < F; w++) {
+            float sum = 0.f;
+            int nw = 0;
+            for (int t = w; t < F; t += SEG_WARPS, nw++) sum += __ldcg(rows + (size_t)t * FROW + lane);
+            const float mu = sum / (float)nw;
+            float m2 = 0.f;
+            for (int t = w; t < F; t += SEG_WARPS) { const float d = __ldcg(rows + (size_t)t * FROW + lane) - mu; m2 = fmaf(d, d, m2); }
+            const float cw = (float)((F - w + SEG_WARPS - 1) / SEG_WARPS);
+            const float delta = mu - mean, nn = n + cw;
+            mean = fmaf(delta, cw / nn, mean);
+            M2 += m2 + delta * delta * (n * cw / nn);
+            n = nn;
+        }
+        const bool kept = lane < ft->n_mfcc;
+        feat[lane] = kept ? mean : 0.f;
+        feat[N_MFCC + lane] = kept ? sqrtf(M2 / (float)F) : 0.f;
+    }
+    __syncwarp();
+    // best score over the stream's template set (NaN never wins: NaN >= x is false, as in wakeword.py:638-639)
+    const StreamParams& prm = B.prm[e.stream];
+    const int t0 = max(0, prm.template_first);
+    const int nt = max(0, min(prm.template_count, n_tmpl_slots - t0));
+    float best = __int_as_float(0x7fc00000);
+    int arg = nt > 0 ? t0 : -1;
+    for (int k0 = 0; k0 < nt; k0 += 32) {
+        const int k = k0 + lane;
+        float sc = __int_as_float(0x7fc00000);
+        if (k < nt) {
+            const TemplateFeat& tf = tmpl[t0 + k];
+            if (tf.valid) sc = similarity_score(tf.mean, tf.std, feat, feat + N_MFCC);
+        }
+        // sequential order over k (the first best wins), as the one-CTA form
+        for (int j = 0; j < 32 && k0 + j < nt; j++) {
+            const float v = __shfl_sync(FULL, sc, j);
+            if (!(v != v) && (best != best || v > best)) { best = v; arg = t0 + k0 + j; }
+        }
+    }
+    if (lane == 0) {
+        const int ok = best >= prm.similarity_threshold ? 1 : 0;
+        EventRec* o = B.events + idx;
+        o->score = best; o->tmpl = arg; o->matched = ok; o->kind = EV_SCORED;
+        if (B.st[e.stream].last_ev == idx) {
+            StreamResult res = B.results[e.stream];
+            res.score = best;
+            res.flags = (res.flags & ~1u) | (unsigned)ok;
+            store_result(B.results + e.stream, res);
+        }
+    }
+    __syncwarp();
+}
+
+template <bool PRE>
+__global__ void __launch_bounds__(512, 2)
+segment_frames_kernel(const DeviceTables* __restrict__ T, BankView B, const TemplateFeat* __restrict__ tmpl, int n_tmpl_slots) {
+    extern __shared__ __align__(16) float smem[];
+    FrameTables* ft = reinterpret_cast<FrameTables*>(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* scr = smem + sizeof(FrameTables) / sizeof(float) + (size_t)warp * (SCR_WARP + FEAT);
+    float* feat = scr + SCR_WARP;
+    const int n = min(B.ev_count[0], B.max_events);
+    const int f_lo = min(B.ev_count[5], B.frow_cap), f_hi = min(max(B.ev_count[6], 0), B.frow_cap);
+    if (f_hi > f_lo) {
+        copy_frame_tables(*ft, T, tid, blockDim.x);
+        __syncthreads();
+        for (;;) {
+            int c0 = 0;
+            if (lane == 0) c0 = atomicAdd(B.ev_count + 2, FQ_CHUNK);
+            c0 = f_lo + __shfl_sync(FULL, c0, 0);
+            if (c0 >= f_hi) break;
+            const int c1 = min(c0 + FQ_CHUNK, f_hi);
+            int done_ev = -1, done_cnt = 0, done_F = 0;            // frames of one candidate computed in this chunk, not yet delivered
+            auto deliver = [&]() {
+                int old = 0;
+                __threadfence();
+                if (lane == 0) old = atomicAdd(B.ev_done + done_ev, done_cnt);
+                old = __shfl_sync(FULL, old, 0);
+                if (old + done_cnt == done_F) {                    // this warp delivered the candidate's last frame: it scores it
+                    __threadfence();
+                    fq_finish<PRE>(FqView{B.ring, B.events, B.frow, B.prm, B.st, B.results, B.P, B.fmt}, done_ev, ft, scr, feat, tmpl,
+                                   n_tmpl_slots);
+                }
+                done_cnt = 0;
+            };
+            for (int f = c0; f < c1; f++) {
+                const int idx = B.frame_ev[f];
+                if (idx != done_ev && done_cnt) deliver();          // leaving a candidate
+                if (idx < 0) continue;                             // hole left by a dropped candidate
+                float2 x[8];
+                {
+                    // the candidate's descriptor is re-read per frame (L1 / L2 hits) rather than kept live across the pipeline call
+                    const EventRec* ep = B.events + idx;
+                    const int len = ep->seg_len;
+                    PcmReader rd;
+                    fq_reader<PRE>(B.ring, B.P, B.fmt, ep->stream, ep->seg_start, len, ft->preemph, rd);
+                    done_F = 1 + len / HOP;
+                    load_frame_pairs<PRE>(rd, f - ep->tmpl, lane, x);
+                }
+                float mn, mx;
+                float* row = B.frow + (size_t)f * FROW;
+                warp_frame_mfcc(x, *ft, scr, lane, -INFINITY, row, mn, mx);
+                if (lane == 0) { row[N_MFCC] = mn; row[N_MFCC + 1] = mx; }
+                done_ev = idx;
+                done_cnt++;
+            }
+            if (done_cnt) deliver();
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(B.ev_count + 4, 1) == (int)gridDim.x - 1) {       // every other CTA is done: nobody reads the counters any more
+            B.ev_count[3] = n;
+            B.ev_count[5] = 0;                                           // rows are scratch of one launch: the frame table restarts,
+            B.ev_count[6] = 0;                                           // so it stays small and L2-resident
             B.ev_count[2] = 0;
             B.ev_count[4] = 0;
         }
