@@ -581,7 +581,7 @@ int ewk_ctx::init_streams() {
     CK(cudaMalloc(&bank.block_ss, sizeof(double) * (size_t)n * std::max(1, bank.NB)));
     CK(cudaMalloc(&own_results, sizeof(StreamResult) * (size_t)n));
     bank.results = (StreamResult*)own_results;
-    if (const char* e = getenv("EWK_K3")) k3_frames = atoi(e) != 1;      // EWK_K3=1: one CTA per segment (the round-1 form)
+    if (const char* e = getenv("EWK_K3")) k3_frames = atoi(e) == 2;      // EWK_K3=2: the frame-parallel form (measured, not the default)
     if (!k3_frames) {
         if (use_lm) CK(cudaMalloc(&bank.lm_ws, sizeof(float) * (size_t)queue_grid() * SEG_SMEM_FRAMES * LM_ROW));
     } else {

@@ -39,7 +39,7 @@ struct ewk_ctx {
     int device = 0;
     int sm_count = 0;
     bool use_lm = true;          // keep log-mel rows of K3 frames in a global workspace (EWK_SEG_LM=0 disables)
-    bool k3_frames = true;       // queue-form K3 with frames as the unit of work (EWK_K3=1: one CTA per segment)
+    bool k3_frames = false;      // EWK_K3=2: queue-form K3 with frames as the unit of work (default: one CTA per segment)
     ewk_config cfg{};
     std::string err;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;

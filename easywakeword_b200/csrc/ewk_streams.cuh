@@ -1122,43 +1122,96 @@ __device__ __noinline__ void fq_finish(const FqView B, int idx, const FrameTable
     const EventRec e = B.events[idx];
     const int F = 1 + e.seg_len / HOP;
     float* rows = B.frow + (size_t)e.tmpl * FROW;              // e.tmpl still holds the candidate's first frame
-    // floor = (max over frames of the log-mel max) - 80
+    // floor = (max over frames of the log-mel max) - 80.  The (min, max) of up to 320 frames are fetched with ten
+    // independent loads per lane: one L2 latency instead of one per frame
+    constexpr int MMR = (SEG_SMEM_FRAMES + 31) / 32;
+    float2 mm[MMR];
+#pragma unroll
+    for (int i = 0; i < MMR; i++) {
+        const int t = lane + 32 * i;
+        mm[i] = t < F ? __ldcg(reinterpret_cast<const float2*>(rows + (size_t)t * FROW + N_MFCC)) : make_float2(INFINITY, -INFINITY);
+    }
     float vmax = -INFINITY;
-    for (int t = lane; t < F; t += 32) vmax = fmaxf(vmax, __ldcg(rows + (size_t)t * FROW + N_MFCC + 1));
+#pragma unroll
+    for (int i = 0; i < MMR; i++) vmax = fmaxf(vmax, mm[i].y);
 #pragma unroll
     for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
     const float floor_db = vmax - 80.0f;                        // librosa.power_to_db(top_db=80)
     // frames that reach below the floor are recomputed with it (same function, same bits as the one-CTA form's re-floor)
-    PcmReader rd;
-    fq_reader<PRE>(B.ring, B.P, B.fmt, e.stream, e.seg_start, e.seg_len, ft->preemph, rd);
-    for (int t0 = 0; t0 < F; t0 += 32) {
-        const int t = t0 + lane;
-        unsigned m = __ballot_sync(FULL, t < F && __ldcg(rows + (size_t)t * FROW + N_MFCC) < floor_db);
-        while (m) {
-            const int tt = t0 + __ffs(m) - 1;
-            m &= m - 1;
-            float2 x[8];
-            load_frame_pairs<PRE>(rd, tt, lane, x);
-            float mn, mx;
-            warp_frame_mfcc(x, *ft, scr, lane, floor_db, rows + (size_t)tt * FROW, mn, mx);
+    {
+        PcmReader rd;
+        fq_reader<PRE>(B.ring, B.P, B.fmt, e.stream, e.seg_start, e.seg_len, ft->preemph, rd);
+#pragma unroll
+        for (int i = 0; i < MMR; i++) {
+            unsigned m = __ballot_sync(FULL, mm[i].x < floor_db);
+            while (m) {
+                const int tt = 32 * i + __ffs(m) - 1;
+                m &= m - 1;
+                float2 x[8];
+                load_frame_pairs<PRE>(rd, tt, lane, x);
+                float mn, mx;
+                warp_frame_mfcc(x, *ft, scr, lane, floor_db, rows + (size_t)tt * FROW, mn, mx);
+            }
         }
     }
     __syncwarp();
-    // mean / std over frames, operation for operation as segment_features: partial w owns frames w, w + 14, ...
+    // mean / std over frames, operation for operation as segment_features: partial w owns frames w, w + 14, ... (its sum,
+    // then its M2 about its own mean, each in frame order), the 14 partials pooled in order (Chan et al.).  The rows come
+    // through the warp's scratch in tiles of FQ_TILE frames, fetched with independent 16-byte loads.
+    constexpr int FQ_TILE = 24;                                  // 24 frames x 96 B = 2304 B of the 2560 B scratch
+    float acc[SEG_WARPS], mu[SEG_WARPS];
+#pragma unroll
+    for (int w = 0; w < SEG_WARPS; w++) { acc[w] = 0.f; mu[w] = 0.f; }
+    const int cl = lane < N_MFCC ? lane : 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+#pragma unroll 1
+        for (int t0 = 0; t0 < F; t0 += FQ_TILE) {
+            const int nt = min(FQ_TILE, F - t0);
+            __syncwarp();
+            {
+                const float4* src = reinterpret_cast<const float4*>(rows + (size_t)t0 * FROW);
+                float4* dst = reinterpret_cast<float4*>(scr);
+                const int n4 = nt * (FROW / 4);
+                float4 v[5];                                     // 24 * 6 = 144 words of 16 bytes: at most 5 per lane
+#pragma unroll
+                for (int u = 0; u < 5; u++) { const int i = lane + 32 * u; v[u] = i < n4 ? __ldcg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+                for (int u = 0; u < 5; u++) { const int i = lane + 32 * u; if (i < n4) dst[i] = v[u]; }
+            }
+            __syncwarp();
+            const int ph = t0 % SEG_WARPS;
+#pragma unroll
+            for (int w = 0; w < SEG_WARPS; w++) {
+                int j = w - ph; if (j < 0) j += SEG_WARPS;       // first frame of the tile that belongs to partial w
+                for (; j < nt; j += SEG_WARPS) {
+                    const float v = scr[j * FROW + cl];
+                    if (pass == 0) acc[w] += v;
+                    else { const float d = v - mu[w]; acc[w] = fmaf(d, d, acc[w]); }
+                }
+            }
+        }
+        if (pass == 0) {
+#pragma unroll
+            for (int w = 0; w < SEG_WARPS; w++) {
+                const int nw = (F - w + SEG_WARPS - 1) / SEG_WARPS;
+                mu[w] = w < F ? acc[w] / (float)nw : 0.f;
+                acc[w] = 0.f;
+            }
+        }
+    }
+    __syncwarp();
     if (lane < N_MFCC) {
         float n = 0.f, mean = 0.f, M2 = 0.f;
-        for (int w = 0; w < SEG_WARPS && w < F; w++) {
-            float sum = 0.f;
-            int nw = 0;
-            for (int t = w; t < F; t += SEG_WARPS, nw++) sum += __ldcg(rows + (size_t)t * FROW + lane);
-            const float mu = sum / (float)nw;
-            float m2 = 0.f;
-            for (int t = w; t < F; t += SEG_WARPS) { const float d = __ldcg(rows + (size_t)t * FROW + lane) - mu; m2 = fmaf(d, d, m2); }
-            const float cw = (float)((F - w + SEG_WARPS - 1) / SEG_WARPS);
-            const float delta = mu - mean, nn = n + cw;
-            mean = fmaf(delta, cw / nn, mean);
-            M2 += m2 + delta * delta * (n * cw / nn);
-            n = nn;
+#pragma unroll
+        for (int w = 0; w < SEG_WARPS; w++) {
+            if (w < F) {
+                const float cw = (float)((F - w + SEG_WARPS - 1) / SEG_WARPS);
+                const float delta = mu[w] - mean, nn = n + cw;
+                mean = fmaf(delta, cw / nn, mean);
+                M2 += acc[w] + delta * delta * (n * cw / nn);
+                n = nn;
+            }
         }
         const bool kept = lane < ft->n_mfcc;
         feat[lane] = kept ? mean : 0.f;

@@ -202,3 +202,32 @@ def test_overlap_mode_bulk_push_matches_sequential(word, dtype):
         assert bytes(a) == bytes(b)
     for a, b in zip(g0, g1):
         assert np.array_equal(a, b)
+
+
+def test_frame_parallel_k3_gives_identical_events(word, monkeypatch):
+    """EWK_K3=2 selects the frame-parallel queue form of K3 (experiments/README.md: measured, not the default).  Its
+    features follow the one-CTA form operation for operation, so events, scores and result records are bit-identical."""
+    from easywakeword_b200.bank import WakeWordBank
+    from easywakeword_b200.synth import stream_batch
+    pcm16 = stream_batch(4300, 48, 24.0, word, zero_gaps=1, distractor_prob=0.3)
+    out = []
+    for mode in ("1", "2"):
+        monkeypatch.setenv("EWK_K3", mode)
+        bank = WakeWordBank(48, [word], device=0, buffer_seconds=5, speech_duration_min=0.5, speech_duration_max=1.6)
+        try:
+            evs = []
+            for i, b in enumerate(range(0, pcm16.shape[1], 16000)):
+                bank.step(np.ascontiguousarray(pcm16[:, b:b + 16000]))
+                if i % 4 == 3:
+                    evs.append(bank.poll())
+            evs.append(bank.poll())
+            out.append((np.concatenate(evs), bank.ctx.results()))
+        finally:
+            bank.close()
+    monkeypatch.delenv("EWK_K3")
+    (e0, r0), (e1, r1) = out
+    assert len(e0) == len(e1) and (e0["kind"] == 2).sum() > 20
+    for f in e0.dtype.names:
+        assert np.array_equal(e0[f], e1[f], equal_nan=e0[f].dtype.kind == "f"), f
+    for f in r0.dtype.names:
+        assert np.array_equal(r0[f], r1[f], equal_nan=r0[f].dtype.kind == "f"), f
