@@ -131,6 +131,11 @@ __device__ __forceinline__ float2 operator-(float2 a, float2 b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
     return u64_as_f2(r);
 }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {            // element-wise (a.x b.x, a.y b.y): one FMUL2
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+    return u64_as_f2(r);
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -167,7 +172,7 @@ __device__ __forceinline__ void warp_power_spectrum(const float2 (&x)[8], const 
 #pragma unroll
     for (int a = 0; a < 8; a++) {
         const float2 h = ft.hw[a * 32 + lane];
-        v[a] = make_float2(x[a].x * h.x, x[a].y * h.y);
+        v[a] = mul2(x[a], h);
     }
     // radix-8 over a  (n = 32a + lane)
     fft8(v);
