@@ -57,10 +57,10 @@ def main():
                 bank.tick(10)
             c.wait_published(1, c.publish_seq())
             ev.append(bank.poll())
+            hits = ev[-1][ev[-1]["kind"] == 2][:2]
+            if len(hits):
+                bank.prepare_for_transcription(hits)              # K5 on segments that are still in the rings
         ev = np.concatenate(ev)
-        hits = ev[ev["kind"] == 2][:4]
-        if len(hits):
-            bank.prepare_for_transcription(hits)
         c.set_results_peers([])
         bank.close()
         print(f"EWK_K3={k3}: {int((ev['kind'] == 2).sum())} level-2 events")

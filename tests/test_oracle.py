@@ -337,3 +337,26 @@ def test_staged_reference_is_the_reference(tmp_path):
         a = open(os.path.join(stage_ref.SRC_ROOT, f), "rb").read()
         b = open(os.path.join(stage_ref.DST_ROOT, f), "rb").read()
         assert a == b and hashlib.sha256(b).hexdigest() == man["files"][f]
+
+
+@pytest.mark.parametrize("sr", [44100, 48000, 22050, 8000])
+def test_resample_oracle_against_an_independent_kaiser_sinc_resampler(sr):
+    """N3 stays PARITY UNPINNED against the reference's soxr (no soxr / librosa binary offline, no resampled golden in the
+    reference).  What can be stated: on band-limited content (twelve tones below 0.8 of the lower Nyquist) the restated
+    converter agrees with an independent implementation of band-limited resampling — torchaudio's Kaiser-windowed sinc
+    interpolator in its 'kaiser_best' setting — to 2e-5 of a 1.3 full-scale signal, i.e. to the two filters' pass-band
+    ripple.  Differences between any two such filters (soxr HQ included) live in the 0.913 .. 1.0 transition band."""
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    from oracle import resample_restated as R
+    t = np.arange(int(sr * 0.5)) / sr
+    fmax = 0.8 * min(sr, 16000) / 2
+    rng = np.random.default_rng(0)
+    x = sum(rng.uniform(0.05, 0.2) * np.sin(2 * np.pi * f * t + rng.uniform(0, 6)) for f in rng.uniform(100, fmax, 12)).astype(np.float32)
+    y = R.resample(x, sr)
+    z = torchaudio.functional.resample(torch.from_numpy(x), sr, 16000, lowpass_filter_width=64, rolloff=0.9475,
+                                       resampling_method="sinc_interp_kaiser", beta=14.769656459379492).numpy()
+    n = min(len(y), len(z))
+    assert abs(len(y) - len(z)) <= 1
+    dev = float(np.abs(y[:n][400:n - 400] - z[:n][400:n - 400]).max())
+    assert dev <= 5e-5, dev
