@@ -466,13 +466,21 @@ def config3_leg(torch, dist, dev, stream, local_rank, rank, world, word, pool_de
     ctx.set_overlap(overlap)
     gathered = torch.zeros(world * n, 2, dtype=torch.int32, device=dev) if world > 1 else None
     pushed = [0]
+    stepped = [0]
 
-    def step():
+    def push():
         j = pushed[0] % POOL_SECONDS
         pushed[0] += 1
         bank.push((big.data_ptr() + j * n * STEP_SAMPLES * 2, n, STEP_SAMPLES, STEP_SAMPLES), where=_lib.DEVICE)
+
+    def step():
+        if pushed[0] == stepped[0]:
+            push()
+        stepped[0] += 1
         bank.tick(TICKS_PER_STEP)
         if gathered is not None:
+            if overlap:
+                push()                                              # the next step's K1 beside this step's K3, ahead of the gather
             ctx.join()
             dist.all_gather_into_tensor(gathered, results)
 

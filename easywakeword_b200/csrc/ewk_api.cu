@@ -185,7 +185,6 @@ void ewk_ctx::release() {
     if (d_wait_flag) { cudaFree(d_wait_flag); d_wait_flag = nullptr; }
     if (pub_stream) { cudaStreamSynchronize(pub_stream); cudaStreamDestroy(pub_stream); pub_stream = nullptr; }
     if (ev_k3) { cudaEventDestroy(ev_k3); ev_k3 = nullptr; }
-    if (ev_snap) { cudaEventDestroy(ev_snap); ev_snap = nullptr; }
     for (int i = 0; i < 2; i++) if (ev_pub[i]) { cudaEventDestroy(ev_pub[i]); ev_pub[i] = nullptr; }
     if (d_pub_snap) { cudaFree(d_pub_snap); d_pub_snap = nullptr; }
     if (d_tables) cudaFree(d_tables);
@@ -940,10 +939,8 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         B.pub_seq = (unsigned long long)ctx->publish_seq;
         B.pub_parity = (int)((ctx->publish_seq - 1) & 1);
     }
-    if (ctx->snap_pending) {                              // the previous call's records must be snapshotted before K2 rewrites them
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_snap, 0));
-        ctx->snap_pending = false;
-    }
+    if (B.n_pub > 0 && ctx->ev_pub_valid[B.pub_parity])   // K2 rewrites this parity's copy: its sender (two calls ago) is long done
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_pub[B.pub_parity], 0));
     cudaEvent_t pe = ctx->prof_begin(1);
     for (int done = 0; done < n_ticks; done += GATE_MAX_TICKS) {
         const int nt = std::min(GATE_MAX_TICKS, n_ticks - done);
@@ -968,8 +965,6 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         ks = ctx->match_stream;
     }
     ctx->last_match_stream = ks;
-    if (B.n_pub > 0 && ctx->ev_pub_valid[B.pub_parity])
-        CK(cudaStreamWaitEvent(ks, ctx->ev_pub[B.pub_parity], 0));       // this parity's snapshot was sent two calls ago: long done
     pe = ctx->prof_begin(2, ks);
     if (ctx->k3_frames) {
         auto k3f = ctx->cfg.preemphasis != 0.f ? segment_frames_kernel<true> : segment_frames_kernel<false>;
@@ -989,9 +984,6 @@ static int tick_impl(ewk_ctx* ctx, int n_ticks, uint8_t* silent, uint8_t* state,
         // the sender: off everybody's critical path on its own stream, behind K3's snapshot of the records
         CK(cudaEventRecord(ctx->ev_k3, ks));
         CK(cudaStreamWaitEvent(ctx->pub_stream, ctx->ev_k3, 0));
-        snapshot_records_kernel<<<std::min(32, (B.n_streams + 255) / 256), 256, 0, ctx->pub_stream>>>(B);
-        CK(cudaEventRecord(ctx->ev_snap, ctx->pub_stream));                 // the next gate rewrites `results`: it waits for this
-        ctx->snap_pending = true;
         cudaEvent_t pp = ctx->prof_begin(6, ctx->pub_stream);
         publish_records_kernel<<<B.n_pub, 256, 0, ctx->pub_stream>>>(B);
         ctx->prof_end(pp, 6, ctx->pub_stream);
@@ -1380,7 +1372,6 @@ extern "C" int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bas
     if (n_bases && !ctx->pub_stream) {
         CK(cudaStreamCreateWithFlags(&ctx->pub_stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ctx->ev_k3, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ctx->ev_snap, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&ctx->ev_pub[i], cudaEventDisableTiming));
         CK(cudaMalloc(&ctx->d_pub_snap, sizeof(StreamResult) * 2 * (size_t)B.n_streams));
     }

@@ -53,8 +53,7 @@ struct ewk_ctx {
     long long publish_seq = 0;               // ewk_tick calls since ewk_set_results_peers (peer publication); parity = (seq - 1) & 1
     int* d_wait_flag = nullptr;              // set by peer_wait_kernel when it gave up
     cudaStream_t pub_stream = nullptr;       // publish_records_kernel: the call's records -> every destination, then the signal
-    cudaEvent_t ev_k3 = nullptr, ev_snap = nullptr, ev_pub[2] = {nullptr, nullptr};
-    bool snap_pending = false;
+    cudaEvent_t ev_k3 = nullptr, ev_pub[2] = {nullptr, nullptr};
     bool ev_pub_valid[2] = {false, false};
     void* d_pub_snap = nullptr;              // StreamResult [2][n_streams]: K3's snapshots, one per parity
     cudaStream_t last_match_stream = nullptr;   // where the latest ewk_tick launched K3

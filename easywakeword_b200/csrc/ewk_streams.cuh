@@ -96,11 +96,12 @@ struct BankView {
     double* block_ss;       // [n_streams][NB]: sum of squares of absolute block b = a / 1600 at b % NB (written by K1)
     float* lm_ws;           // K3 log-mel workspace: [segment_queue CTAs][SEG_SMEM_FRAMES][LM_ROW]
     int n_streams, R, P, fmt, chunk_cap, max_events, NB;
-    // peer publication (ewk_set_results_peers): behind K3 of a tick call, on a side stream, one small kernel snapshots
-    // `results` into pub_snap[pub_parity] (local: the next gate may rewrite `results` as soon as that is done) and a second
-    // one copies the snapshot to pub[p] + pub_parity * pub_stride + pub_off for each destination p — local or NVLink
-    // peer-mapped memory — and releases the call's sequence number into every destination's signal row: a put-with-signal
-    // that is on nobody's critical path (the next push depends on nothing of it, the next gate on the snapshot only).
+    // peer publication (ewk_set_results_peers): K2 and K3 store every record they write into `results` also into the
+    // call's local copy pub_snap[pub_parity] (K2 writes every stream's record in every call, so the copy is complete when
+    // K3 ends); behind K3, on a side stream, a small kernel sends that copy to pub[p] + pub_parity * pub_stride + pub_off
+    // for each destination p — local or NVLink peer-mapped memory — and releases the call's sequence number into every
+    // destination's signal row: a put-with-signal that is on nobody's critical path (the next push and the next gate
+    // depend on nothing of it; the call after next, which reuses the copy, finds the sender long done).
     StreamResult* pub[MAX_PUB];
     int n_pub, pub_parity;
     long long pub_stride, pub_off;
@@ -115,13 +116,6 @@ struct BankView {
 // plain (weak) 8-byte stores — remote destinations travel over NVLink as posted writes that pipeline behind each other —
 // then every thread orders its stores at system scope and thread 0 releases the call's sequence number into slot
 // `pub_slot` of the destination's signal row: whoever reads that number (ld.acquire.sys) holds all records of the call.
-__global__ void __launch_bounds__(256)
-snapshot_records_kernel(BankView B) {
-    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(B.results);
-    unsigned long long* dst = reinterpret_cast<unsigned long long*>(B.pub_snap + (size_t)B.pub_parity * B.n_streams);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B.n_streams; i += gridDim.x * blockDim.x) dst[i] = __ldcg(src + i);
-}
-
 __global__ void __launch_bounds__(256)
 publish_records_kernel(BankView B) {
     const int p = blockIdx.x;
@@ -956,6 +950,7 @@ tick_gate_kernel(BankView B, int n_ticks, TraceView tr, int trace_stride, int tr
         r.flags = (r.flags & 1u) | (st.last_silent ? 2u : 0u) | ((unsigned)st.state << 2) | evflag |
                   ((unsigned)st.n_events << 8);
         store_result(B.results + s, r);
+        if (B.n_pub) store_result(B.pub_snap + (size_t)B.pub_parity * B.n_streams + s, r);   // the call's copy for the sender
     }
 }
 
@@ -1067,6 +1062,7 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
                 res.score = best;
                 res.flags = (res.flags & ~1u) | (unsigned)ok;
                 store_result(B.results + e.stream, res);
+                if (B.n_pub) store_result(B.pub_snap + (size_t)B.pub_parity * B.n_streams + e.stream, res);
             }
         }
         r = next_s;
@@ -1101,6 +1097,7 @@ struct FqView {                                // what the epilogue needs of the
     const StreamParams* prm;
     const StreamState* st;
     StreamResult* results;
+    StreamResult* pub_snap;                    // this call's snapshot for the publication sender (null: publication off)
     int P, fmt;
 };
 
@@ -1246,6 +1243,7 @@ __device__ __noinline__ void fq_finish(const FqView B, int idx, const FrameTable
             res.score = best;
             res.flags = (res.flags & ~1u) | (unsigned)ok;
             store_result(B.results + e.stream, res);
+            if (B.pub_snap) store_result(B.pub_snap + e.stream, res);
         }
     }
     __syncwarp();
@@ -1278,7 +1276,8 @@ segment_frames_kernel(const DeviceTables* __restrict__ T, BankView B, const Temp
                 old = __shfl_sync(FULL, old, 0);
                 if (old + done_cnt == done_F) {                    // this warp delivered the candidate's last frame: it scores it
                     __threadfence();
-                    fq_finish<PRE>(FqView{B.ring, B.events, B.frow, B.prm, B.st, B.results, B.P, B.fmt}, done_ev, ft, scr, feat, tmpl,
+                    fq_finish<PRE>(FqView{B.ring, B.events, B.frow, B.prm, B.st, B.results,
+                                          B.n_pub ? B.pub_snap + (size_t)B.pub_parity * B.n_streams : nullptr, B.P, B.fmt}, done_ev, ft, scr, feat, tmpl,
                                    n_tmpl_slots);
                 }
                 done_cnt = 0;
