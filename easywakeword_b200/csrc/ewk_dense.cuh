@@ -411,7 +411,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
         // ================================================================ phase B: window max / min and un-floored window sums
         if (tid == 0) ctl[0] = 0;
         const int n_b0 = NT * n_half * B0_PARTS, n_b1 = NT * n_half * n_mfcc;
-        for (int job = next_task(ctl + 1, lane); job < n_b0 + n_b1; job = next_task(ctl + 1, lane)) {
+        for (int job = warp; job < n_b0 + n_b1; job += nwarps) {                      // uniform tasks: a static share
             if (job < n_b0) {
                 // ---- B0: partial max / min over a quarter of the window's frames, lanes = hops
                 const int p = job % B0_PARTS, kh = job / B0_PARTS, hh = kh % n_half, k = kh / n_half;
@@ -456,7 +456,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
         __syncthreads();
 
         // ================================================================ phase S: floors, scores of un-floored windows
-        for (int job = next_task(ctl + 2, lane); job < NT * n_half; job = next_task(ctl + 2, lane)) {
+        for (int job = warp; job < NT * n_half; job += nwarps) {
             const int hh = job % n_half, k = job / n_half;
             const DenseTmplDev& tp = A.t[k];
             const int hl = 32 * hh + lane;
@@ -613,7 +613,7 @@ dense_score_kernel(const DeviceTables* __restrict__ T, BankView B, const Templat
             }
             __syncthreads();
             // ---- E: scores of the floored windows (both kinds)
-            for (int job = next_task(ctl + 6, lane); job < NT * n_half; job = next_task(ctl + 6, lane)) {
+            for (int job = warp; job < NT * n_half; job += nwarps) {
                 const int hh = job % n_half, k = job / n_half;
                 const int hl = 32 * hh + lane;
                 if (hl >= nh || WAY[k * DH + hl] < 0) continue;
