@@ -1,26 +1,29 @@
 """bench.py — audio-seconds per wall-second of the level-1/level-2 hot path at 4096 streams per B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--only sweep|config3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
 A "step" pushes 1.0 s of new 16 kHz int16 audio into each of the 4096 device rings of a rank and runs
-the 10 ticks it covers: K1 ring_push (or direct H2D into the rings), K2 tick_gate (adaptive silence
-threshold, is_silent, timing state machine), K3 segment_queue (fused MFCC + template match on every
-candidate the state machine cut).  That is the reference's WakeWord loop (wakeword.py:454-517,
-1036-1157) for 4096 rooms.  Streams shard across ranks (4096 per GPU, weak scaling); the only
-exchange is the delivery of the 8-byte per-stream result records to every rank: by peer stores from K2/K3 over NVLink
-with a completion signal (--gather peer, the default when symmetric memory is available) or by one NCCL all-gather per
-step (--gather nccl).
+the 10 ticks it covers: K1 ring_push, K2 tick_gate (adaptive silence threshold, is_silent, timing state machine),
+K3 segment_queue (fused MFCC + template match on every candidate the state machine cut).  That is the reference's
+WakeWord loop (wakeword.py:454-517, 1036-1157) for 4096 rooms.  Streams shard across ranks (4096 per GPU, weak
+scaling); the only exchange is the delivery of the 8-byte per-stream result records to every rank: a put-with-signal
+by a sender kernel behind K3 over NVLink (--gather peer, the default when symmetric memory is available) or one NCCL
+all-gather per step (--gather nccl).
 
-Printed JSON (one line, rank 0): `value` = whole-job audio-s/s with inputs resident in HBM;
-`e2e` = the same through the public API with host (pinned) PCM, H2D copies and the event read-back
-inside the timed region; `roofline` for the dominant kernel from CUDA-event timings taken inside
-this run; `cpu_baseline` = the oracle port timed on this box's cores (N=1 only), with a best-effort C + OpenMP
-statement of the same semantics beside it (`best_effort_c`); `e2e_g711` = the end-to-end step fed with G.711 codes;
-`dense` = the per-hop scoring mode (K4).
-`--impl reference` times the reference's CPU algorithm (oracle port, reference-exact statement
-order; librosa itself is not installable offline) on all host cores on the same workload.
+Printed JSON (one line, rank 0).  W warm-up steps, then --repeats (5) blocks of exactly K steps, each bracketed by
+barrier + synchronize and timed with CUDA events on the launching stream (max over ranks): the MEDIAN block is reported
+and every block is listed.  `value` = whole-job audio-s/s with inputs resident in HBM; `e2e` = the same through the
+public API with host (pinned) PCM, H2D copies and the event read-back inside the timed region; `roofline` for the
+dominant kernel from CUDA-event timings taken inside this run; `cpu_baseline` = the reference's own classes (staged
+under oracle/_ref by oracle/stage_ref.py; the oracle port when absent) on this box's cores, one single-threaded
+process per core (N=1 only), with a best-effort C + OpenMP statement of the same semantics beside it
+(`best_effort_c`, `e2e_vs_best_effort_c`); `e2e_g711` = the end-to-end step fed with G.711 codes; secondary legs:
+`dense` (per-hop scoring, K4, 100 hops per step), `sweep` (BASELINE configs[4]: 1024 streams x 600 s, T = 4 and
+T = 1 templates, 10 s chunks) and `config3` (BASELINE configs[3]: 8192 streams per GPU, NCCL gather).
+`--impl reference` times the reference's CPU implementation on all host cores on a bounded sample of the same
+workload (same `config`).
 """
 from __future__ import annotations
 
@@ -373,13 +376,23 @@ def sweep_leg(torch, dist, dev, stream, local_rank, rank, world, word, hbm_peak,
     out_pin = _lib.PinnedArray((n, hops, T), np.float32)
     pushed = [0]
 
-    def chunk_step(where, t_first, t_count, to_host):
+    scored = [0]
+
+    def push_chunk(where):
         j = pushed[0] % n_pool
         src = pool if where == _lib.DEVICE else host
-        hop0 = pushed[0] * hops + 1
         bank.push((src.data_ptr() + j * n * chunk * 2, n, chunk, chunk), where=where)
         pushed[0] += 1
+
+    def chunk_step(where, t_first, t_count, to_host):
+        """push + score one chunk.  With host PCM the NEXT chunk's push is issued before this chunk is scored, so that its
+        H2D copy runs beside K4 (every chunk still pays its own copy and its own read-back inside the timed region)."""
+        if pushed[0] == scored[0]:
+            push_chunk(where)
+        hop0 = scored[0] * hops + 1
+        scored[0] += 1
         if to_host:
+            push_chunk(where)
             ctx._ck(ctx.lib.ewk_dense_scores(ctx.h, hop0, hops, t_first, t_count, out_pin.ptr, _lib.HOST))
         else:
             ctx.dense_scores(hop0, hops, t_first, t_count, out_device_ptr=out_dev.data_ptr())
@@ -784,9 +797,11 @@ def run_ours(args):
                 raise SystemExit("bench.py: peer-published records differ from the NCCL all-gather of the same step")
             gather_info.update({"mode": ("peer stores by K2/K3 over NVLink (symmetric memory) + one barrier per step behind K3"
                                          if args.gather == "peer-barrier" else
-                                         "put-with-signal: K2/K3 store the records, K3's last CTA releases the step's sequence "
-                                         "number, into every rank's copy over NVLink (symmetric memory); no collective, no "
-                                         "per-step barrier; the timed region ends with a device-side wait for every rank's last step"),
+                                         "put-with-signal: K2/K3 write the call's local copy of the records, a sender kernel on a "
+                                         "side stream behind K3 stores it into every rank's copy over NVLink (symmetric memory) and "
+                                         "releases the step's sequence number; no collective, no per-step barrier, nothing of it on "
+                                         "the next step's critical path; the timed region ends with a device-side wait for every "
+                                         "rank's last step"),
                                 "symm_barrier_us": peer_us, "peer_copy_equals_nccl_all_gather": True})
 
     # per-kernel device time (CUDA events on the launching stream), same workload, separate loop; sequential order
@@ -947,9 +962,9 @@ def run_ours(args):
                                       "cp.async.bulk form); the timed region ends after the last K3 (ewk_join); per-kernel "
                                       "times are taken in sequential order, each kernel alone")
                           if overlap else "off: K1, K2, K3 in sequence on one stream",
-                          "exchange": (("8 B/stream result records + completion signal stored by K2/K3 into every rank's copy "
-                                        "over NVLink" + (", one barrier per step" if args.gather == "peer-barrier" else
-                                                         " (put-with-signal, no collective)") if exchange is not None else
+                          "exchange": (("8 B/stream result records + completion signal put into every rank's copy over NVLink by a "
+                                        "sender kernel behind K3 (side stream)" + (", one barrier per step" if args.gather == "peer-barrier" else
+                                                                                   " (put-with-signal, no collective)") if exchange is not None else
                                         "all_gather of 8 B/stream results per step")) if world > 1 else None},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * STEP_SAMPLES * esz,

@@ -1199,9 +1199,15 @@ extern "C" int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int tmpl
     int rc = need_streams(ctx, "ewk_dense_scores");
     if (rc) return rc;
     cudaSetDevice(ctx->device);
-    rc = ctx->flush_pending();
-    if (rc) return rc;
     BankView& B = ctx->bank;
+    if (ctx->pending.valid) {
+        // a host push whose copy is still in flight lands now only if these hops reach into its samples: otherwise the copy
+        // of the NEXT block keeps overlapping this call's kernel (offline sweeps: push block j + 1, then score block j)
+        bool need = false;
+        for (int s = ctx->pending.stream0; !need && s < ctx->pending.stream0 + ctx->pending.n_streams; s++)
+            need = ctx->h_written[s] < 160LL * (hop0 + n_hops - 1);
+        if (need) { rc = ctx->flush_pending(); if (rc) return rc; }
+    }
     if (!out || hop0 < 0 || n_hops < 1 || tmpl_count < 1 || tmpl_count > DENSE_MAX_T || tmpl_first < 0 ||
         tmpl_first + tmpl_count > ctx->cfg.max_templates) {
         ctx->fail("ewk_dense_scores: bad arguments (hop0=%lld n_hops=%d templates [%d, %d), at most %d per call)", (long long)hop0,

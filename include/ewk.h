@@ -237,7 +237,9 @@ int ewk_resample(ewk_ctx* ctx, const void* in, int pcm_format, int where_in, int
  * i.e. the latest template-length window that starts on the hop grid and is complete at hop h
  * (window-local zero-pad centring and top_db floor).  out[(stream * n_hops + (h - hop0)) * template_count
  * + k], NaN where the window starts before the stream.  The audio must have been pushed and still be in
- * the ring (EWK_ERR_STATE otherwise).  Templates must have 640 <= L_k <= 35680 samples; template_count <= 4.
+ * the ring (EWK_ERR_STATE otherwise).  Templates must have 640 <= L_k <= 48000 samples (the reference's own 3.0 s
+ * segment cap, wakeword.py:1114-1118); template_count <= 8 per call.  Left-edge frames are shared by all templates, right-
+ * edge frames by templates with the same padding to the hop grid; every call may continue where the previous one stopped.
  * `where` tells whether `out` is host or device memory. */
 int ewk_dense_scores(ewk_ctx* ctx, int64_t hop0, int n_hops, int template_first, int template_count,
                      float* out, int where);

@@ -17,6 +17,10 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "sm__cycles_active.avg", "sm__cycles_elapsed.avg", "sm__inst_executed.sum",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
