@@ -453,12 +453,19 @@ def sweep_leg(torch, dist, dev, stream, local_rank, rank, world, word, hbm_peak,
                 "what": "pinned host PCM -> H2D -> K1 -> K4 -> scores copied back into pinned host memory, every chunk"},
         "algorithmic_bytes_per_chunk": pcm_bytes + n * hops * T * 4,
         "hbm_frac": (pcm_bytes + n * hops * T * 4) / (k4_ms * 1e-3) / 1e9 / hbm_peak,
+        "traffic": _traffic().get("dense_score_sweep_t4") if T == 4 else None,
         "geometry": "K4 chooses hops per sub-chunk / threads per CTA / CTAs per SM from shared memory (csrc/ewk_api.cu dense_plan)",
     }
     bank.close()
     pin.free()
     out_pin.free()
     return leg
+
+
+def _traffic():
+    """dram read+write bytes per launch from the committed `ncu --set full` captures (profiles/traffic.json)."""
+    tp = os.path.join(REPO, "profiles", "traffic.json")
+    return json.load(open(tp)) if os.path.exists(tp) else {}
 
 
 def config3_leg(torch, dist, dev, stream, local_rank, rank, world, word, pool_dev, K, W, overlap):
@@ -898,10 +905,7 @@ def run_ours(args):
             return {"avg_launch_ms": ms, "algorithmic_bytes": alg_bytes.get(name), "achieved_gbs": gbs, "frac": gbs / hbm_peak,
                     "traffic": traffic.get(name)}
 
-        traffic = {}
-        tp = os.path.join(REPO, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp))      # dram read+write bytes per launch from the committed ncu --set full captures
+        traffic = _traffic()
         avg_ms = kern[dom]["ms"] / kern[dom]["launches"]
         achieved = alg_bytes.get(dom, 0.0) / (avg_ms * 1e-3) / 1e9
         frames_per_step = ev_per_step * 111.0          # 1 + 17600 // 160 frames per candidate
@@ -910,7 +914,7 @@ def run_ours(args):
                     "avg_launch_ms": avg_ms, "share_of_kernel_time": share,
                     "note": "the dominant kernel (fused MFCC+match on candidate segments) does ~45 flop per PCM byte "
                             "(DESIGN.md §4) and is bound on the SM, not on HBM: ncu shows the shared-memory data pipe "
-                            "(l1tex lsu wavefronts) at ~78 % of peak while an SM is busy (profiles/README.md); its HBM "
+                            "(l1tex lsu wavefronts) at ~73 % of peak while an SM is busy (profiles/README.md); its HBM "
                             "fraction is small by construction.  `compute` gives its FP32 rate and `hbm_bound_kernel` "
                             "the roofline of the HBM-bound kernel of the step (K1 fused push+sums)",
                     "compute": {"frames_per_launch": frames_per_step, "flop_per_frame": 15300,
@@ -987,6 +991,7 @@ def run_ours(args):
                       "ms_per_step": ms_dense / dense_steps,
                       "kernel_ms": prof_dense["dense_score"]["ms"] / max(1, prof_dense["dense_score"]["launches"]),
                       "windows_per_s": n * 100 * world * dense_steps / (ms_dense * 1e-3),
+                      "traffic": traffic.get("dense_score"),
                       "hbm_frac": (n * STEP_SAMPLES * esz + n * 400) * dense_steps / (ms_dense * 1e-3) / 1e9 / hbm_peak,
                       "cpu_baseline": dense_cpu},
             "sweep": sweep,
