@@ -575,6 +575,15 @@ int ewk_ctx::init_streams() {
     CK(cudaMalloc(&bank.events, sizeof(EventRec) * (size_t)bank.max_events));
     CK(cudaMalloc(&bank.ev_count, sizeof(int) * 8));
     CK(cudaMemsetAsync(bank.ev_count, 0, sizeof(int) * 8, stream));
+    CK(cudaMalloc(&bank.bk_count, sizeof(int) * SEG_NB));
+    CK(cudaMemsetAsync(bank.bk_count, 0, sizeof(int) * SEG_NB, stream));
+    CK(cudaMalloc(&bank.bk_list, sizeof(int) * (size_t)SEG_NB * bank.max_events));
+#ifdef EWK_K3_TRACE
+    if (getenv("EWK_K3_TRACE")) {
+        CK(cudaMalloc(&bank.k3_trace, sizeof(long long) * K3_TRACE_WORDS * (size_t)queue_grid()));
+        CK(cudaMemsetAsync(bank.k3_trace, 0, sizeof(long long) * K3_TRACE_WORDS * (size_t)queue_grid(), stream));
+    }
+#endif
 
     bank.NB = bank.P / TICK;
     CK(cudaMalloc(&bank.block_ss, sizeof(double) * (size_t)n * std::max(1, bank.NB)));
@@ -627,9 +636,18 @@ int ewk_ctx::init_streams() {
 }
 
 void ewk_ctx::release_streams() {
+#ifdef EWK_K3_TRACE
+    if (bank.k3_trace) {                          // the last launch's timeline -> $EWK_K3_TRACE (raw int64 [CTAs][K3_TRACE_WORDS])
+        cudaDeviceSynchronize();
+        std::vector<long long> h((size_t)K3_TRACE_WORDS * queue_grid());
+        cudaMemcpy(h.data(), bank.k3_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(getenv("EWK_K3_TRACE"), "wb")) { fwrite(h.data(), sizeof(long long), h.size(), f); fclose(f); }
+        cudaFree(bank.k3_trace);
+    }
+#endif
     for (void* p : {bank.ring, (void*)bank.st, (void*)bank.prm, (void*)bank.chunk_ms, (void*)bank.events,
                     (void*)bank.ev_count, (void*)bank.block_ss, (void*)bank.lm_ws, own_results, (void*)bank.frow,
-                    (void*)bank.frame_ev, (void*)bank.ev_done})
+                    (void*)bank.frame_ev, (void*)bank.ev_done, (void*)bank.bk_count, (void*)bank.bk_list})
         if (p) cudaFree(p);
     bank = BankView{};
     own_results = nullptr;

@@ -78,6 +78,7 @@ struct StreamResult {       // dense per-stream record (what multi-GPU runs gath
 };
 
 constexpr int MAX_PUB = 16;  // destinations of a peer publication (GPUs of one NVLink domain)
+constexpr int SEG_NB = 24;   // length classes of queued candidates: ceil(frames / SEG_WARPS) <= ceil(301 / 14) = 22
 constexpr int FROW = 24;     // floats per frame row of the frame-parallel K3: mfcc[20], log-mel min, log-mel max, pad (96 B)
 
 struct BankView {
@@ -95,6 +96,9 @@ struct BankView {
     StreamResult* results;
     double* block_ss;       // [n_streams][NB]: sum of squares of absolute block b = a / 1600 at b % NB (written by K1)
     float* lm_ws;           // K3 log-mel workspace: [segment_queue CTAs][SEG_SMEM_FRAMES][LM_ROW]
+    int* bk_count;          // [SEG_NB] candidates queued since the last K3 launch, by length class (rounds of SEG_WARPS frames)
+    int* bk_list;           // [SEG_NB][max_events] their event indices: K3 takes the longest class first
+    long long* k3_trace;    // measuring builds (-DEWK_K3_TRACE) with EWK_K3_TRACE=<file> set: per-CTA timeline of the last K3 launch
     int n_streams, R, P, fmt, chunk_cap, max_events, NB;
     // peer publication (ewk_set_results_peers): K2 and K3 store every record they write into `results` also into the
     // call's local copy pub_snap[pub_parity] (K2 writes every stream's record in every call, so the copy is complete when
@@ -673,6 +677,11 @@ __device__ __forceinline__ unsigned gate_state_step(const BankView& B, int s, St
                                 B.ev_done[idx] = 0;
                                 for (int t = 0; t < nf; t++) B.frame_ev[f0 + t] = idx;
                             }
+                            {   // length class for K3's longest-first order (no tail of one long segment started last)
+                                const int b = min(SEG_NB - 1, (nf + SEG_WARPS - 1) / SEG_WARPS);
+                                const int q = atomicAdd(B.bk_count + b, 1);
+                                if (q < B.max_events) B.bk_list[(size_t)b * B.max_events + q] = idx;
+                            }
                             st.n_events++;
                             st.last_ev = idx;
                             evflag = 16u;
@@ -1004,10 +1013,20 @@ segment_prepare_kernel(BankView B, const PrepDesc* __restrict__ d, float* __rest
 // ------------------------------------------------------------------------------------ K3 (queue form)
 // Persistent CTAs drain the segments K2 queued: PCM straight from the stream's device ring ->
 // fused MFCC + template match -> score written back into the event record and the per-stream result.
-// Scheduling: segments differ in length (0.3 .. 3 s) and there are only a few per CTA, so CTAs take them
-// dynamically — first index = watermark + blockIdx.x, then an atomic counter (ev_count[2]) — which bounds the
-// tail by one segment instead of a static share.  Events below the watermark ev_count[3] were scored by earlier
-// launches and are not visited again; the last CTA to finish advances it and zeroes the counters.
+// Scheduling: segments differ in length (0.3 .. 3 s) and there are only a few per CTA (555 over 296 in the bench
+// workload), so (1) CTAs take them dynamically — first task = blockIdx.x, then an atomic counter (ev_count[2]) — and
+// (2) in LONGEST-FIRST order: K2 files every candidate it queues under its length class (rounds of SEG_WARPS frames,
+// bk_count / bk_list), and task t is the t-th candidate counted from the longest class down.  The kernel then ends
+// with its shortest segments instead of whatever came last (list scheduling, longest processing time first).
+// The lists hold the candidates queued since the previous K3 launch; the last CTA to finish zeroes the counters and
+// advances the scored watermark ev_count[3].
+
+#ifdef EWK_K3_TRACE
+// timeline of one launch (a measuring build only: -DEWK_K3_TRACE, profiles/tools/k3_timeline.py): per CTA
+// [0] SM id, [1] start, [2] tables loaded, [3] exit, [4] segments taken; then per segment start, end, samples, event index
+constexpr int K3_TRACE_SEGS = 14, K3_TRACE_WORDS = 8 + 4 * K3_TRACE_SEGS;
+__device__ __forceinline__ long long k3_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 
 template <bool PRE>
 __global__ void __launch_bounds__(512, 2)
@@ -1016,23 +1035,43 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
     const SegSmem m = seg_carve(smem, SEG_SMEM_FRAMES);
     __shared__ float sc_s[EWK_MAX_TEMPLATES];
     __shared__ int next_s;
+    __shared__ int cum_s[SEG_NB + 1];
     const int tid = threadIdx.x;
     const int n = min(B.ev_count[0], B.max_events);
-    const int lo = min(B.ev_count[3], n);
-    int r = lo + blockIdx.x;
-    if (r < n) seg_prologue(T, m);                                       // tables; ends with __syncthreads()
+    // task t of this launch = the t-th candidate in longest-class-first order (K2 filed them by class)
+    auto task_event = [&](int t) -> int {
+        if (t >= cum_s[SEG_NB]) return -1;
+        int j = 0;
+        while (t >= cum_s[j + 1]) j++;
+        return B.bk_list[(size_t)(SEG_NB - 1 - j) * B.max_events + (t - cum_s[j])];
+    };
+#ifdef EWK_K3_TRACE
+    long long* trc = B.k3_trace ? B.k3_trace + (size_t)blockIdx.x * K3_TRACE_WORDS : nullptr;
+    int trc_n = 0;
+    if (trc && tid == 0) { unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); trc[0] = sm; trc[1] = k3_now(); }
+#endif
+    if (tid == 0) {
+        int c = 0;
+        for (int j = 0; j < SEG_NB; j++) { cum_s[j] = c; c += min(B.bk_count[SEG_NB - 1 - j], B.max_events); }
+        cum_s[SEG_NB] = c;
+        next_s = task_event(blockIdx.x);
+    }
+    __syncthreads();
+    int r = next_s;
+    if (r >= 0) seg_prologue(T, m);                                      // tables; ends with __syncthreads()
     const size_t esz = B.fmt == 1 ? 2 : 4;
     float* lm = B.lm_ws ? B.lm_ws + (size_t)blockIdx.x * SEG_SMEM_FRAMES * LM_ROW : nullptr;
-    while (r < n) {
+#ifdef EWK_K3_TRACE
+    if (trc && tid == 0) trc[2] = k3_now();
+#endif
+    while (r >= 0) {
         const int i = r;
         const EventRec e = B.events[i];
-        if (tid == 0) next_s = lo + gridDim.x + atomicAdd(B.ev_count + 2, 1);
-        if (e.kind != EV_PENDING) {                                     // uniform across the CTA
-            __syncthreads();
-            r = next_s;
-            __syncthreads();
-            continue;
-        }
+#ifdef EWK_K3_TRACE
+        if (trc && tid == 0 && trc_n < K3_TRACE_SEGS) { trc[8 + 4 * trc_n] = k3_now(); trc[8 + 4 * trc_n + 2] = e.seg_len; trc[8 + 4 * trc_n + 3] = i; }
+#endif
+        int t_next = 0;
+        if (tid == 0) t_next = (int)gridDim.x + atomicAdd(B.ev_count + 2, 1);     // its latency hides behind the segment
         SegDesc sd;
         sd.base = (const char*)B.ring + (size_t)e.stream * B.P * esz;
         sd.start = e.seg_start % B.P; sd.ring = B.P; sd.len = e.seg_len; sd.fmt = B.fmt;
@@ -1047,6 +1086,7 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
         }
         __syncthreads();
         if (tid == 0) {
+            const int nx = task_event(t_next);                           // the list load overlaps the record updates below
             // best score over the stream's template set (NaN never wins: NaN >= x is false, as in wakeword.py:638-639)
             float best = __int_as_float(0x7fc00000);
             int arg = nt > 0 ? t0 : -1;
@@ -1064,16 +1104,24 @@ segment_queue_kernel(const DeviceTables* __restrict__ T, BankView B, const Templ
                 store_result(B.results + e.stream, res);
                 if (B.n_pub) store_result(B.pub_snap + (size_t)B.pub_parity * B.n_streams + e.stream, res);
             }
+            next_s = nx;
         }
-        r = next_s;
         __syncthreads();
+#ifdef EWK_K3_TRACE
+        if (trc && tid == 0 && trc_n < K3_TRACE_SEGS) { trc[8 + 4 * trc_n + 1] = k3_now(); trc_n++; }
+#endif
+        r = next_s;
     }
+#ifdef EWK_K3_TRACE
+    if (trc && tid == 0) { trc[3] = k3_now(); trc[4] = trc_n; }
+#endif
     if (tid == 0) {
         __threadfence();
         if (atomicAdd(B.ev_count + 4, 1) == (int)gridDim.x - 1) {       // every other CTA has read the counters
             B.ev_count[3] = n;
             B.ev_count[2] = 0;
             B.ev_count[4] = 0;
+            for (int j = 0; j < SEG_NB; j++) B.bk_count[j] = 0;
         }
     }
 }
@@ -1315,6 +1363,7 @@ segment_frames_kernel(const DeviceTables* __restrict__ T, BankView B, const Temp
             B.ev_count[6] = 0;                                           // so it stays small and L2-resident
             B.ev_count[2] = 0;
             B.ev_count[4] = 0;
+            for (int j = 0; j < SEG_NB; j++) B.bk_count[j] = 0;
         }
     }
 }
