@@ -430,6 +430,40 @@ __device__ __forceinline__ void warp_sort_build(const double* ms, double* sorted
 __device__ __forceinline__ void warp_sorted_replace(double*& S, double*& T, int n, double oldv, double newv, int lane) {
     const long long bo = __double_as_longlong(oldv), bn = __double_as_longlong(newv);
     if (bo == bn) return;
+    if (n <= 128) {
+        // in place: the lane keeps its (up to four) elements from the counting pass in registers; the elements between
+        // the old and the new position move by one slot — every lane stores its own element into the neighbouring slot —
+        // and one lane drops the new value into the gap.  No second pass of loads, no second buffer.
+        long long v[4];
+        int lo = 0, ln = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int i = 32 * r + lane;
+            v[r] = i < n ? __double_as_longlong(S[i]) : 0x7fffffffffffffffLL;
+            lo += __popc(__ballot_sync(FULL, v[r] < bo));
+            ln += __popc(__ballot_sync(FULL, v[r] < bn));
+        }
+        const int pos_old = lo;
+        const int pos_new = ln - (bo < bn ? 1 : 0);    // index in the array with `oldv` removed
+        __syncwarp();
+        if (pos_new > pos_old) {                       // (pos_old, pos_new] move down
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int i = 32 * r + lane;
+                if (i > pos_old && i <= pos_new) S[i - 1] = __longlong_as_double(v[r]);
+            }
+        } else if (pos_new < pos_old) {                // [pos_new, pos_old) move up
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int i = 32 * r + lane;
+                if (i >= pos_new && i < pos_old) S[i + 1] = __longlong_as_double(v[r]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) S[pos_new] = newv;
+        __syncwarp();
+        return;
+    }
     int lo = 0, ln = 0;
     for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + lane;
