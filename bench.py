@@ -28,6 +28,7 @@ workload (same `config`).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -596,11 +597,11 @@ def run_ours(args):
     ctx.set_results_buffer(results.data_ptr())
     overlap = not args.no_overlap
     ctx.set_overlap(overlap)
-    gathered = torch.zeros(world * n, 2, dtype=torch.int32, device=dev) if world > 1 else None
+    gathered = torch.zeros(world * n, 2, dtype=torch.int32, device=dev) if world > 1 and args.gather != "none" else None
     # multi-GPU result exchange: the producing kernels store every record into all ranks' copies over NVLink
     # (peer-mapped symmetric memory) and a step ends with a barrier behind K3; NCCL all-gather otherwise
     exchange, exchange_note = None, None
-    if world > 1 and args.gather != "nccl":
+    if world > 1 and args.gather not in ("nccl", "none"):
         try:
             from easywakeword_b200.dist import PeerResultExchange
             exchange = PeerResultExchange(world * n, world, rank, dev)
@@ -669,6 +670,8 @@ def run_ours(args):
             step(where, True)
         blocks = []
         for _ in range(repeats):
+            gc.collect()
+            gc.disable()            # a collection inside a 3 ms block stalls the enqueueing thread for longer than the queue is deep
             barrier()
             l0 = ctx.launch_count()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -688,6 +691,7 @@ def run_ours(args):
                     exchange.wait(ctx)                              # ... and so does the arrival of every rank's last step
             e1.record(stream)
             barrier()
+            gc.enable()
             ms = e0.elapsed_time(e1)
             br = {"ms_per_step": [ms / steps], "host_enqueue_ms_per_step": [cpu_issue_ms / steps]}
             if world > 1:
@@ -775,8 +779,8 @@ def run_ours(args):
 
     # the exchange on its own ("report gather latency separately"), and a self-check that the
     # peer-published copy equals an NCCL all-gather of the local records
-    gather_info = None
-    if world > 1:
+    gather_info = {"mode": "none (--gather none: a diagnostic, the ranks exchange nothing)"} if world > 1 and gathered is None else None
+    if world > 1 and gathered is not None:
         def per_call_us(fn, reps=50):
             for _ in range(5):
                 fn()
@@ -979,7 +983,8 @@ def run_ours(args):
                           "exchange": (("8 B/stream result records + completion signal put into every rank's copy over NVLink by a "
                                         "sender kernel behind K3 (side stream)" + (", one barrier per step" if args.gather == "peer-barrier" else
                                                                                    " (put-with-signal, no collective)") if exchange is not None else
-                                        "all_gather of 8 B/stream results per step")) if world > 1 else None},
+                                        ("all_gather of 8 B/stream results per step" if gathered is not None else
+                                         "none (--gather none)"))) if world > 1 else None},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * STEP_SAMPLES * esz,
                     "d2h_bytes_per_step": int(8 + ev_per_step * 40), "ms_per_step": ms_e2e / K,
@@ -1065,7 +1070,7 @@ def main():
                     help="streams per GPU (default 4096 = BASELINE configs[2]; 8192 = the per-GPU shard of configs[3], 65536 / 8)")
     ap.add_argument("--pcm", default="int16", choices=["int16", "f32"],
                     help="ring / push sample format (int16: the wire format, default; f32: what PortAudio hands the reference)")
-    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "peer-barrier", "nccl"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "peer-barrier", "nccl", "none"],
                     help="multi-GPU result exchange: peer = K2/K3 store records and a completion signal into every rank's "
                          "copy over NVLink (no collective, no per-step barrier); peer-barrier = same stores, one "
                          "symmetric-memory barrier per step; nccl = all_gather per step; auto = peer when symmetric "

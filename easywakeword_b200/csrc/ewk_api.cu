@@ -1394,7 +1394,11 @@ extern "C" int ewk_set_results_peers(ewk_ctx* ctx, void* const* bases, int n_bas
     if (ctx->pub_stream) CK(cudaStreamSynchronize(ctx->pub_stream));
     ctx->ev_pub_valid[0] = ctx->ev_pub_valid[1] = false;
     if (n_bases && !ctx->pub_stream) {
-        CK(cudaStreamCreateWithFlags(&ctx->pub_stream, cudaStreamNonBlocking));
+        // highest priority: the sender is a handful of CTAs that should start the moment K3 ends, not queue behind the
+        // full grids of the next push
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&ctx->pub_stream, cudaStreamNonBlocking, prio_hi));
         CK(cudaEventCreateWithFlags(&ctx->ev_k3, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&ctx->ev_pub[i], cudaEventDisableTiming));
         CK(cudaMalloc(&ctx->d_pub_snap, sizeof(StreamResult) * 2 * (size_t)B.n_streams));
