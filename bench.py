@@ -538,18 +538,22 @@ def config3_leg(torch, dist, dev, stream, local_rank, rank, world, word, pool_de
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ev = bank.poll()
+    KP = 2 * POOL_SECONDS                                           # whole periods of the feed, as in the main leg's profile pass
     ctx.set_overlap(False)
     ctx.profile(True)
-    for _ in range(K):
+    for _ in range(KP):
         step()
     prof = ctx.profile_read()
     ctx.profile(False)
-    bank.poll()
+    evp = bank.poll()
+    evp = evp[evp["kind"] == _lib.EV_SCORED]
     leg = {"what": f"configs[3]: {n} streams per GPU x {world} GPU(s) = {n * world} streams (65 536 at 8 GPUs), gated level-1+2 path, "
                    "PCM resident in HBM, one NCCL all-gather of the 8-byte result records per step" + ("" if world > 1 else " (N > 1 only)"),
            "streams_per_gpu": n, "streams_total": n * world, "value": n * STEP_SECONDS * world * K / (ms * 1e-3), "unit": UNIT,
            "ms_per_step": ms / K, "level2_events_per_step": int((ev["kind"] == 2).sum()) / K,
-           "kernel_ms_per_step": {k: v["ms"] / K for k, v in prof.items() if v["launches"]},
+           "kernel_ms_per_step": {k: v["ms"] / KP for k, v in prof.items() if v["launches"]},
+           "profile_pass": {"steps": KP, "candidates_per_step": len(evp) / KP,
+                            "candidate_frames_per_step": float((1 + evp["seg_len"] // 160).sum()) / KP},
            "rings_gb_per_gpu": n * (RING_SECONDS * 16000 + int(2 * STEP_SECONDS * 16000) + 3200) * 2 / 1e9}
     bank.close()
     del big
@@ -826,19 +830,28 @@ def run_ours(args):
 
     # per-kernel device time (CUDA events on the launching stream), same workload, separate loop; sequential order
     # (no overlap) so that every kernel is timed alone
+    # The pass covers whole periods of the feed (2 x POOL_SECONDS steps), so that it sees the feed's average step and
+    # two passes see the same steps; the candidates it scored are read back afterwards: K3's algorithmic bytes and
+    # frames are THEIR samples and frames, not an assumed mean.
+    KP = 2 * POOL_SECONDS
     ctx.set_overlap(False)
+    bank.poll()
     ctx.profile(True)
-    for _ in range(K):
+    for _ in range(KP):
         step(_lib.DEVICE, False)
     prof = ctx.profile_read()
     ctx.profile(False)
-    bank.poll()
+    ev_prof = bank.poll()
+    ev_prof = ev_prof[ev_prof["kind"] == _lib.EV_SCORED]
+    prof_cand = len(ev_prof) / KP                                   # candidates per K3 launch
+    prof_samples = float(ev_prof["seg_len"].sum()) / KP             # their PCM samples per launch
+    prof_frames = float((1 + ev_prof["seg_len"] // 160).sum()) / KP  # and frames (1 + len // hop each)
     prof_nopub = None
     if exchange is not None:
-        # what the peer stores cost the kernels: the same loop (same workload) with publication off
+        # what the peer stores cost the kernels: the same loop (the same steps of the feed) with publication off
         ctx.set_results_peers([])
         ctx.profile(True)
-        for _ in range(K):
+        for _ in range(KP):
             step(_lib.DEVICE, False)
         prof_nopub = ctx.profile_read()
         ctx.profile(False)
@@ -904,10 +917,10 @@ def run_ours(args):
         #  ring_push   (K1 fused): step PCM read once + written once into the rings + one 8-byte block sum per tick
         #  tick_gate   (K2): with K1's block sums it reads no PCM: 10 block sums + state in/out per stream;
         #              (host pushes: it reads the step's PCM once itself)
-        #  segment_queue (K3): the PCM of every candidate segment once (mean 17.6 k samples) + its 40-byte event
+        #  segment_queue (K3): the PCM of every candidate segment of the profiled launches once + its 40-byte event
         alg_bytes = {"ring_push": n * (STEP_SAMPLES * esz * 2 + TICKS_PER_STEP * 8),
                      "tick_gate": n * (TICKS_PER_STEP * 8 + 2 * 104 + 72 + 2 * 1600),
-                     "segment_queue": ev_per_step * (17600 * esz + 40)}
+                     "segment_queue": prof_samples * esz + prof_cand * 40}
         share = {k: v["ms"] / tot_ms for k, v in kern.items()}
 
         def kroof(name):
@@ -921,7 +934,7 @@ def run_ours(args):
         traffic = _traffic()
         avg_ms = kern[dom]["ms"] / kern[dom]["launches"]
         achieved = alg_bytes.get(dom, 0.0) / (avg_ms * 1e-3) / 1e9
-        frames_per_step = ev_per_step * 111.0          # 1 + 17600 // 160 frames per candidate
+        frames_per_step = prof_frames
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic.get(dom), "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "share_of_kernel_time": share,
@@ -1012,8 +1025,12 @@ def run_ours(args):
             "sweep": sweep,
             "config3": config3,
             "level2_events_per_step": ev_per_step,
-            "kernel_ms_per_step": {k: v["ms"] / max(1, K) for k, v in kern.items()},
-            "kernel_ms_per_step_without_publication": ({k: v["ms"] / max(1, K) for k, v in prof_nopub.items() if v["launches"]}
+            "profile_pass": {"steps": KP, "candidates_per_step": prof_cand, "candidate_samples_per_step": prof_samples,
+                             "candidate_frames_per_step": prof_frames,
+                             "what": "the per-kernel times and the roofline come from this separate pass: sequential order, whole "
+                                     "periods of the feed, its own candidates counted"},
+            "kernel_ms_per_step": {k: v["ms"] / KP for k, v in kern.items()},
+            "kernel_ms_per_step_without_publication": ({k: v["ms"] / KP for k, v in prof_nopub.items() if v["launches"]}
                                                        if prof_nopub else None),
         }
         print(json.dumps(line), flush=True)
