@@ -79,3 +79,51 @@ def test_result_record_is_the_latest_event(word):
             assert np.abs(mine["score"] - np.array([e["score"] for e in ref])).max() <= 0.01
     finally:
         ctx.close()
+
+
+def test_candidate_overflow_keeps_the_queue_consistent(word):
+    """More candidates than event slots: the ones that found a slot are all scored (none left pending, K3's length-class
+    lists hold exactly them), the rest are counted as dropped, and the next call works on a clean queue."""
+    from easywakeword_b200 import _lib
+    n, cap = 256, 64
+    P = dict(frame_size=1600, pre_speech_silence=0.1, speech_duration_min=0.1, speech_duration_max=0.35,
+             post_speech_silence=0.1, timeout=0.0, similarity_threshold=60.0)
+    xs = np.stack([synth.to_int16(burst_stream(1900 + s, 9.6)) for s in range(n)])
+    ctx = _lib.Context(device=0, n_streams=n, ring_samples=16000, slack_samples=3200 * 17, pcm_format=_lib.PCM_I16,
+                       max_templates=1, max_events=cap)
+    try:
+        ctx.set_template(0, word)
+        ctx.set_stream_params(-1, **P)
+        seen_drop = 0
+        for p in range(0, xs.shape[1] - 32 * 1600 + 1, 32 * 1600):
+            ctx.push(np.ascontiguousarray(xs[:, p:p + 32 * 1600]))
+            ctx.tick(32)
+            ev = ctx.poll()
+            assert len(ev) <= cap
+            assert (ev["kind"] == 2).all(), np.unique(ev["kind"])          # nothing left pending, no timeouts configured
+            assert np.isfinite(ev["score"]).all() and (ev["seg_len"] > 0).all()
+            seen_drop += ctx.dropped
+        assert seen_drop > 0
+        # with room for everything the same audio gives the same scores for the events that fit before
+        ctx2 = _lib.Context(device=0, n_streams=n, ring_samples=16000, slack_samples=3200 * 17, pcm_format=_lib.PCM_I16,
+                            max_templates=1, max_events=1 << 15)
+        try:
+            ctx2.set_template(0, word)
+            ctx2.set_stream_params(-1, **P)
+            ctx.close()
+            ctx = _lib.Context(device=0, n_streams=n, ring_samples=16000, slack_samples=3200 * 17, pcm_format=_lib.PCM_I16,
+                               max_templates=1, max_events=cap)
+            ctx.set_template(0, word)
+            ctx.set_stream_params(-1, **P)
+            blk = np.ascontiguousarray(xs[:, :32 * 1600])
+            ctx.push(blk); ctx.tick(32)
+            ctx2.push(blk); ctx2.tick(32)
+            few, full = ctx.poll(), ctx2.poll()
+            assert len(full) > cap and len(few) == cap
+            key = {(int(e["stream"]), int(e["tick"])): float(e["score"]) for e in full}
+            for e in few:
+                assert key[(int(e["stream"]), int(e["tick"]))] == float(e["score"])
+        finally:
+            ctx2.close()
+    finally:
+        ctx.close()
